@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+EXAMPLE = os.path.join(GOLDEN, "example")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def example_dir():
+    return EXAMPLE
+
+
+@pytest.fixture(scope="session")
+def expected():
+    import json
+
+    with open(os.path.join(EXAMPLE, "expected.json")) as f:
+        return json.load(f)
