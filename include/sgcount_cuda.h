@@ -1,0 +1,170 @@
+/*
+ * sgcount_cuda.h — C ABI of libsgcount_cuda.so, the B200 (sm_100a) implementation of
+ * sgcount's read->guide matching and counting path.
+ *
+ * The reference (noamteyssier/sgcount v0.1.35, pure Rust) has no FFI boundary; this header
+ * declares the entry points a Rust `sgcount-sys` crate would bind, one per reference call
+ * site on the path.  INTEGRATION.md shows the Rust side.
+ *
+ * Conventions
+ *  - every function returns an int status (0 = SGC_OK) and never unwinds; the message for
+ *    the last failure on the calling thread is sgc_last_error();
+ *  - each status that stands for a reference panic / Err names the reference line;
+ *  - the caller owns every host buffer; the library owns all device memory except a
+ *    caller-provided count vector (sgc_counter_create: d_state);
+ *  - a sgc_library is immutable after creation and may be shared by any number of
+ *    sgc_counters on the same device (the reference shares &Library / &Option<Permuter>
+ *    across rayon workers, count.rs:127-128);
+ *  - a sgc_counter is used from one thread at a time, one per (GPU, sample or sample shard);
+ *  - there is no CPU fallback: with no usable CUDA device every entry point fails with
+ *    SGC_ERR_CUDA.
+ */
+#ifndef SGCOUNT_CUDA_H
+#define SGCOUNT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGC_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------- */
+#define SGC_OK 0
+#define SGC_ERR_INVALID_ARG 1
+#define SGC_ERR_CUDA 2
+#define SGC_ERR_DUPLICATE_SEQUENCE 3 /* panic "Unexpected duplicate sequence in library", library.rs:92 */
+#define SGC_ERR_NON_ACGT_LIBRARY 4   /* library byte outside A,C,G,T: not representable 2-bit (documented deviation) */
+#define SGC_ERR_K_UNSUPPORTED 5      /* guide length outside 1..30 */
+#define SGC_ERR_READ_TOO_SHORT 6     /* Err "Sequences in reference library are larger...", offsetter.rs:154-156 */
+#define SGC_ERR_NAN_ENTROPY 7        /* panic "Unexpected minmax error in entropy", offsetter.rs:123-141 */
+#define SGC_ERR_EMPTY_READER 8       /* panic "empty reader", offsetter.rs:38 */
+#define SGC_ERR_TOO_MANY_GUIDES 9    /* more than SGC_MAX_GUIDES library sequences */
+#define SGC_ERR_BATCH_TOO_LARGE 10   /* a variable-length batch must stay below 4 GiB (u32 line offsets) */
+
+#define SGC_MAX_GUIDES 4194302u
+#define SGC_MAX_K 30u
+
+/* how Record::seq_rev_comp (fxread, used at counter.rs:203) maps non-ACGT bytes; see DESIGN.md */
+#define SGC_RC_BITTRICK 0 /* c&2 ? c^4 : c^21 — 'N' becomes 'J' and 'J' becomes 'N' (default) */
+#define SGC_RC_KEEP_N 1   /* A<->T, C<->G, every other byte unchanged */
+
+typedef struct sgc_library sgc_library;
+typedef struct sgc_counter sgc_counter;
+
+const char* sgc_last_error(void);
+int sgc_abi_version(void);
+int sgc_device_count(int* n);
+
+/* Pinned host memory for the caller's read batches (the ingest ring buffers). */
+int sgc_host_alloc(void** ptr, size_t bytes);
+int sgc_host_free(void* ptr);
+
+/* ---- Library + Permuter ---------------------------------------------------------------
+ * Replaces Library::from_reader (library.rs:17-21,89-99) and Permuter::new
+ * (permutes.rs:47-75, called at count.rs:56).
+ *
+ * seqs: n*k ASCII bytes, row-major, in LIBRARY-FILE ORDER.  Index i of this array is the
+ * guide index used by every other call; index 0 is also the record the entropy routine
+ * consumes without counting (offsetter.rs:57,190-191).
+ * with_permutations: 0 = --exact (count.rs:103-107 passes None), 1 = build the
+ * unambiguous one-mismatch variants.
+ * Errors: SGC_ERR_DUPLICATE_SEQUENCE, SGC_ERR_NON_ACGT_LIBRARY, SGC_ERR_K_UNSUPPORTED,
+ * SGC_ERR_TOO_MANY_GUIDES, SGC_ERR_EMPTY_READER (n == 0; library.rs:74 unwraps).
+ */
+int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, int with_permutations,
+                       sgc_library** out);
+void sgc_library_destroy(sgc_library*);
+
+typedef struct sgc_library_info {
+  uint32_t n_guides;
+  uint32_t k;
+  int32_t with_permutations;
+  int32_t device;
+  uint64_t n_variants;   /* one-mismatch ACGT variants that map to exactly one parent   */
+  uint64_t n_ambiguous;  /* ACGT variants shared by >= 2 parents (the reference's _null) */
+  uint64_t n_slots;      /* slots in the device table                                    */
+  uint64_t table_bytes;
+  double build_ms;       /* device time of the build kernels                             */
+} sgc_library_info;
+int sgc_library_get_info(const sgc_library*, sgc_library_info* out);
+
+/* Composed lookup of n_tokens k-byte tokens: Library::contains (library.rs:34-40), then
+ * Permuter::contains -> Library::alias (counter.rs:111-117).  idx_out[i] = guide index or -1.
+ * kind_out (optional): 0 no match, 1 library member, 2 one-mismatch variant. */
+int sgc_library_lookup(const sgc_library*, const uint8_t* tokens, uint64_t n_tokens, int32_t* idx_out,
+                       uint8_t* kind_out);
+
+/* ---- Offsetter --------------------------------------------------------------------------
+ * Sequence batches are passed as newline-terminated lines:
+ *   line_off != NULL: read i is lines[line_off[i] .. line_off[i+1]-1)  (n_reads+1 entries)
+ *   line_off == NULL: fixed stride — read i is lines[i*stride .. i*stride+read_len)
+ */
+
+/* position_counts (offsetter.rs:55-79): first read gives `size` and is not counted; a byte
+ * outside A,C,G,T adds one to all four columns.  out: size*4 uint32 (row-major [pos][ACGT]),
+ * capacity out_cap rows; *size receives the first read's length. */
+int sgc_position_counts(int device, const uint8_t* lines, uint64_t n_bytes, const uint32_t* line_off,
+                        uint32_t stride, uint32_t read_len, uint64_t n_reads, uint32_t* out,
+                        uint32_t out_cap, uint32_t* size);
+
+/* entropy_offset for one sample (offsetter.rs:167-210 with main.rs:117's subsample applied
+ * by the caller: pass at most `subsample` reads, first record included).  The reference
+ * entropy comes from the library handle.  Errors: SGC_ERR_READ_TOO_SHORT,
+ * SGC_ERR_NAN_ENTROPY, SGC_ERR_EMPTY_READER. */
+int sgc_offset_detect(const sgc_library*, const uint8_t* lines, uint64_t n_bytes, const uint32_t* line_off,
+                      uint32_t stride, uint32_t read_len, uint64_t n_reads, int* is_reverse,
+                      uint32_t* index);
+
+/* ---- Counter ----------------------------------------------------------------------------
+ * Replaces Counter::new / Counter::count (counter.rs:36-66,211-236) for one sample or one
+ * read shard of a sample.
+ *
+ * is_reverse/offset: the Offset (offsetter.rs:10-15).  position_recursion: !-p.
+ * rc_mode: SGC_RC_*.  stream: a cudaStream_t to run on (NULL = a stream owned by the counter).
+ * d_state: optional device buffer of (n_guides + 2) uint64 owned by the caller — counts in
+ * guide-index order, then total_reads, then matched_reads — so a collective (NCCL) can sum
+ * shards in place; NULL = owned by the counter.  The buffer is zeroed by create.
+ */
+int sgc_counter_create(const sgc_library*, int is_reverse, uint32_t offset, int position_recursion,
+                       int rc_mode, void* stream, uint64_t* d_state, sgc_counter** out);
+void sgc_counter_destroy(sgc_counter*);
+
+/* Count a batch held in HOST memory (pinned memory makes the copies asynchronous).  The
+ * batch is cut into chunks that are copied and counted on alternating buffers so copy and
+ * kernel overlap; returns after the last chunk has been enqueued.  The host buffers must
+ * stay valid until sgc_counter_sync / sgc_counter_finish. */
+int sgc_counter_submit(sgc_counter*, const uint8_t* lines, uint64_t n_bytes, const uint32_t* line_off,
+                       uint32_t stride, uint32_t read_len, uint64_t n_reads);
+
+/* Count a batch already resident in DEVICE memory (kernel only, asynchronous).
+ * d_assign_out (optional, n_reads int32): guide index or -1 per read. */
+int sgc_counter_submit_device(sgc_counter*, const uint8_t* d_lines, uint64_t n_bytes,
+                              const uint32_t* d_line_off, uint32_t stride, uint32_t read_len,
+                              uint64_t n_reads, int32_t* d_assign_out);
+
+int sgc_counter_sync(sgc_counter*);
+int sgc_counter_reset(sgc_counter*); /* zero the state vector */
+
+/* Wait, then copy out counts[n_guides] (guide-index order), total_reads, matched_reads
+ * (counter.rs:239-246).  The reference keys results by alias (counter.rs:232-235); the host
+ * maps index -> alias and sums indices that share one. */
+int sgc_counter_finish(sgc_counter*, uint64_t* counts, uint64_t* total, uint64_t* matched);
+
+/* Device pointer / length (in uint64 words) of the state vector, for the caller's collective. */
+int sgc_counter_state(sgc_counter*, uint64_t** d_state, uint64_t* n_words);
+
+/* Statistics of the last sgc_counter_submit_device call, for benchmarking. */
+typedef struct sgc_launch_info {
+  uint32_t grid, block, smem_bytes;
+  uint32_t kernel; /* 0 = staged fixed-stride kernel, 1 = generic kernel */
+  uint64_t launches_total;
+} sgc_launch_info;
+int sgc_counter_launch_info(const sgc_counter*, sgc_launch_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,59 @@
+// internal.h — host-side objects behind the opaque handles of include/sgcount_cuda.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/sgcount_cuda.h"
+#include "common.cuh"
+
+namespace sgc {
+
+int set_error(int code, const std::string& msg);
+int cuda_error(cudaError_t e, const char* what, const char* file, int line);
+
+#define SGC_CUDA_TRY(expr)                                                   \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) return ::sgc::cuda_error(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+// Selects a device for the lifetime of the guard and restores the caller's device.
+class DeviceGuard {
+  int prev_ = -1;
+  bool ok_ = false;
+
+ public:
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) prev_ = -1;
+    ok_ = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev_ >= 0) cudaSetDevice(prev_);
+  }
+  bool ok() const { return ok_; }
+};
+
+// position histogram of a batch of reads (offsetter.rs:55-79), defined in offset.cu
+int position_counts_device(const uint8_t* d_lines, const uint32_t* d_line_off, uint32_t stride,
+                           uint32_t read_len, uint64_t n_reads, uint32_t size, uint32_t* d_hist /* size*4, zeroed */,
+                           cudaStream_t stream);
+
+}  // namespace sgc
+
+struct sgc_library {
+  int device = 0;
+  uint32_t n = 0, k = 0;
+  bool with_perm = false;
+  bool wide = false;
+  uint64_t* d_slots = nullptr;
+  uint32_t n_buckets = 0;
+  uint64_t* d_keys = nullptr;      // n packed guides, library order
+  uint32_t* d_lib_hist = nullptr;  // k*4 positional counts over guides 1..n-1 (offsetter.rs:190-191)
+  int sm_count = 0;
+  sgc_library_info info{};
+
+  sgc::TableView view() const { return sgc::TableView{d_slots, n_buckets, k, wide ? 1u : 0u}; }
+};

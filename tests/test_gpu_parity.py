@@ -1,0 +1,214 @@
+"""CUDA path vs the oracle on the same inputs, through the C ABI.
+
+Bit-exact bar: per-read assignment, per-guide counts, total/matched, detected Offset."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import sgcount_b200 as sg
+from oracle import oracle as orc
+from sgcount_b200 import _cabi
+
+from helpers import make_library, make_reads, oracle_library
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = ["sequence", "zero.sequence", "diff.sequence", "offset", "offset_clipped"]
+
+
+def torch_dev(arr):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+
+
+def gpu_assign(library, permuter, batch, offset, recursion=True, rc_mode=_cabi.RC_BITTRICK, pad=0):
+    """per-read assignment + (counts, total, matched) from sgc_counter_submit_device"""
+    import torch
+
+    lines = batch.lines
+    if pad:
+        lines = np.concatenate([lines, np.zeros(pad, np.uint8)])
+    d_lines = torch_dev(lines)
+    d_off = None if batch.line_off is None else torch_dev(batch.line_off)
+    d_assign = torch.full((max(len(batch), 1),), -7, dtype=torch.int32, device="cuda")
+    c = sg.Counter(library, permuter, offset, recursion, rc_mode)
+    c.submit_device(d_lines.data_ptr(), lines.nbytes, len(batch), batch.stride, batch.read_len,
+                    None if d_off is None else d_off.data_ptr(), d_assign.data_ptr())
+    counts, total, matched = c.finish()
+    return d_assign.cpu().numpy()[:len(batch)], counts, total, matched, c.launch_info()
+
+
+def oracle_count(guides, seqs, with_perm, offset, recursion=True, rc_mode=orc.RC_BITTRICK, n_threads=4):
+    olib, _ = oracle_library(guides)
+    operm = orc.Permuter.new(olib) if with_perm else None
+    oc = orc.Counter.new(orc.Records.from_seqs(seqs), olib, operm, orc.Offset(offset.reverse, offset.index),
+                         None, recursion, rc_mode=rc_mode, n_threads=n_threads, want_assignments=True)
+    return oc.assignments, oc.counts_by_index(), oc.total_reads(), oc.matched_reads()
+
+
+# ---- config 1: the example fixtures ---------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def example_library(example_dir):
+    reader = sg.read_fastx(os.path.join(example_dir, "library.fasta.gz"))
+    library = sg.Library.from_reader(reader)
+    return library, sg.Permuter.new(library)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_example_offset_detection(name, example_dir, example_library):
+    library, _ = example_library
+    reads = sg.read_fastx(os.path.join(example_dir, name + ".fastq.gz"))
+    assert sg.entropy_offset(library, reads, 5000) == sg.Offset.Forward(5)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("name", FIXTURES)
+def test_example_counts(name, exact, example_dir, example_library, expected):
+    library, permuter = example_library
+    fx = expected["fixtures"][name]
+    reads = sg.read_fastx(os.path.join(example_dir, name + ".fastq.gz"))
+    counter = sg.Counter.new(reads, library, None if exact else permuter, sg.Offset.Forward(5), 20, True)
+    assert counter.total_reads() == fx["total_reads"]
+    assert counter.matched_reads() == fx["matched_reads"]
+    assert counter.counts_by_index().tolist() == fx["counts"]
+    rows = "\n".join(f"{a.decode()}\t{c}" for a, c in sorted(zip(library.values(), counter.counts_by_index())))
+    assert hashlib.sha256(rows.encode()).hexdigest()[:16] == fx["sha256_16"]
+    assert counter.get_value(b"lib.0") == fx["counts"][0]
+
+
+def test_example_permuter_stats(example_library):
+    _, permuter = example_library
+    info = permuter.info()
+    assert info.n_variants == 100 * 20 * 3 and info.n_ambiguous == 0
+
+
+# ---- synthetic: every class of read, both kernels, both orientations ------------------------
+
+CASES = [
+    # k, n_guides, read_len, offset, reverse, variable
+    (20, 300, 75, 5, False, False),
+    (20, 300, 75, 5, True, False),
+    (20, 300, 80, 0, False, False),     # stride 81: unaligned spans in the staged kernel
+    (20, 300, 80, 23, True, False),
+    (20, 300, 75, 12, False, True),     # variable length -> generic kernel
+    (20, 300, 75, 12, True, True),
+    (5, 40, 30, 3, False, False),       # dense library: many ambiguous variants
+    (5, 40, 30, 3, True, True),
+    (12, 200, 50, 37, False, False),    # window flush with the read end: Plus never fits
+    (21, 200, 75, 5, False, False),     # wide slots
+    (25, 200, 75, 7, True, False),
+    (30, 100, 64, 1, False, True),
+    (30, 100, 64, 33, True, False),
+]
+
+
+@pytest.mark.parametrize("with_perm", [True, False])
+@pytest.mark.parametrize("k,n_guides,read_len,offset,reverse,variable", CASES)
+def test_per_read_assignment_matches_oracle(k, n_guides, read_len, offset, reverse, variable, with_perm):
+    rng = np.random.default_rng(k * 1000 + offset + 7 * reverse + 3 * variable)
+    guides = make_library(rng, n_guides, k, plant=0.05)
+    wild = b"J" if reverse else b"N"
+    seqs = make_reads(rng, guides, 3000, read_len, offset, reverse, variable, wild=wild)
+    library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+    permuter = sg.Permuter.new(library) if with_perm else None
+    off = sg.Offset(reverse, offset)
+    for recursion in (True, False):
+        batch = sg.ReadBatch.from_seqs(seqs)
+        got = gpu_assign(library, permuter, batch, off, recursion)
+        want = oracle_count(guides, seqs, with_perm, off, recursion)
+        assert np.array_equal(got[0], want[0])
+        assert np.array_equal(got[1], want[1])
+        assert got[2:4] == want[2:4]
+        assert got[3] == int(got[1].sum())
+        if not variable:
+            assert got[4].kernel == 0  # the staged kernel took the whole tiles
+            # the same reads as a variable-length batch go through the generic kernel
+            alt = gpu_assign(library, permuter, sg.ReadBatch.from_seqs(seqs, force_offsets=True), off, recursion)
+            assert alt[4].kernel == 1
+            assert np.array_equal(alt[0], got[0]) and np.array_equal(alt[1], got[1])
+
+
+@pytest.mark.parametrize("rc_mode", [_cabi.RC_BITTRICK, _cabi.RC_KEEP_N])
+def test_reverse_complement_n_modes(rc_mode):
+    """under the fxread bit trick N -> J and J -> N on reverse reads"""
+    rng = np.random.default_rng(11)
+    guides = make_library(rng, 100, 20)
+    seqs = make_reads(rng, guides, 2000, 75, 9, reverse=True, wild=b"N")
+    seqs += make_reads(rng, guides, 2000, 75, 9, reverse=True, wild=b"J")
+    library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+    permuter = sg.Permuter.new(library)
+    off = sg.Offset.Reverse(9)
+    got = gpu_assign(library, permuter, sg.ReadBatch.from_seqs(seqs), off, True, rc_mode)
+    want = oracle_count(guides, seqs, True, off, True, rc_mode)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+def test_host_submit_equals_device_submit_and_accumulates():
+    rng = np.random.default_rng(3)
+    guides = make_library(rng, 500, 20)
+    seqs = make_reads(rng, guides, 5000, 75, 5)
+    library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+    permuter = sg.Permuter.new(library)
+    want = oracle_count(guides, seqs, True, sg.Offset.Forward(5))
+    for force in (False, True):
+        batch = sg.ReadBatch.from_seqs(seqs, force_offsets=force)
+        c = sg.Counter(library, permuter, sg.Offset.Forward(5))
+        c.submit(batch)
+        c.submit(batch)  # a second batch accumulates, like a longer file would
+        counts, total, matched = c.finish()
+        assert np.array_equal(counts, 2 * want[1]) and total == 2 * want[2] and matched == 2 * want[3]
+        c.reset()
+        c.submit(batch)
+        counts, total, matched = c.finish()
+        assert np.array_equal(counts, want[1]) and total == want[2] and matched == want[3]
+
+
+def test_empty_and_tiny_batches():
+    library = sg.Library([b"ACGTACGTACGTACGTACGT"], [b"g0"])
+    c = sg.Counter(library, None, sg.Offset.Forward(0))
+    c.submit(sg.ReadBatch(np.zeros(0, np.uint8), 0, None, 21, 20))
+    assert c.finish()[1:] == (0, 0)
+    c.submit(sg.ReadBatch.from_seqs([b""], force_offsets=True))
+    c.submit(sg.ReadBatch.from_seqs([b"ACGTACGTACGTACGTACGT"]))
+    counts, total, matched = c.finish()
+    assert counts.tolist() == [1] and total == 2 and matched == 1
+
+
+def test_unaligned_device_buffer_falls_back_to_generic_kernel():
+    import torch
+
+    rng = np.random.default_rng(5)
+    guides = make_library(rng, 200, 20)
+    seqs = make_reads(rng, guides, 2048, 75, 5)
+    library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+    batch = sg.ReadBatch.from_seqs(seqs)
+    d = torch.zeros(batch.lines.nbytes + 16, dtype=torch.uint8, device="cuda")
+    d[3:3 + batch.lines.nbytes] = torch.from_numpy(batch.lines).cuda()
+    c = sg.Counter(library, None, sg.Offset.Forward(5))
+    c.submit_device(d.data_ptr() + 3, batch.lines.nbytes, len(batch), batch.stride, batch.read_len)
+    got = c.finish()
+    assert c.launch_info().kernel == 1
+    want = oracle_count(guides, seqs, False, sg.Offset.Forward(5))
+    assert np.array_equal(got[0], want[1])
+
+
+def test_brunello_shaped_two_million_reads():
+    """config-2 shape (77 441 x 20 bp, Forward(5), one-mismatch on) at 2 M reads: the size the
+    oracle still finishes in seconds on a few threads"""
+    rng = np.random.default_rng(0xB2000002)
+    guides = make_library(rng, 77441, 20, plant=0.005)
+    library = sg.Library(guides, [b"lib.%d" % i for i in range(len(guides))])
+    permuter = sg.Permuter.new(library)
+    info = permuter.info()
+    assert info.n_variants + 2 * info.n_ambiguous <= 77441 * 60
+    base = make_reads(rng, guides, 20000, 75, 5)
+    seqs = [base[i] for i in rng.integers(0, len(base), 2_000_000)]
+    off = sg.Offset.Forward(5)
+    got = gpu_assign(library, permuter, sg.ReadBatch.from_seqs(seqs), off)
+    want = oracle_count(guides, seqs, True, off, n_threads=os.cpu_count() or 4)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1]) and got[2:4] == want[2:4]
