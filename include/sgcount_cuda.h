@@ -123,7 +123,8 @@ int sgc_offset_detect(const sgc_library*, const uint8_t* lines, uint64_t n_bytes
  * read shard of a sample.
  *
  * is_reverse/offset: the Offset (offsetter.rs:10-15).  position_recursion: !-p.
- * rc_mode: SGC_RC_*.  stream: a cudaStream_t to run on (NULL = a stream owned by the counter).
+ * rc_mode: SGC_RC_*.  stream: the cudaStream_t every kernel of this counter runs on (NULL = the CUDA
+ * default stream).
  * d_state: optional device buffer of (n_guides + 2) uint64 owned by the caller — counts in
  * guide-index order, then total_reads, then matched_reads — so a collective (NCCL) can sum
  * shards in place; NULL = owned by the counter.  The buffer is zeroed by create.
@@ -159,7 +160,7 @@ int sgc_counter_state(sgc_counter*, uint64_t** d_state, uint64_t* n_words);
 /* Statistics of the last sgc_counter_submit_device call, for benchmarking. */
 typedef struct sgc_launch_info {
   uint32_t grid, block, smem_bytes;
-  uint32_t kernel; /* 0 = staged fixed-stride kernel, 1 = generic kernel */
+  uint32_t kernel; /* 0 = streaming fixed-stride kernel, 1 = generic kernel */
   uint64_t launches_total;
 } sgc_launch_info;
 int sgc_counter_launch_info(const sgc_counter*, sgc_launch_info* out);

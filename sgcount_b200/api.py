@@ -139,9 +139,12 @@ class _Handle:
         return idx, kind
 
     def __del__(self):
-        if getattr(self, "ptr", None):
-            _cabi.load().sgc_library_destroy(self.ptr)
-            self.ptr = None
+        try:
+            if getattr(self, "ptr", None):
+                _cabi.load().sgc_library_destroy(self.ptr)
+                self.ptr = None
+        except Exception:  # interpreter shutdown
+            pass
 
 
 class Library:
@@ -245,9 +248,12 @@ class Counter:
         self._result = None
 
     def __del__(self):
-        if getattr(self, "_ptr", None):
-            _cabi.load().sgc_counter_destroy(self._ptr)
-            self._ptr = None
+        try:
+            if getattr(self, "_ptr", None):
+                _cabi.load().sgc_counter_destroy(self._ptr)
+                self._ptr = None
+        except Exception:  # interpreter shutdown
+            pass
 
     @staticmethod
     def new(reader: ReadBatch, library: Library, permuter: Optional[Permuter], offset: Offset,

@@ -3,7 +3,7 @@
 // Replaces /root/reference/src/counter.rs:36-236 (Counter::new/count/assign/bounds/trim_*).
 //
 // Two kernels share one decision procedure (common.cuh assign_span):
-//   count_staged_kernel  : fixed-stride sequence lines.  Persistent CTAs stream tiles of reads
+//   count_stream_kernel  : fixed-stride sequence lines.  Persistent warps stream tiles of reads
 //                          HBM -> shared memory with 1-D bulk async copies (TMA engine,
 //                          cp.async.bulk + mbarrier complete_tx) through a multi-stage ring;
 //                          each thread lifts the 4-byte words that cover its read's guide
@@ -15,6 +15,7 @@
 // Per-guide counts are 64-bit atomics in the L2-resident state vector; matched reads are
 // accumulated in registers and flushed once per warp.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "internal.h"
@@ -34,13 +35,14 @@ struct CountParams {
   unsigned long long* state;  // counts[n_guides], total, matched
   uint32_t n_guides;
   int32_t* assign_out;
+  uint32_t debug;  // SGC_DEBUG bit mask (tuning only): 1 no count atomics, 2 no table probe, 4 no slow path
 };
 
 __device__ __forceinline__ void record_hit(const CountParams& p, int32_t hit, uint64_t read_idx, uint32_t& matched) {
   if (p.assign_out) p.assign_out[read_idx] = hit;
   if (hit >= 0) {
     ++matched;
-    atomicAdd(p.state + hit, 1ull);  // counter.rs:232-235
+    if (!(p.debug & 1u)) atomicAdd(p.state + hit, 1ull);  // counter.rs:232-235
   }
 }
 
@@ -58,11 +60,11 @@ struct SpanGeom {
   int m;     // number of bases
   int src;   // position in the read (as stored) of the first span byte
 };
-__device__ __forceinline__ SpanGeom span_geom(int n, int offset, int k, bool reverse) {
+__host__ __device__ __forceinline__ SpanGeom span_geom(int n, int offset, int k, bool reverse) {
   SpanGeom g;
   g.base = offset > 0 ? offset - 1 : 0;
-  int end = min(offset + k + 1, n);
-  g.m = max(end - g.base, 0);
+  int end = offset + k + 1 < n ? offset + k + 1 : n;
+  g.m = end > g.base ? end - g.base : 0;
   g.src = reverse ? n - end : g.base;  // revcomp(r)[a:b] == comp(reverse(r[n-b : n-a]))
   return g;
 }
@@ -111,11 +113,22 @@ __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// staged kernel
+// staged kernel: warp-private streaming rings
+//
+// Every warp owns a ring of kStages shared-memory buffers of ONE warp tile (32 reads =
+// 32*stride bytes, always a multiple of 16) and one mbarrier per buffer; lane 0 keeps the
+// ring full with 1-D bulk async copies, so warps never synchronise with each other and each
+// SM keeps (warps x (kStages-1)) tiles in flight.  Per read the hot path is
+//   LDS the span words -> funnel-align -> 2-bit pack + ASCII round-trip validity check ->
+//   one 32-byte table probe for the Centered window -> RED.64 on the guide's counter.
+// Reads the Centered probe does not settle (mismatch beyond the table, N, other bytes; about
+// 10-20 %) are parked in a warp-private shared-memory queue and walked 32 at a time through
+// the full Counter::assign procedure, so the rare path runs with full warps instead of
+// dragging every warp through it.
 // ------------------------------------------------------------------------------------------
-constexpr int kTileReads = 256;  // one read per thread per tile
-constexpr int kStages = 3;
-constexpr int kSpanWords = 9;    // words covering a <= 32 byte span at any alignment
+constexpr int kWarpReads = 32;
+constexpr int kMaxStages = 4;
+constexpr int kQueueCap = 64;  // <= 31 parked + 32 new
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -152,108 +165,206 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
       : "memory");
 }
 
-// pack up to 32 span bytes held in aligned words aw[0..7]
-__device__ __forceinline__ void pack_words(const uint32_t (&aw)[8], int m, uint8_t wild_byte, Span& sp) {
-  uint64_t codes = 0;
-  uint32_t bad = 0, wild = 0;
+// 2-bit pack NW window-aligned words (4 bases each).  `xs[i]` receives each word's XOR against
+// the ASCII its codes stand for (A 41, C 43, T 54, G 47), masked to the bytes that belong to
+// the window: all zero iff every window byte is A/C/G/T.  Returns the OR of xs.
+template <int NW>
+__device__ __forceinline__ uint32_t pack_window(const uint32_t (&aw)[NW], uint32_t last_mask, int n_words,
+                                                uint64_t& codes, uint32_t (&xs)[NW]) {
+  uint32_t lo = 0, hi = 0, any = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (4 * i < m) {
-      const uint32_t w = aw[i];
-      const uint32_t c = (w >> 1) & 0x03030303u;            // code of each byte
-      codes |= (uint64_t)((c * 0x01041040u) >> 24) << (8 * i);  // gather 4 x 2 bits
-      // rebuild the ASCII each code stands for (A 41, C 43, T 54, G 47) and compare
-      const uint32_t b0 = c & 0x01010101u, b1 = (c >> 1) & 0x01010101u;
-      const uint32_t expect = 0x41414141u + 2u * b0 + 0x13u * b1 - 0x0Fu * (b0 & b1);
-      const uint32_t x = w ^ expect;
-      if (x) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if ((x >> (8 * j)) & 0xFFu) {
-            bad |= 1u << (4 * i + j);
-            if (((w >> (8 * j)) & 0xFFu) == wild_byte) wild |= 1u << (4 * i + j);
-          }
-        }
-      }
-    }
+  for (int i = 0; i < NW; ++i) {
+    const uint32_t w = aw[i];
+    const uint32_t c = (w >> 1) & 0x03030303u;
+    const uint32_t packed = (c * 0x01041040u) >> 24;  // gather 4 x 2 bits
+    if (i < 4) lo |= packed << (8 * i); else hi |= packed << (8 * (i - 4));
+    const uint32_t b0 = c & 0x01010101u, b1 = (c >> 1) & 0x01010101u;
+    const uint32_t expect = 0x41414141u + 2u * b0 + 0x13u * b1 - 0x0Fu * (b0 & b1);
+    // NW is the compile-time bound; words at or past n_words hold no window byte
+    const uint32_t m = (NW == 5 || i < n_words - 1) ? ((i == NW - 1 && NW == 5) ? last_mask : ~0u)
+                                                    : (i == n_words - 1 ? last_mask : 0u);
+    xs[i] = (w ^ expect) & m;
+    any |= xs[i];
   }
-  const uint32_t mmask = m >= 32 ? ~0u : ((1u << m) - 1);
-  sp.codes = codes;
-  sp.bad = bad & mmask;
-  sp.wild = wild & mmask;
+  codes = ((uint64_t)hi << 32) | lo;
+  return any;
 }
 
-__global__ void __launch_bounds__(kTileReads) count_staged_kernel(CountParams p, uint64_t n_tiles) {
+// 4-bit mask of the non-zero bytes of x
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) {
+  const uint32_t nz = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+  return ((nz >> 7) * 0x10204080u) >> 28;
+}
+
+struct WarpQueue {
+  uint64_t codes[kQueueCap];
+  uint32_t bad[kQueueCap];
+  uint32_t wild[kQueueCap];
+  uint32_t read[kQueueCap];   // read index relative to the launch's first read
+  uint8_t first_pos[kQueueCap];
+};
+
+// NW = words that hold the k window bytes: 5 (k = 17..20, the common guide lengths) or 8.
+template <int NW, bool WIDE>
+__global__ void __launch_bounds__(384) count_stream_kernel(CountParams p, uint64_t n_wtiles, int n_stages,
+                                                           uint32_t stage_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[kStages];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  // shared layout: [warp][stage] tile buffers | [warp][stage] mbarriers | [warp] queues
+  uint8_t* my_tiles = smem + (size_t)warp * n_stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)warps_per_cta * n_stages * stage_bytes);
+  uint64_t* my_bar = bars + warp * kMaxStages;
+  WarpQueue* q = reinterpret_cast<WarpQueue*>(bars + warps_per_cta * kMaxStages) + warp;
 
-  const uint32_t tile_bytes = kTileReads * p.stride;            // multiple of 16
-  const uint32_t stage_bytes = (tile_bytes + 16 + 127) & ~127u;  // +16: the last span may read past the tile
-  const int tid = threadIdx.x;
-  const int k = (int)p.table.k;
-
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
+  const uint32_t tile_bytes = kWarpReads * p.stride;  // multiple of 16
+  const uint64_t gwarp = (uint64_t)blockIdx.x * warps_per_cta + warp;
+  const uint64_t gwarps = (uint64_t)gridDim.x * warps_per_cta;
 
   uint64_t policy = 0;
-  const uint64_t first_tile = blockIdx.x;
-  const uint64_t tile_step = gridDim.x;
-  if (tid == 0) {
+  if (lane == 0) {
+    for (int s = 0; s < n_stages; ++s) mbar_init(&my_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     policy = l2_evict_first_policy();
-    for (int s = 0; s < kStages; ++s) {
-      uint64_t t = first_tile + (uint64_t)s * tile_step;
-      if (t < n_tiles) {
-        mbar_expect_tx(&full_bar[s], tile_bytes);
-        bulk_load(smem + (size_t)s * stage_bytes, p.lines + (p.first_read + t * kTileReads) * p.stride, tile_bytes,
-                  &full_bar[s], policy);
+    for (int s = 0; s < n_stages; ++s) {
+      const uint64_t t = gwarp + (uint64_t)s * gwarps;
+      if (t < n_wtiles) {
+        mbar_expect_tx(&my_bar[s], tile_bytes);
+        bulk_load(my_tiles + (size_t)s * stage_bytes, p.lines + t * tile_bytes, tile_bytes, &my_bar[s], policy);
       }
     }
   }
+  __syncwarp();
 
-  // every read has the same length, so the span geometry is uniform
+  // Every read has the same length n, so the geometry is uniform.  Stored (as-read)
+  // coordinates of the Centered window: forward [o, o+k), reverse [n-o-k, n-o).
+  const int k = (int)p.table.k;
   const int n = (int)p.read_len;
-  const SpanGeom g = span_geom(n, p.offset, k, p.reverse);
-  const uint32_t byte0 = (uint32_t)tid * p.stride + (uint32_t)g.src;  // tile-local address of the span
-  const uint32_t word0 = byte0 >> 2;
-  const uint32_t shift = (byte0 & 3u) * 8;
-  const int n_words = (int)(((byte0 & 3u) + (uint32_t)g.m + 3u) >> 2);
+  const int o = p.offset;
+  const bool centered_fits = o + k <= n;  // else every read fails its first trim (counter.rs:105-108)
+  const int win_src = p.reverse ? n - o - k : o;
+  // the bytes just outside the window, needed only by the Plus / Minus positions
+  const bool has_before = win_src > 0, has_after = win_src + k < n;
+  const uint32_t wbyte = (uint32_t)lane * p.stride + (uint32_t)(centered_fits ? win_src : 0);
+  const uint32_t word0 = wbyte >> 2;
+  const uint32_t shift = (wbyte & 3u) * 8;
+  const int n_words = (k + 3) >> 2;
+  const uint32_t last_mask = (k & 3) ? ((1u << (8 * (k & 3))) - 1) : ~0u;
+  const uint64_t kmask = (1ull << (2 * k)) - 1;
+  const uint64_t* __restrict__ slots = p.table.slots;
+  const uint32_t n_buckets = p.table.n_buckets;
+  const uint32_t wild4 = 0x01010101u * p.wild_byte;
 
   uint32_t matched = 0;
-  uint32_t it = 0;
-  for (uint64_t t = first_tile; t < n_tiles; t += tile_step, ++it) {
-    const int s = it % kStages;
-    const uint32_t parity = (it / kStages) & 1u;
-    mbar_wait(&full_bar[s], parity);
+  uint32_t qn = 0;  // parked reads (warp-uniform)
 
-    const uint32_t* tile = reinterpret_cast<const uint32_t*>(smem + (size_t)s * stage_bytes);
-    uint32_t raw[kSpanWords];
+  // the full walk of Counter::assign for parked reads [from, from + count) of the queue;
+  // their spans are [before][window][after] in oriented coordinates, base o-1
+  auto drain = [&](uint32_t from, uint32_t count) {
+    if ((uint32_t)lane < count) {
+      const uint32_t e = from + lane;
+      Span sp{q->codes[e], q->bad[e], q->wild[e]};
+      int32_t hit = assign_span(p.table, p.with_perm, sp, o - 1, n, o, p.recursion, nullptr, q->first_pos[e]);
+      record_hit(p, hit, (uint64_t)q->read[e], matched);
+    }
+  };
+
+  int s = 0;
+  uint32_t parity = 0;
+  for (uint64_t t = gwarp; t < n_wtiles; t += gwarps) {
+    mbar_wait(&my_bar[s], parity);
+
+    const uint8_t* tile8 = my_tiles + (size_t)s * stage_bytes;
+    const uint32_t* tile = reinterpret_cast<const uint32_t*>(tile8);
+    uint32_t raw[NW + 1];
 #pragma unroll
-    for (int i = 0; i < kSpanWords; ++i) raw[i] = (i < n_words) ? tile[word0 + i] : 0u;
-
-    __syncthreads();  // all spans are in registers: the stage can be refilled
-    if (tid == 0) {
-      uint64_t nt = t + (uint64_t)kStages * tile_step;
-      if (nt < n_tiles) {
+    for (int i = 0; i <= NW; ++i) raw[i] = tile[word0 + i];
+    const uint32_t b_before = has_before ? tile8[wbyte - 1] : 0u;
+    const uint32_t b_after = has_after ? tile8[wbyte + k] : 0u;
+    __syncwarp();  // the whole warp has its bytes in registers: refill this buffer
+    if (lane == 0) {
+      const uint64_t nt = t + (uint64_t)n_stages * gwarps;
+      if (nt < n_wtiles) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&full_bar[s], tile_bytes);
-        bulk_load(smem + (size_t)s * stage_bytes, p.lines + (p.first_read + nt * kTileReads) * p.stride, tile_bytes,
-                  &full_bar[s], policy);
+        mbar_expect_tx(&my_bar[s], tile_bytes);
+        bulk_load(my_tiles + (size_t)s * stage_bytes, p.lines + nt * tile_bytes, tile_bytes, &my_bar[s], policy);
       }
     }
+    if (++s == n_stages) {
+      s = 0;
+      parity ^= 1u;
+    }
+    const uint32_t read_idx = (uint32_t)(t * kWarpReads + lane);
+    if (!centered_fits) {
+      if (p.assign_out) p.assign_out[read_idx] = kMiss;
+      continue;
+    }
 
-    uint32_t aw[8];
+    uint32_t aw[NW], xs[NW];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) aw[i] = __funnelshift_r(raw[i], raw[i + 1], shift);
-    Span sp;
-    pack_words(aw, g.m, p.wild_byte, sp);
-    orient(sp, g.m, p.reverse);
-    int32_t hit = assign_span(p.table, p.with_perm, sp, g.base, n, p.offset, p.recursion, nullptr);
-    record_hit(p, hit, p.first_read + t * kTileReads + tid, matched);
+    for (int i = 0; i < NW; ++i) aw[i] = __funnelshift_r(raw[i], raw[i + 1], shift);
+    uint64_t codes;
+    const uint32_t any = pack_window<NW>(aw, last_mask, n_words, codes, xs);
+    codes &= kmask;
+    if (p.reverse) codes = revcomp_codes(codes, k);
+
+    // Centered window: one probe settles a library member or an unambiguous variant
+    int32_t hit = kMiss;
+    bool park;
+    if (any == 0) {
+      if (p.debug & 2u)
+        hit = (int32_t)(codes % p.n_guides);
+      else
+        hit = meta_hit(table_find_t<WIDE>(slots, n_buckets, codes));
+      park = hit == kMiss && p.recursion && !(p.debug & 4u);
+      if (!park) record_hit(p, hit, (uint64_t)read_idx, matched);
+    } else {
+      park = true;  // N / other bytes inside the window: full procedure
+    }
+    const uint32_t pm = __ballot_sync(0xffffffffu, park);
+    if (pm) {
+      if (park) {
+        // per-base masks of the window, then the oriented span [before][window][after]
+        uint32_t badw = 0, wildw = 0;
+        if (any) {
+#pragma unroll
+          for (int i = 0; i < NW; ++i) {
+            badw |= nonzero_bytes(xs[i]) << (4 * i);
+            const uint32_t xw = aw[i] ^ wild4;
+            wildw |= (nonzero_bytes(xw) ^ 0xFu) << (4 * i);
+          }
+          wildw &= badw;
+          if (p.reverse) {
+            badw = reverse_bits(badw, k);
+            wildw = reverse_bits(wildw, k);
+          }
+        }
+        // oriented neighbours: reverse swaps and complements them
+        const uint32_t prev = p.reverse ? b_after : b_before, next = p.reverse ? b_before : b_after;
+        const bool has_prev = p.reverse ? has_after : has_before, has_next = p.reverse ? has_before : has_after;
+        const uint32_t cflip = p.reverse ? 2u : 0u;
+        const bool prev_bad = !has_prev || !is_acgt((uint8_t)prev), next_bad = !has_next || !is_acgt((uint8_t)next);
+        const uint32_t e = qn + __popc(pm & ((1u << lane) - 1));
+        q->codes[e] = (uint64_t)(code_of((uint8_t)prev) ^ cflip) | (codes << 2) |
+                      ((uint64_t)(code_of((uint8_t)next) ^ cflip) << (2 * k + 2));
+        q->bad[e] = (prev_bad ? 1u : 0u) | (badw << 1) | ((next_bad ? 1u : 0u) << (k + 1));
+        q->wild[e] = ((has_prev && prev == p.wild_byte) ? 1u : 0u) | (wildw << 1) |
+                     (((has_next && next == p.wild_byte) ? 1u : 0u) << (k + 1));
+        q->read[e] = read_idx;
+        q->first_pos[e] = any ? 0 : 1;  // Centered already probed and missed
+      }
+      qn += __popc(pm);
+      __syncwarp();
+      if (qn >= 32) {
+        qn -= 32;
+        drain(qn, 32);
+        __syncwarp();
+      }
+    }
   }
+  if (qn) drain(0, qn);
   flush_matched(p, matched);
 }
 
@@ -270,7 +381,6 @@ struct sgc_counter {
   int recursion = 1;
   int rc_mode = SGC_RC_BITTRICK;
   cudaStream_t stream = nullptr;
-  bool own_stream = false;
   unsigned long long* d_state = nullptr;
   bool own_state = false;
   // host-batch staging (sgc_counter_submit)
@@ -281,7 +391,6 @@ struct sgc_counter {
   cudaEvent_t copy_done[2] = {nullptr, nullptr}, kernel_done[2] = {nullptr, nullptr};
   uint64_t chunks_submitted = 0;
   sgc_launch_info last{};
-  int staged_blocks_per_sm = 0;
 };
 
 using namespace sgc;
@@ -289,6 +398,12 @@ using namespace sgc;
 namespace {
 
 constexpr size_t kChunkBytes = 64ull << 20;
+constexpr uint64_t kChunkAlignReads = 256;  // chunk starts stay 16-byte aligned for any stride
+
+int env_int(const char* name, int fallback) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : fallback;
+}
 
 uint8_t wild_byte_for(const sgc_counter* c) {
   // the byte that reads as 'N' to the lookup: under the fxread bit trick a reverse-complemented
@@ -312,7 +427,34 @@ CountParams make_params(const sgc_counter* c, const uint8_t* d_lines, const uint
   p.state = c->d_state;
   p.n_guides = c->lib->n;
   p.assign_out = d_assign;
+  p.debug = (uint32_t)env_int("SGC_DEBUG", 0);
   return p;
+}
+
+struct StreamConfig {
+  int warps = 0, stages = 0, ctas_per_sm = 0;
+};
+size_t stream_smem_bytes(const StreamConfig& c, uint32_t stage_bytes) {
+  return (size_t)c.warps * ((size_t)c.stages * stage_bytes + kMaxStages * sizeof(uint64_t) + sizeof(WarpQueue));
+}
+// Largest ring that fits: prefer 2 resident CTAs of 12 warps with >= 3 buffers per warp.
+// SGC_WARPS / SGC_STAGES / SGC_CTAS override the choice (tuning only).
+StreamConfig pick_stream_config(uint32_t stage_bytes) {
+  const size_t sm_budget = 227 * 1024;
+  StreamConfig best{};
+  const int want_warps = env_int("SGC_WARPS", 12), want_ctas = env_int("SGC_CTAS", 2);
+  const int want_stages = env_int("SGC_STAGES", 3);
+  for (int ctas = want_ctas; ctas >= 1 && !best.stages; --ctas) {
+    for (int stages = std::min(want_stages, kMaxStages); stages >= 2; --stages) {
+      StreamConfig c{want_warps, stages, ctas};
+      if (c.warps < 1 || c.warps > 12) c.warps = 12;
+      if ((stream_smem_bytes(c, stage_bytes) + 1024) * ctas <= sm_budget) {
+        best = c;
+        break;
+      }
+    }
+  }
+  return best;
 }
 
 // Enqueue the kernels for one device-resident batch.
@@ -325,30 +467,30 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
   c->last = sgc_launch_info{};
   c->last.launches_total = launches_before;
   c->last.kernel = 1;
-  const bool stageable = d_off == nullptr && ((uintptr_t)d_lines & 15u) == 0 && stride >= read_len &&
-                         (uint64_t)kTileReads * stride + 16 <= 48 * 1024;
-  if (stageable && n_reads >= (uint64_t)kTileReads && n_bytes >= (uint64_t)kTileReads * stride) {
-    // whole tiles only, and never a bulk copy that would run past n_bytes
-    const uint64_t n_tiles = std::min(n_reads / kTileReads, n_bytes / ((uint64_t)kTileReads * stride));
-    const uint32_t tile_bytes = kTileReads * stride;
-    const uint32_t stage_bytes = (tile_bytes + 16 + 127) & ~127u;
-    const size_t smem = (size_t)kStages * stage_bytes;
-    if (c->staged_blocks_per_sm == 0) {
-      SGC_CUDA_TRY(cudaFuncSetAttribute(count_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    }
-    int per_sm = 0;
-    SGC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_staged_kernel, kTileReads, smem));
-    if (per_sm < 1) return set_error(SGC_ERR_CUDA, "staged kernel does not fit on an SM");
-    c->staged_blocks_per_sm = per_sm;
-    uint64_t grid = (uint64_t)c->lib->sm_count * per_sm;  // persistent: every CTA resident
-    if (grid > n_tiles) grid = n_tiles;
-    p.n_reads = n_tiles * kTileReads;
+  // staged kernel: fixed stride, 16-byte aligned base, whole warp tiles, < 2^32 reads per launch
+  const uint32_t tile_bytes = kWarpReads * stride;
+  const uint32_t stage_bytes = (tile_bytes + 48 + 15) & ~15u;  // +48: span words may run past the tile
+  const bool stageable = d_off == nullptr && ((uintptr_t)d_lines & 15u) == 0 && stride >= read_len;
+  StreamConfig cfg = stageable ? pick_stream_config(stage_bytes) : StreamConfig{};
+  // whole tiles only, and never a bulk copy that would run past n_bytes
+  uint64_t n_wtiles = stageable && cfg.stages ? std::min(n_reads / kWarpReads, n_bytes / tile_bytes) : 0;
+  n_wtiles = std::min<uint64_t>(n_wtiles, 0xFFFFFFFFull / kWarpReads);
+  if (n_wtiles > 0) {
+    const bool nw5 = c->lib->k > 16 && c->lib->k <= 20;
+    auto kernel = c->lib->wide ? count_stream_kernel<8, true>
+                               : (nw5 ? count_stream_kernel<5, false> : count_stream_kernel<8, false>);
+    const size_t smem = stream_smem_bytes(cfg, stage_bytes);
+    SGC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t grid = (uint64_t)c->lib->sm_count * cfg.ctas_per_sm;  // persistent: every CTA resident
+    const uint64_t ctas_needed = (n_wtiles + cfg.warps - 1) / cfg.warps;
+    if (grid > ctas_needed) grid = ctas_needed;
+    p.n_reads = n_wtiles * kWarpReads;
     p.first_read = 0;
-    count_staged_kernel<<<(unsigned)grid, kTileReads, smem, stream>>>(p, n_tiles);
+    kernel<<<(unsigned)grid, cfg.warps * 32, smem, stream>>>(p, n_wtiles, cfg.stages, stage_bytes);
     SGC_CUDA_TRY(cudaGetLastError());
-    done = n_tiles * kTileReads;
+    done = n_wtiles * kWarpReads;
     c->last.grid = (uint32_t)grid;
-    c->last.block = kTileReads;
+    c->last.block = cfg.warps * 32;
     c->last.smem_bytes = (uint32_t)smem;
     c->last.kernel = 0;
     c->last.launches_total += 1;
@@ -408,12 +550,7 @@ int sgc_counter_create(const sgc_library* lib, int is_reverse, uint32_t offset, 
       if (c) sgc_counter_destroy(c);
     }
   } cleanup{c};
-  if (stream) {
-    c->stream = (cudaStream_t)stream;
-  } else {
-    SGC_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    c->own_stream = true;
-  }
+  c->stream = (cudaStream_t)stream;  // NULL is the CUDA default stream
   const size_t words = (size_t)lib->n + 2;
   if (d_state) {
     c->d_state = reinterpret_cast<unsigned long long*>(d_state);
@@ -430,7 +567,7 @@ int sgc_counter_create(const sgc_library* lib, int is_reverse, uint32_t offset, 
 void sgc_counter_destroy(sgc_counter* c) {
   if (!c) return;
   DeviceGuard guard(c->lib->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->stream);
   if (c->copy_stream) {
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamDestroy(c->copy_stream);
@@ -442,7 +579,6 @@ void sgc_counter_destroy(sgc_counter* c) {
     if (c->kernel_done[i]) cudaEventDestroy(c->kernel_done[i]);
   }
   if (c->own_state) cudaFree(c->d_state);
-  if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
@@ -482,7 +618,7 @@ int sgc_counter_submit(sgc_counter* c, const uint8_t* lines, uint64_t n_bytes, c
       }
       r1 = lo > r0 ? lo : r0 + 1;
     } else {
-      uint64_t per = std::max<uint64_t>(kTileReads, (kChunkBytes / stride) / kTileReads * kTileReads);
+      uint64_t per = std::max<uint64_t>(kChunkAlignReads, (kChunkBytes / stride) / kChunkAlignReads * kChunkAlignReads);
       r1 = std::min(n_reads, r0 + per);
     }
     const int b = (int)(c->chunks_submitted & 1);
