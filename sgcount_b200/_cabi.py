@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "lib", "libsgcount_cuda.so")
+# SGC_CUDA_LIB overrides the path (A/B timing of two builds; tuning only)
+SO_PATH = os.environ.get("SGC_CUDA_LIB") or os.path.join(_HERE, "lib", "libsgcount_cuda.so")
 
 OK = 0
 ERR_INVALID_ARG = 1

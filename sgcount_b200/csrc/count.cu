@@ -35,6 +35,11 @@ struct CountParams {
   unsigned long long* state;  // counts[n_guides], total, matched
   uint32_t n_guides;
   int32_t* assign_out;
+  // reads the streaming kernel could not settle, as structure-of-arrays records of park_cap
+  // entries each: window words [NW], misc, read index (see WarpQueueT)
+  uint32_t* park_rec;
+  unsigned int* park_count;
+  uint32_t park_cap;
   uint32_t debug;  // SGC_DEBUG bit mask (tuning only): 1 no count atomics, 2 no table probe, 4 no slow path
 };
 
@@ -156,6 +161,11 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 // 1-D bulk async copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
   asm volatile(
@@ -196,18 +206,136 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) {
   return ((nz >> 7) * 0x10204080u) >> 28;
 }
 
-struct WarpQueue {
-  uint64_t codes[kQueueCap];
-  uint32_t bad[kQueueCap];
-  uint32_t wild[kQueueCap];
-  uint32_t read[kQueueCap];   // read index relative to the launch's first read
-  uint8_t first_pos[kQueueCap];
+// Parked reads keep the raw window words; everything else is re-derived when a full warp of
+// them is drained, so parking costs a handful of shared-memory stores.
+// Layout per warp (words): w[NW][kQueueCap] | misc[kQueueCap] | read[kQueueCap]
+//   misc = before | after << 8 | flags << 16   (flag 1: the Centered probe was a definite miss)
+template <int NW>
+struct WarpQueueT {
+  uint32_t w[NW][kQueueCap];
+  uint32_t misc[kQueueCap];
+  uint32_t read[kQueueCap];  // read index relative to the launch's first read
 };
 
-// NW = words that hold the k window bytes: 5 (k = 17..20, the common guide lengths) or 8.
+// Everything a parked read needs, uniform across the warp.
+struct WalkGeom {
+  int k, n, o;
+  bool reverse, recursion, with_perm, has_before, has_after;
+  uint32_t last_mask, wild_byte;
+  int n_words;
+};
+
+__device__ __forceinline__ WalkGeom make_geom(const CountParams& p) {
+  WalkGeom g;
+  g.k = (int)p.table.k;
+  g.n = (int)p.read_len;
+  g.o = p.offset;
+  g.reverse = p.reverse;
+  g.recursion = p.recursion;
+  g.with_perm = p.with_perm;
+  // stored (as-read) coordinates of the Centered window: forward [o, o+k), reverse [n-o-k, n-o)
+  const int win_src = g.reverse ? g.n - g.o - g.k : g.o;
+  g.has_before = win_src > 0;         // the bytes just outside the window are needed
+  g.has_after = win_src + g.k < g.n;  // only by the Plus / Minus positions
+  g.n_words = (g.k + 3) >> 2;
+  g.last_mask = (g.k & 3) ? ((1u << (8 * (g.k & 3))) - 1) : ~0u;
+  g.wild_byte = p.wild_byte;
+  return g;
+}
+
+// Full Counter::assign (counter.rs:96-140) for one parked read.
 template <int NW, bool WIDE>
-__global__ void __launch_bounds__(384) count_stream_kernel(CountParams p, uint64_t n_wtiles, int n_stages,
-                                                           uint32_t stage_bytes) {
+__device__ __forceinline__ int32_t walk_parked(const TableView& t, const WalkGeom& g, const uint32_t (&aw)[NW],
+                                               uint32_t misc) {
+  uint32_t xs[NW];
+  uint64_t codes;
+  const uint32_t any = pack_window<NW>(aw, g.last_mask, g.n_words, codes, xs);
+  const uint64_t kmask = (1ull << (2 * g.k)) - 1;
+  codes &= kmask;
+  if (g.reverse) codes = revcomp_codes(codes, g.k);
+  const uint32_t b_before = misc & 0xFFu, b_after = (misc >> 8) & 0xFFu;
+  const int first_pos = (misc >> 16) & 1u;
+  // oriented neighbours: reverse swaps and complements them
+  const uint32_t prev = g.reverse ? b_after : b_before, next = g.reverse ? b_before : b_after;
+  const bool has_prev = g.reverse ? g.has_after : g.has_before, has_next = g.reverse ? g.has_before : g.has_after;
+  const uint32_t cflip = g.reverse ? 2u : 0u;
+  const bool prev_bad = !has_prev || !is_acgt((uint8_t)prev), next_bad = !has_next || !is_acgt((uint8_t)next);
+  Span sp;
+  sp.codes = (uint64_t)(code_of((uint8_t)prev) ^ cflip) | (codes << 2) |
+             ((uint64_t)(code_of((uint8_t)next) ^ cflip) << (2 * g.k + 2));
+  if (any == 0 && !(has_prev && prev_bad) && !(has_next && next_bad) && t.bloom != nullptr) {
+    // Clean bases (the common parked read).  Everything the walk may consult that lives in
+    // L2 -- the Bloom words of the three windows and the front-table buckets of Plus and
+    // Minus -- is fetched in one go; the main table is touched only for keys the filter
+    // cannot rule out.  Resolution keeps the reference's order: Centered, Plus, Minus, a
+    // library member before a variant at each (counter.rs:111-135); a window whose trim
+    // would fail is never consulted.
+    const bool try_c = first_pos == 0;
+    const bool front_c_open = (misc >> 17) & 1u;  // the streaming probe could not decide membership
+    const bool try_p = g.recursion && g.o + 1 + g.k <= g.n;
+    const bool try_m = try_p && g.o > 0;
+    const uint64_t key_c = (sp.codes >> 2) & kmask, key_p = (sp.codes >> 4) & kmask, key_m = sp.codes & kmask;
+    uint64_t fp[4], fm[4], bc = 0, bp = 0, bm = 0, mc, mp, mm, meta;
+    uint32_t wc, wp, wm;
+    bloom_locate(key_c, t.n_bloom_words, wc, mc);
+    bloom_locate(key_p, t.n_bloom_words, wp, mp);
+    bloom_locate(key_m, t.n_bloom_words, wm, mm);
+    if (try_c) bc = __ldg(t.bloom + wc);
+    if (try_p) {
+      load_bucket(t.front_slots + (size_t)bucket_of(key_p, t.front_buckets) * 4, fp);
+      bp = __ldg(t.bloom + wp);
+    }
+    if (try_m) {
+      load_bucket(t.front_slots + (size_t)bucket_of(key_m, t.front_buckets) * 4, fm);
+      bm = __ldg(t.bloom + wm);
+    }
+    if (try_c) {
+      if (front_c_open) {
+        const int32_t hit = meta_hit(table_find_t<WIDE>(t.front_slots, t.front_buckets, key_c));
+        if (hit != kMiss) return hit;
+      }
+      if ((bc & mc) == mc) {
+        const int32_t hit = meta_hit(table_find_t<WIDE>(t.slots, t.n_buckets, key_c));
+        if (hit != kMiss) return hit;
+      }
+    }
+    if (!try_p) return kMiss;  // no recursion, or the Plus trim fails: return (counter.rs:105-108)
+    // one window: member in the front table, else (filter permitting) the main table
+    auto settle = [&](const uint64_t (&f)[4], bool maybe, uint64_t key) -> int32_t {
+      const int r = bucket_match<WIDE>(f, key, meta);
+      if (r == kFound) return meta_hit(meta);
+      if (!maybe) return kMiss;
+      return meta_hit(table_find_t<WIDE>(t.slots, t.n_buckets, key));
+    };
+    const int32_t hit_p = settle(fp, (bp & mp) == mp, key_p);
+    if (hit_p != kMiss) return hit_p;
+    if (!try_m) return kMiss;  // checked_sub(1) -> None
+    return settle(fm, (bm & mm) == mm, key_m);
+  }
+  uint32_t badw = 0, wildw = 0;
+  if (any) {
+    const uint32_t wild4 = 0x01010101u * g.wild_byte;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      badw |= nonzero_bytes(xs[i]) << (4 * i);
+      wildw |= (nonzero_bytes(aw[i] ^ wild4) ^ 0xFu) << (4 * i);
+    }
+    wildw &= badw;
+    if (g.reverse) {
+      badw = reverse_bits(badw, g.k);
+      wildw = reverse_bits(wildw, g.k);
+    }
+  }
+  sp.bad = (prev_bad ? 1u : 0u) | (badw << 1) | ((next_bad ? 1u : 0u) << (g.k + 1));
+  sp.wild = ((has_prev && prev == g.wild_byte) ? 1u : 0u) | (wildw << 1) |
+            (((has_next && next == g.wild_byte) ? 1u : 0u) << (g.k + 1));
+  return assign_span(t, g.with_perm, sp, g.o - 1, g.n, g.o, g.recursion, nullptr, first_pos);
+}
+
+// Pass 1.  NW = words that hold the k window bytes: 5 (k = 17..20, the common guide lengths) or 8.
+template <int NW, bool WIDE>
+__global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams p, uint64_t n_wtiles, int n_stages,
+                                                              uint32_t stage_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -216,88 +344,94 @@ __global__ void __launch_bounds__(384) count_stream_kernel(CountParams p, uint64
   uint8_t* my_tiles = smem + (size_t)warp * n_stages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)warps_per_cta * n_stages * stage_bytes);
   uint64_t* my_bar = bars + warp * kMaxStages;
-  WarpQueue* q = reinterpret_cast<WarpQueue*>(bars + warps_per_cta * kMaxStages) + warp;
+  WarpQueueT<NW>* q = reinterpret_cast<WarpQueueT<NW>*>(bars + warps_per_cta * kMaxStages) + warp;
 
   const uint32_t tile_bytes = kWarpReads * p.stride;  // multiple of 16
   const uint64_t gwarp = (uint64_t)blockIdx.x * warps_per_cta + warp;
   const uint64_t gwarps = (uint64_t)gridDim.x * warps_per_cta;
+  const uint64_t src_step = gwarps * tile_bytes;
+  const uint8_t* next_src = p.lines + gwarp * tile_bytes;  // source of the next tile to request
 
   uint64_t policy = 0;
+  uint64_t requested = gwarp;  // tile index of the next request
   if (lane == 0) {
     for (int s = 0; s < n_stages; ++s) mbar_init(&my_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     policy = l2_evict_first_policy();
     for (int s = 0; s < n_stages; ++s) {
-      const uint64_t t = gwarp + (uint64_t)s * gwarps;
-      if (t < n_wtiles) {
+      if (requested < n_wtiles) {
         mbar_expect_tx(&my_bar[s], tile_bytes);
-        bulk_load(my_tiles + (size_t)s * stage_bytes, p.lines + t * tile_bytes, tile_bytes, &my_bar[s], policy);
+        bulk_load(my_tiles + (size_t)s * stage_bytes, next_src, tile_bytes, &my_bar[s], policy);
+        requested += gwarps;
+        next_src += src_step;
       }
     }
   }
   __syncwarp();
 
-  // Every read has the same length n, so the geometry is uniform.  Stored (as-read)
-  // coordinates of the Centered window: forward [o, o+k), reverse [n-o-k, n-o).
-  const int k = (int)p.table.k;
-  const int n = (int)p.read_len;
-  const int o = p.offset;
-  const bool centered_fits = o + k <= n;  // else every read fails its first trim (counter.rs:105-108)
-  const int win_src = p.reverse ? n - o - k : o;
-  // the bytes just outside the window, needed only by the Plus / Minus positions
-  const bool has_before = win_src > 0, has_after = win_src + k < n;
+  // every read has the same length n, so the geometry is uniform
+  const WalkGeom g = make_geom(p);
+  const int k = g.k;
+  const bool centered_fits = g.o + k <= g.n;  // else every read fails its first trim (counter.rs:105-108)
+  const int win_src = g.reverse ? g.n - g.o - k : g.o;
   const uint32_t wbyte = (uint32_t)lane * p.stride + (uint32_t)(centered_fits ? win_src : 0);
   const uint32_t word0 = wbyte >> 2;
   const uint32_t shift = (wbyte & 3u) * 8;
-  const int n_words = (k + 3) >> 2;
-  const uint32_t last_mask = (k & 3) ? ((1u << (8 * (k & 3))) - 1) : ~0u;
   const uint64_t kmask = (1ull << (2 * k)) - 1;
-  const uint64_t* __restrict__ slots = p.table.slots;
-  const uint32_t n_buckets = p.table.n_buckets;
-  const uint32_t wild4 = 0x01010101u * p.wild_byte;
+  const uint64_t* __restrict__ front = p.table.front_slots;
+  const uint32_t front_buckets = p.table.front_buckets;
+  const bool park_misses = g.recursion;
+  const uint64_t table_policy = l2_evict_last_policy();
 
   uint32_t matched = 0;
   uint32_t qn = 0;  // parked reads (warp-uniform)
 
-  // the full walk of Counter::assign for parked reads [from, from + count) of the queue;
-  // their spans are [before][window][after] in oriented coordinates, base o-1
-  auto drain = [&](uint32_t from, uint32_t count) {
+  // Parked reads leave the streaming loop: `count` queue entries starting at `from` are
+  // appended to the global record buffer (coalesced, one reservation per flush) and walked
+  // later by count_parked_kernel at full occupancy.
+  auto flush = [&](uint32_t from, uint32_t count) {
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(p.park_count, count);
+    base = __shfl_sync(0xffffffffu, base, 0);
     if ((uint32_t)lane < count) {
       const uint32_t e = from + lane;
-      Span sp{q->codes[e], q->bad[e], q->wild[e]};
-      int32_t hit = assign_span(p.table, p.with_perm, sp, o - 1, n, o, p.recursion, nullptr, q->first_pos[e]);
-      record_hit(p, hit, (uint64_t)q->read[e], matched);
+      uint32_t* dst = p.park_rec + base + lane;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) dst[(size_t)i * p.park_cap] = q->w[i][e];
+      dst[(size_t)NW * p.park_cap] = q->misc[e];
+      dst[(size_t)(NW + 1) * p.park_cap] = q->read[e];
     }
   };
 
   int s = 0;
   uint32_t parity = 0;
-  for (uint64_t t = gwarp; t < n_wtiles; t += gwarps) {
+  uint32_t read_idx = (uint32_t)(gwarp * kWarpReads) + lane;
+  const uint32_t read_step = (uint32_t)(gwarps * kWarpReads);
+  for (uint64_t t = gwarp; t < n_wtiles; t += gwarps, read_idx += read_step) {
+    // wait for the tile, lift this lane's window out of shared memory, hand the buffer back
     mbar_wait(&my_bar[s], parity);
-
     const uint8_t* tile8 = my_tiles + (size_t)s * stage_bytes;
     const uint32_t* tile = reinterpret_cast<const uint32_t*>(tile8);
     uint32_t raw[NW + 1];
 #pragma unroll
     for (int i = 0; i <= NW; ++i) raw[i] = tile[word0 + i];
-    const uint32_t b_before = has_before ? tile8[wbyte - 1] : 0u;
-    const uint32_t b_after = has_after ? tile8[wbyte + k] : 0u;
+    uint32_t misc = 0;
+    if (g.has_before) misc = tile8[wbyte - 1];
+    if (g.has_after) misc |= (uint32_t)tile8[wbyte + k] << 8;
     __syncwarp();  // the whole warp has its bytes in registers: refill this buffer
-    if (lane == 0) {
-      const uint64_t nt = t + (uint64_t)n_stages * gwarps;
-      if (nt < n_wtiles) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&my_bar[s], tile_bytes);
-        bulk_load(my_tiles + (size_t)s * stage_bytes, p.lines + nt * tile_bytes, tile_bytes, &my_bar[s], policy);
-      }
+    if (lane == 0 && requested < n_wtiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&my_bar[s], tile_bytes);
+      bulk_load(my_tiles + (size_t)s * stage_bytes, next_src, tile_bytes, &my_bar[s], policy);
+      requested += gwarps;
+      next_src += src_step;
     }
     if (++s == n_stages) {
       s = 0;
       parity ^= 1u;
     }
-    const uint32_t read_idx = (uint32_t)(t * kWarpReads + lane);
-    if (!centered_fits) {
+    if (!centered_fits) {  // every read fails its first trim: nothing is tried (counter.rs:105-108)
       if (p.assign_out) p.assign_out[read_idx] = kMiss;
       continue;
     }
@@ -306,66 +440,81 @@ __global__ void __launch_bounds__(384) count_stream_kernel(CountParams p, uint64
 #pragma unroll
     for (int i = 0; i < NW; ++i) aw[i] = __funnelshift_r(raw[i], raw[i + 1], shift);
     uint64_t codes;
-    const uint32_t any = pack_window<NW>(aw, last_mask, n_words, codes, xs);
+    const uint32_t any = pack_window<NW>(aw, g.last_mask, g.n_words, codes, xs);
     codes &= kmask;
-    if (p.reverse) codes = revcomp_codes(codes, k);
+    if (g.reverse) codes = revcomp_codes(codes, k);
 
-    // Centered window: one probe settles a library member or an unambiguous variant
-    int32_t hit = kMiss;
-    bool park;
+    // Centered window against the FRONT table (library members only, L2 resident), one
+    // bucket: settles every exact read whose guide sits in its home bucket.  Everything else
+    // is parked for the full walk over the unified table.
+    bool park = true;
     if (any == 0) {
-      if (p.debug & 2u)
+      int32_t hit;
+      int r;
+      if (p.debug & 2u) {
         hit = (int32_t)(codes % p.n_guides);
-      else
-        hit = meta_hit(table_find_t<WIDE>(slots, n_buckets, codes));
-      park = hit == kMiss && p.recursion && !(p.debug & 4u);
-      if (!park) record_hit(p, hit, (uint64_t)read_idx, matched);
-    } else {
-      park = true;  // N / other bytes inside the window: full procedure
+        r = kFound;
+      } else {
+        uint64_t w[4], meta;
+        load_bucket(front + (size_t)bucket_of(codes, front_buckets) * 4, w, table_policy);
+        r = bucket_match<WIDE>(w, codes, meta);
+        hit = meta_hit(meta);
+      }
+      if (r == kFound) {
+        park = false;
+        record_hit(p, hit, (uint64_t)read_idx, matched);
+      } else if (r == kUndecided) {
+        misc |= 1u << 17;  // the member may sit in a later bucket: the walk re-probes the front table
+      } else if (!g.with_perm) {
+        // no Permuter: the front table is the whole table, Centered is decided
+        misc |= 1u << 16;
+        park = park_misses;
+        if (!park) record_hit(p, kMiss, (uint64_t)read_idx, matched);
+      }
     }
+    if (p.debug & 4u) park = false;
     const uint32_t pm = __ballot_sync(0xffffffffu, park);
     if (pm) {
       if (park) {
-        // per-base masks of the window, then the oriented span [before][window][after]
-        uint32_t badw = 0, wildw = 0;
-        if (any) {
-#pragma unroll
-          for (int i = 0; i < NW; ++i) {
-            badw |= nonzero_bytes(xs[i]) << (4 * i);
-            const uint32_t xw = aw[i] ^ wild4;
-            wildw |= (nonzero_bytes(xw) ^ 0xFu) << (4 * i);
-          }
-          wildw &= badw;
-          if (p.reverse) {
-            badw = reverse_bits(badw, k);
-            wildw = reverse_bits(wildw, k);
-          }
-        }
-        // oriented neighbours: reverse swaps and complements them
-        const uint32_t prev = p.reverse ? b_after : b_before, next = p.reverse ? b_before : b_after;
-        const bool has_prev = p.reverse ? has_after : has_before, has_next = p.reverse ? has_before : has_after;
-        const uint32_t cflip = p.reverse ? 2u : 0u;
-        const bool prev_bad = !has_prev || !is_acgt((uint8_t)prev), next_bad = !has_next || !is_acgt((uint8_t)next);
         const uint32_t e = qn + __popc(pm & ((1u << lane) - 1));
-        q->codes[e] = (uint64_t)(code_of((uint8_t)prev) ^ cflip) | (codes << 2) |
-                      ((uint64_t)(code_of((uint8_t)next) ^ cflip) << (2 * k + 2));
-        q->bad[e] = (prev_bad ? 1u : 0u) | (badw << 1) | ((next_bad ? 1u : 0u) << (k + 1));
-        q->wild[e] = ((has_prev && prev == p.wild_byte) ? 1u : 0u) | (wildw << 1) |
-                     (((has_next && next == p.wild_byte) ? 1u : 0u) << (k + 1));
+#pragma unroll
+        for (int i = 0; i < NW; ++i) q->w[i][e] = aw[i];
+        q->misc[e] = misc;
         q->read[e] = read_idx;
-        q->first_pos[e] = any ? 0 : 1;  // Centered already probed and missed
       }
       qn += __popc(pm);
       __syncwarp();
       if (qn >= 32) {
         qn -= 32;
-        drain(qn, 32);
+        flush(qn, 32);
         __syncwarp();
       }
     }
   }
-  if (qn) drain(0, qn);
+  if (qn) flush(0, qn);
   flush_matched(p, matched);
+}
+
+// Pass 2: one thread per parked read, the full Counter::assign walk (walk_parked).  Plain
+// grid-stride kernel at full occupancy: the dependent table lookups of the rare reads are
+// hidden by thread-level parallelism instead of stalling the streaming warps.
+template <int NW, bool WIDE>
+__global__ void __launch_bounds__(256) count_parked_kernel(CountParams p) {
+  const WalkGeom g = make_geom(p);
+  const unsigned int n = *p.park_count;
+  uint32_t matched = 0;
+  for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const uint32_t* src = p.park_rec + e;
+    uint32_t aw[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) aw[i] = src[(size_t)i * p.park_cap];
+    const uint32_t misc = src[(size_t)NW * p.park_cap];
+    const uint32_t read = src[(size_t)(NW + 1) * p.park_cap];
+    const int32_t hit = walk_parked<NW, WIDE>(p.table, g, aw, misc);
+    record_hit(p, hit, (uint64_t)read, matched);
+  }
+  matched = __reduce_add_sync(0xffffffffu, matched);
+  if ((threadIdx.x & 31) == 0 && matched) atomicAdd(p.state + p.n_guides + 1, (unsigned long long)matched);
 }
 
 }  // namespace
@@ -390,6 +539,10 @@ struct sgc_counter {
   size_t stage_cap = 0, stage_off_cap = 0;
   cudaEvent_t copy_done[2] = {nullptr, nullptr}, kernel_done[2] = {nullptr, nullptr};
   uint64_t chunks_submitted = 0;
+  // parked-read records of the streaming kernel (pass 1 -> pass 2)
+  uint32_t* d_park = nullptr;
+  unsigned int* d_park_count = nullptr;
+  size_t park_cap = 0;  // entries
   sgc_launch_info last{};
 };
 
@@ -434,12 +587,12 @@ CountParams make_params(const sgc_counter* c, const uint8_t* d_lines, const uint
 struct StreamConfig {
   int warps = 0, stages = 0, ctas_per_sm = 0;
 };
-size_t stream_smem_bytes(const StreamConfig& c, uint32_t stage_bytes) {
-  return (size_t)c.warps * ((size_t)c.stages * stage_bytes + kMaxStages * sizeof(uint64_t) + sizeof(WarpQueue));
+size_t stream_smem_bytes(const StreamConfig& c, uint32_t stage_bytes, size_t queue_bytes) {
+  return (size_t)c.warps * ((size_t)c.stages * stage_bytes + kMaxStages * sizeof(uint64_t) + queue_bytes);
 }
 // Largest ring that fits: prefer 2 resident CTAs of 12 warps with >= 3 buffers per warp.
 // SGC_WARPS / SGC_STAGES / SGC_CTAS override the choice (tuning only).
-StreamConfig pick_stream_config(uint32_t stage_bytes) {
+StreamConfig pick_stream_config(uint32_t stage_bytes, size_t queue_bytes) {
   const size_t sm_budget = 227 * 1024;
   StreamConfig best{};
   const int want_warps = env_int("SGC_WARPS", 12), want_ctas = env_int("SGC_CTAS", 2);
@@ -448,7 +601,7 @@ StreamConfig pick_stream_config(uint32_t stage_bytes) {
     for (int stages = std::min(want_stages, kMaxStages); stages >= 2; --stages) {
       StreamConfig c{want_warps, stages, ctas};
       if (c.warps < 1 || c.warps > 12) c.warps = 12;
-      if ((stream_smem_bytes(c, stage_bytes) + 1024) * ctas <= sm_budget) {
+      if ((stream_smem_bytes(c, stage_bytes, queue_bytes) + 1024) * ctas <= sm_budget) {
         best = c;
         break;
       }
@@ -471,15 +624,33 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
   const uint32_t tile_bytes = kWarpReads * stride;
   const uint32_t stage_bytes = (tile_bytes + 48 + 15) & ~15u;  // +48: span words may run past the tile
   const bool stageable = d_off == nullptr && ((uintptr_t)d_lines & 15u) == 0 && stride >= read_len;
-  StreamConfig cfg = stageable ? pick_stream_config(stage_bytes) : StreamConfig{};
+  const bool nw5 = !c->lib->wide && c->lib->k > 16;
+  const size_t queue_bytes = nw5 ? sizeof(WarpQueueT<5>) : sizeof(WarpQueueT<8>);
+  StreamConfig cfg = stageable ? pick_stream_config(stage_bytes, queue_bytes) : StreamConfig{};
   // whole tiles only, and never a bulk copy that would run past n_bytes
   uint64_t n_wtiles = stageable && cfg.stages ? std::min(n_reads / kWarpReads, n_bytes / tile_bytes) : 0;
   n_wtiles = std::min<uint64_t>(n_wtiles, 0xFFFFFFFFull / kWarpReads);
   if (n_wtiles > 0) {
-    const bool nw5 = c->lib->k > 16 && c->lib->k <= 20;
     auto kernel = c->lib->wide ? count_stream_kernel<8, true>
                                : (nw5 ? count_stream_kernel<5, false> : count_stream_kernel<8, false>);
-    const size_t smem = stream_smem_bytes(cfg, stage_bytes);
+    auto parked = c->lib->wide ? count_parked_kernel<8, true>
+                               : (nw5 ? count_parked_kernel<5, false> : count_parked_kernel<8, false>);
+    // worst case every read is parked: (NW + 2) words per read
+    const size_t need = n_wtiles * kWarpReads;
+    const size_t rec_words = (nw5 ? 5 : 8) + 2;
+    if (need > c->park_cap) {
+      SGC_CUDA_TRY(cudaStreamSynchronize(stream));
+      cudaFree(c->d_park);
+      c->d_park = nullptr;
+      SGC_CUDA_TRY(cudaMalloc(&c->d_park, need * rec_words * sizeof(uint32_t)));
+      c->park_cap = need;
+    }
+    if (!c->d_park_count) SGC_CUDA_TRY(cudaMalloc(&c->d_park_count, sizeof(unsigned int)));
+    SGC_CUDA_TRY(cudaMemsetAsync(c->d_park_count, 0, sizeof(unsigned int), stream));
+    p.park_rec = c->d_park;
+    p.park_count = c->d_park_count;
+    p.park_cap = (uint32_t)c->park_cap;
+    const size_t smem = stream_smem_bytes(cfg, stage_bytes, queue_bytes);
     SGC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint64_t grid = (uint64_t)c->lib->sm_count * cfg.ctas_per_sm;  // persistent: every CTA resident
     const uint64_t ctas_needed = (n_wtiles + cfg.warps - 1) / cfg.warps;
@@ -488,6 +659,11 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
     p.first_read = 0;
     kernel<<<(unsigned)grid, cfg.warps * 32, smem, stream>>>(p, n_wtiles, cfg.stages, stage_bytes);
     SGC_CUDA_TRY(cudaGetLastError());
+    if (!(p.debug & 4u)) {
+      parked<<<c->lib->sm_count * 8, 256, 0, stream>>>(p);
+      SGC_CUDA_TRY(cudaGetLastError());
+      c->last.launches_total += 1;
+    }
     done = n_wtiles * kWarpReads;
     c->last.grid = (uint32_t)grid;
     c->last.block = cfg.warps * 32;
@@ -578,6 +754,8 @@ void sgc_counter_destroy(sgc_counter* c) {
     if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
     if (c->kernel_done[i]) cudaEventDestroy(c->kernel_done[i]);
   }
+  cudaFree(c->d_park);
+  cudaFree(c->d_park_count);
   if (c->own_state) cudaFree(c->d_state);
   delete c;
 }

@@ -50,10 +50,16 @@ struct sgc_library {
   bool wide = false;
   uint64_t* d_slots = nullptr;
   uint32_t n_buckets = 0;
+  uint64_t* d_front = nullptr;  // library members only (== d_slots when there is no Permuter)
+  uint32_t front_buckets = 0;
+  uint64_t* d_bloom = nullptr;  // Bloom filter over the main table's keys (Permuter only)
+  uint32_t n_bloom_words = 0;
   uint64_t* d_keys = nullptr;      // n packed guides, library order
   uint32_t* d_lib_hist = nullptr;  // k*4 positional counts over guides 1..n-1 (offsetter.rs:190-191)
   int sm_count = 0;
   sgc_library_info info{};
 
-  sgc::TableView view() const { return sgc::TableView{d_slots, n_buckets, k, wide ? 1u : 0u}; }
+  sgc::TableView view() const {
+    return sgc::TableView{d_slots, n_buckets, k, wide ? 1u : 0u, d_front, front_buckets, d_bloom, n_bloom_words};
+  }
 };

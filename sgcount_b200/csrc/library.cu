@@ -12,6 +12,7 @@
 //      marked AMBIG in place                                                    (insert_variants)
 // Variants with an 'N' are not stored: a read window with one N is answered by four member
 // probes (common.cuh window_lookup), which is exactly the set of parents of that token.
+#include <algorithm>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -173,6 +174,25 @@ __global__ void table_stats_kernel(const uint64_t* __restrict__ slots, size_t n_
   }
 }
 
+// one thread per slot: every occupied key sets its four bits
+__global__ void bloom_build_kernel(const uint64_t* __restrict__ slots, size_t n_slots, bool wide,
+                                   unsigned long long* bloom, uint32_t n_words) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  uint64_t key;
+  if (wide) {
+    if (slots[2 * i + 1] == 0) return;
+    key = slots[2 * i];
+  } else {
+    if (slots[i] == 0) return;
+    key = slots[i] & kKeyMaskNarrow;
+  }
+  uint32_t word;
+  uint64_t mask;
+  bloom_locate(key, n_words, word, mask);
+  atomicOr(bloom + word, (unsigned long long)mask);
+}
+
 // composed lookup of raw k-byte tokens (sgc_library_lookup)
 __global__ void lookup_tokens_kernel(TableView t, bool with_perm, const uint8_t* __restrict__ tokens,
                                      uint64_t n_tokens, int32_t* __restrict__ idx_out, uint8_t* __restrict__ kind_out) {
@@ -237,6 +257,8 @@ int sgc_host_free(void* ptr) {
 void sgc_library_destroy(sgc_library* lib) {
   if (!lib) return;
   DeviceGuard g(lib->device);
+  if (lib->d_front != lib->d_slots) cudaFree(lib->d_front);
+  cudaFree(lib->d_bloom);
   cudaFree(lib->d_slots);
   cudaFree(lib->d_keys);
   cudaFree(lib->d_lib_hist);
@@ -314,6 +336,32 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
       insert_variants_kernel<2><<<blocks_for(nv, T), T>>>(lib->d_slots, lib->n_buckets, lib->d_keys, n, k, d_st.p);
   }
   table_stats_kernel<<<blocks_for(n_slots, T), T>>>(lib->d_slots, n_slots, lib->wide, d_st.p);
+  // front table: members only, <= 25 % load (skipped when the main table already is that)
+  if (lib->with_perm) {
+    uint64_t fb = ((uint64_t)n * 4 + per_bucket - 1) / per_bucket;
+    if (fb < 64) fb = 64;
+    lib->front_buckets = (uint32_t)fb;
+    const size_t f_slots = (size_t)fb * per_bucket;
+    SGC_CUDA_TRY(cudaMalloc(&lib->d_front, (size_t)fb * 32));
+    if (lib->wide) {
+      wide_init_kernel<<<blocks_for(f_slots, T), T>>>(lib->d_front, f_slots);
+      insert_exact_kernel<1><<<blocks_for(n, T), T>>>(lib->d_front, lib->front_buckets, lib->d_keys, n, d_st.p);
+      insert_exact_kernel<2><<<blocks_for(n, T), T>>>(lib->d_front, lib->front_buckets, lib->d_keys, n, d_st.p);
+    } else {
+      SGC_CUDA_TRY(cudaMemsetAsync(lib->d_front, 0, (size_t)fb * 32, 0));
+      insert_exact_kernel<0><<<blocks_for(n, T), T>>>(lib->d_front, lib->front_buckets, lib->d_keys, n, d_st.p);
+    }
+    // Bloom filter: one 64-bit word per 4 expected keys (2 bytes per key, false positives < 1 %)
+    lib->n_bloom_words = (uint32_t)std::max<uint64_t>(entries / 4, 64);
+    SGC_CUDA_TRY(cudaMalloc(&lib->d_bloom, (size_t)lib->n_bloom_words * 8));
+    SGC_CUDA_TRY(cudaMemsetAsync(lib->d_bloom, 0, (size_t)lib->n_bloom_words * 8, 0));
+    bloom_build_kernel<<<blocks_for(n_slots, T), T>>>(lib->d_slots, n_slots, lib->wide,
+                                                      reinterpret_cast<unsigned long long*>(lib->d_bloom),
+                                                      lib->n_bloom_words);
+  } else {
+    lib->d_front = lib->d_slots;
+    lib->front_buckets = lib->n_buckets;
+  }
   // library positional histogram for the offset detector: records 1..n-1 (offsetter.rs:57,190-191)
   SGC_CUDA_TRY(cudaMemsetAsync(lib->d_lib_hist, 0, (size_t)k * 4 * sizeof(uint32_t), 0));
   if (n > 1) {
@@ -346,7 +394,8 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   lib->info.n_variants = st.n_variants;
   lib->info.n_ambiguous = st.n_ambiguous;
   lib->info.n_slots = n_slots;
-  lib->info.table_bytes = table_bytes;
+  lib->info.table_bytes =
+      table_bytes + (lib->with_perm ? (size_t)lib->front_buckets * 32 + (size_t)lib->n_bloom_words * 8 : 0);
   lib->info.build_ms = ms;
   cleanup.l = nullptr;
   *out = lib;
