@@ -214,6 +214,11 @@ def run_gpu(args):
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # Everything timed runs on ONE explicit (non-default) stream: the counter's kernels are
+    # launched on it through the C ABI and the torch events / NCCL collectives are recorded on
+    # it, so the CUDA events bracket exactly the launches they are meant to time.
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -248,7 +253,8 @@ def run_gpu(args):
     torch.cuda.synchronize()
 
     state = torch.zeros(N_GUIDES + 2, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = work_stream.cuda_stream
+    assert stream != 0 and torch.cuda.current_stream().cuda_stream == stream
     counter = sg.Counter(library, permuter, sg.Offset.Forward(OFFSET), True, _cabi.RC_BITTRICK, stream=stream,
                          d_state=state.data_ptr())
 

@@ -57,9 +57,12 @@ class Sample:
                                          int(reverse), C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            _load().sgs_sample_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                _load().sgs_sample_destroy(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     def fill_host(self, first: int, n_reads: int, out: Optional[np.ndarray] = None, n_threads: int = 0) -> np.ndarray:
         if out is None:
