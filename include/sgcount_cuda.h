@@ -85,9 +85,10 @@ typedef struct sgc_library_info {
   int32_t device;
   uint64_t n_variants;   /* one-mismatch ACGT variants that map to exactly one parent   */
   uint64_t n_ambiguous;  /* ACGT variants shared by >= 2 parents (the reference's _null) */
-  uint64_t n_slots;      /* slots in the device table                                    */
-  uint64_t table_bytes;
+  uint64_t n_slots;      /* slots of one front table (members only)                      */
+  uint64_t table_bytes;  /* seed directories + postings + both front tables              */
   double build_ms;       /* device time of the build kernels                             */
+  uint64_t front_left_out; /* members (x2 orientations) resolved through the seed index only */
 } sgc_library_info;
 int sgc_library_get_info(const sgc_library*, sgc_library_info* out);
 

@@ -46,6 +46,7 @@ class LibraryInfo(C.Structure):
         ("n_slots", C.c_uint64),
         ("table_bytes", C.c_uint64),
         ("build_ms", C.c_double),
+        ("front_left_out", C.c_uint64),
     ]
 
 

@@ -1,20 +1,40 @@
-// common.cuh — 2-bit encoding, the unified device table and the per-window decision
+// common.cuh — 2-bit encoding, the device-side library structures and the per-window decision
 // procedure shared by every kernel of libsgcount_cuda.
 //
 // Encoding: code(c) = (c >> 1) & 3 for c in {A,C,G,T}: A=0 C=1 T=2 G=3; complement = code ^ 2.
-// A token of k bases is the integer  sum_j code(tok[j]) << 2j  (base 0 in the low bits).
+// The NATURAL key of a token of k bases is  sum_j code(tok[j]) << 2j  (base 0 in the low bits).
 //
-// Table: ONE open-addressing table holds the library members and, when the Permuter is on,
-// every one-mismatch ACGT variant of every member.  The reference probes Library first and
-// Permuter second at each position (counter.rs:111-117); because a variant that equals a
-// library member is unreachable in the reference and never stored here, a
-// single probe of the unified table answers both.  A variant generated by two or more
-// parents stays in the table with the AMBIG index: that is the reference's `_null` set
-// (permutes.rs:149-152), kept so probe chains are never broken.
+// Two structures stand for the reference's Library + Permuter maps (library.rs:9-62,
+// permutes.rs:34-158).  Both hold the n library members only, so they stay a few MB and live
+// in L2 whatever the read stream does; the 80 n variant strings the reference materialises
+// are never stored.
 //
-// Slot (64 bit):  [63] occupied  [62] variant  [61:40] guide index (22 bit)  [39:0] key (k <= 20)
-// Wide slot (2 x 64 bit, k = 21..30): word0 = key, word1 = same meta in bits [63:40].
-// Bucket = one 32-byte sector (4 narrow slots / 2 wide slots); linear probing by bucket.
+// 1. SEED INDEX (exact semantics of the whole lookup; every kernel's slow path)
+//    The k bases are cut into kSeeds = 3 contiguous parts.  A token within Hamming distance 1
+//    of a member differs from it inside at most one part, so it agrees with the member on the
+//    COMPLEMENT of that part.  Seed i is that complement (13-14 bases at k = 20): directory i
+//    hashes the token with part i masked out to a bucket (start | count) of postings (member
+//    key + guide index) sorted by bucket.  A member at distance 1 whose difference lies in part
+//    i sits in list i and in no other list's matching set, the member itself (distance 0) sits
+//    in all of them.  One window costs three directory loads plus about one posting load:
+//      - a posting equal to the token                          -> library member (library.rs:34-46)
+//      - else exactly ONE member at Hamming distance 1         -> that member (the Permuter's
+//        map entry, permutes.rs:127-144); two or more          -> the Permuter's `_null` set
+//        (permutes.rs:149-152), no match.  SURVEY.md A.2 shows this closed form equals the
+//        reference's insertion-order-dependent build in every observable lookup.
+//      - a token with exactly one N: its parents are the members equal to it everywhere else
+//        (permutes.rs:3 puts N in the lexicon); they all sit in the list of the part the N is in.
+//    Buckets are hashed, so a list can hold members of other seeds; every posting is checked
+//    against the seed before it counts.
+// 2. FRONT TABLE (accelerator of the streaming kernel's common case, members only)
+//    One 32-byte bucket per hash value, no probing chain: a member that does not fit its home
+//    bucket is left out and the bucket is flagged, and a flagged miss is re-resolved through
+//    the seed index.  Keys are in the INTERLEAVED layout the streaming kernel packs for free:
+//    window word i (bases 4i..4i+3, one per byte) contributes (word >> 1) & 0x03030303 shifted
+//    left by 2 (i mod 4) into `lo` (i < 4) or `hi` (i >= 4).
+//      narrow slot (k <= 20), 64 bit: [63:42] guide index [41] occupied [40] bucket flag
+//                                      [39:32] hi gathered to 8 bits [31:0] lo
+//      wide slot (k = 21..30), 2 x 64 bit: word0 = hi << 32 | lo, word1 = same meta in [63:40]
 #pragma once
 
 #include <cuda_runtime.h>
@@ -24,60 +44,43 @@ namespace sgc {
 
 constexpr uint32_t kMaxK = 30;
 constexpr uint32_t kNarrowMaxK = 20;
-constexpr int kKeyBitsNarrow = 40;
-constexpr uint64_t kKeyMaskNarrow = (1ull << kKeyBitsNarrow) - 1;
-constexpr uint64_t kOccupied = 1ull << 63;
-constexpr uint64_t kVariant = 1ull << 62;
-constexpr uint32_t kIdxMask = 0x3FFFFFu;
-constexpr uint32_t kAmbig = kIdxMask;  // index of a variant shared by >= 2 parents
-constexpr int kMetaShift = 40;
-
-// results of a table probe
+constexpr int kSeeds = 3;
 constexpr int32_t kMiss = -1;
 
-struct TableView {
-  const uint64_t* __restrict__ slots;  // n_buckets * 4 words
-  uint32_t n_buckets;
-  uint32_t k;
-  uint32_t wide;  // 0: 4 slots/bucket, 1: 2 two-word slots/bucket
-  // Front table: the library members alone, a few MB at <= 25 % load so it stays L2 resident
-  // whatever the streaming traffic does.  Most reads are exact and end here; only the rest
-  // pays for the big unified table.  Without a Permuter it is the main table itself.
-  const uint64_t* __restrict__ front_slots;
-  uint32_t front_buckets;
-  // Bloom filter over every key of the main table (members, variants, ambiguous): 64-bit words
-  // shared by ~4 keys, 4 bits per key.  Two bytes per key, so it is L2 resident even when the
-  // main table is not; "absent" answers (reads that match nothing) never leave L2.
-  const uint64_t* __restrict__ bloom;  // n_bloom_words; NULL = no filter
-  uint32_t n_bloom_words;
+// directory entry: [21:0] first posting, [31:22] number of postings, saturating (the exact
+// count of a saturated bucket is in LibView::dir_count)
+constexpr uint32_t kDirStartMask = 0x3FFFFFu;
+constexpr int kDirCountShift = 22;
+constexpr uint32_t kDirCountSat = 1023u;
+
+// narrow posting: [39:0] natural key, [61:40] guide index.  Wide posting: {natural key, guide index}.
+constexpr int kPostIdxShift = 40;
+constexpr uint64_t kPostKeyMask = (1ull << kPostIdxShift) - 1;
+
+// front-table meta bits (bit positions inside the 64-bit slot / meta word)
+constexpr uint64_t kFrontFlag = 1ull << 40;      // set in slot 0: some member of this bucket was left out
+constexpr uint64_t kFrontOccupied = 1ull << 41;
+constexpr int kFrontIdxShift = 42;
+
+struct LibView {
+  uint32_t k, n;
+  uint32_t wide;                  // k > 20: 16-byte postings and front slots
+  uint32_t part_end[kSeeds];      // part i = bases [part_end[i-1], part_end[i])
+  uint64_t keep[kSeeds];          // key bits seed i keeps (everything but part i)
+  const uint32_t* __restrict__ dir[kSeeds];        // 1 << dir_bits entries each
+  const uint32_t* __restrict__ dir_count[kSeeds];  // exact bucket sizes (read for saturated entries only)
+  const uint64_t* __restrict__ post[kSeeds];       // n postings sorted by bucket (2 words each when wide)
+  uint32_t dir_shift;                              // bucket = seed_hash >> dir_shift
+  const uint64_t* __restrict__ front;      // forward orientation (keys of the guides as written)
+  const uint64_t* __restrict__ front_rev;  // keys of the guides' reverse complements
+  uint32_t front_shift;                    // bucket = front_hash >> front_shift
 };
 
-// word index and the 4-bit mask of a key
-__host__ __device__ __forceinline__ void bloom_locate(uint64_t key, uint32_t n_words, uint32_t& word, uint64_t& mask) {
-  uint32_t a = (uint32_t)key * 0xCC9E2D51u ^ ((uint32_t)(key >> 32) + 0x1B873593u) * 0xE6546B64u;
-  a ^= a >> 16;
-  a *= 0x85EBCA6Bu;
-  a ^= a >> 13;
-  word = (uint32_t)(((uint64_t)a * n_words) >> 32);
-  uint32_t b = a * 0xC2B2AE35u;
-  b ^= b >> 16;
-  mask = (1ull << (b & 63u)) | (1ull << ((b >> 6) & 63u)) | (1ull << ((b >> 12) & 63u)) | (1ull << ((b >> 18) & 63u));
-}
-
-__host__ __device__ __forceinline__ uint64_t make_meta(uint32_t idx, bool variant) {
-  return kOccupied | (variant ? kVariant : 0ull) | ((uint64_t)idx << kMetaShift);
-}
-__host__ __device__ __forceinline__ uint32_t meta_idx(uint64_t w) { return (uint32_t)(w >> kMetaShift) & kIdxMask; }
-__host__ __device__ __forceinline__ bool meta_variant(uint64_t w) { return (w & kVariant) != 0; }
-
-// 32-bit multiply-xorshift hash of the packed key, range-reduced with a multiply-high
-// (no power-of-two table sizes needed)
-__host__ __device__ __forceinline__ uint32_t bucket_of(uint64_t key, uint32_t n_buckets) {
-  uint32_t h = (uint32_t)key * 0x9E3779B1u ^ ((uint32_t)(key >> 32) + 0x7F4A7C15u) * 0x85EBCA77u;
+// bucket hash of a masked natural key (top bits are used)
+__host__ __device__ __forceinline__ uint32_t seed_hash(uint64_t mkey) {
+  uint32_t h = (uint32_t)mkey * 0x9E3779B1u + (uint32_t)(mkey >> 32) * 0x85EBCA77u;
   h ^= h >> 15;
-  h *= 0x2C1B3C6Du;
-  h ^= h >> 13;
-  return (uint32_t)(((uint64_t)h * n_buckets) >> 32);
+  return h * 0x2C1B3C6Du;
 }
 
 __host__ __device__ __forceinline__ bool is_acgt(uint8_t c) {
@@ -85,135 +88,164 @@ __host__ __device__ __forceinline__ bool is_acgt(uint8_t c) {
 }
 __host__ __device__ __forceinline__ uint32_t code_of(uint8_t c) { return (c >> 1) & 3u; }
 
+// bucket of an interleaved key: multiplicative hash, top bits
+__host__ __device__ __forceinline__ uint32_t front_hash(uint32_t lo, uint32_t hi) {
+  return lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+}
+
+// Interleaved key of a natural key (build side).  Narrow: hi is the gathered 8-bit form.
+__host__ __device__ __forceinline__ void interleave_key(uint64_t key, uint32_t k, bool wide, uint32_t& lo, uint32_t& hi) {
+  lo = 0;
+  hi = 0;
+  for (uint32_t j = 0; j < k; ++j) {
+    const uint32_t c = (uint32_t)(key >> (2 * j)) & 3u;
+    const uint32_t word = j >> 2, byte = j & 3u;
+    if (word < 4)
+      lo |= c << (8 * byte + 2 * word);
+    else if (wide)
+      hi |= c << (8 * byte + 2 * (word - 4));
+    else
+      hi |= c << (2 * byte);  // word 4 only (k <= 20)
+  }
+}
+
 #ifdef __CUDACC__
 
-// one 32-byte bucket = one sector, fetched with a single 256-bit read-only load (LDG.256)
-__device__ __forceinline__ void load_bucket(const uint64_t* p, uint64_t (&w)[4]) {
-  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p));
+__device__ __forceinline__ uint64_t ldg_u64(const uint64_t* p, uint64_t policy) {
+  uint64_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+  return v;
 }
-// the same with an L2 eviction policy (the table is the only data worth keeping in L2)
+__device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p, uint64_t policy) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+  return v;
+}
+// one 32-byte bucket = one sector, fetched with a single 256-bit read-only load (LDG.256)
 __device__ __forceinline__ void load_bucket(const uint64_t* p, uint64_t (&w)[4], uint64_t policy) {
   asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
                : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
                : "l"(p), "l"(policy));
 }
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 
-// Probe the unified table.  Returns the slot's meta word (occupied bit set) or 0 when the
-// key is absent.
-template <bool WIDE>
-__device__ __forceinline__ uint64_t table_find_t(const uint64_t* __restrict__ slots, uint32_t n_buckets, uint64_t key) {
-  uint32_t b = bucket_of(key, n_buckets);
-  for (;;) {
-    uint64_t w[4];
-    load_bucket(slots + (size_t)b * 4, w);
-    if (!WIDE) {
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        if (w[s] == 0) return 0;
-        if (((w[s] ^ key) & kKeyMaskNarrow) == 0) return w[s];
-      }
+// x = XOR of two natural keys: true iff they differ in exactly one base
+__device__ __forceinline__ bool one_base_differs(uint64_t x) {
+  const uint64_t y = (x | (x >> 1)) & 0x5555555555555555ull;
+  return y != 0 && (y & (y - 1)) == 0;
+}
+
+// Walks the postings of one directory entry.  `visit(key, idx)` returning true stops the walk.
+template <bool WIDE, typename F>
+__device__ __forceinline__ void walk_postings(const LibView& v, int seed, uint32_t bucket, uint32_t entry,
+                                              uint64_t policy, F&& visit) {
+  const uint32_t start = entry & kDirStartMask;
+  uint32_t cnt = entry >> kDirCountShift;
+  if (cnt == kDirCountSat) cnt = v.dir_count[seed][bucket];
+  const uint64_t* __restrict__ post = v.post[seed];
+#pragma unroll 1
+  for (uint32_t c = 0; c < cnt; ++c) {
+    uint64_t key;
+    uint32_t idx;
+    if (WIDE) {
+      key = ldg_u64(post + 2 * (size_t)(start + c), policy);
+      idx = (uint32_t)ldg_u64(post + 2 * (size_t)(start + c) + 1, policy);
     } else {
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        if (w[2 * s + 1] == 0) return 0;
-        if (w[2 * s] == key) return w[2 * s + 1];
-      }
+      const uint64_t w = ldg_u64(post + start + c, policy);
+      key = w & kPostKeyMask;
+      idx = (uint32_t)(w >> kPostIdxShift);
     }
-    b = (b + 1 == n_buckets) ? 0 : b + 1;
-  }
-}
-__device__ __forceinline__ uint64_t table_find(const TableView& t, uint64_t key) {
-  return t.wide ? table_find_t<true>(t.slots, t.n_buckets, key) : table_find_t<false>(t.slots, t.n_buckets, key);
-}
-
-// guide index a probe result stands for, or kMiss (absent key, or a variant shared by >= 2 parents)
-__device__ __forceinline__ int32_t meta_hit(uint64_t m) {
-  if (m == 0) return kMiss;
-  const uint32_t idx = meta_idx(m);
-  return (meta_variant(m) && idx == kAmbig) ? kMiss : (int32_t)idx;
-}
-
-// One-bucket probe: 1 = found (meta set), 0 = the key is definitely absent (the bucket has a
-// free slot), 2 = undecided (bucket full, the chain continues in the next bucket).
-constexpr int kAbsent = 0, kFound = 1, kUndecided = 2;
-template <bool WIDE>
-__device__ __forceinline__ int bucket_match(const uint64_t (&w)[4], uint64_t key, uint64_t& meta) {
-  meta = 0;
-  if (!WIDE) {
-    bool free_slot = false;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      if (((w[s] ^ key) & kKeyMaskNarrow) == 0 && w[s] != 0) meta = w[s];
-      free_slot |= w[s] == 0;
-    }
-    return meta ? kFound : (free_slot ? kAbsent : kUndecided);
-  } else {
-    bool free_slot = false;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (w[2 * s] == key && w[2 * s + 1] != 0) meta = w[2 * s + 1];
-      free_slot |= w[2 * s + 1] == 0;
-    }
-    return meta ? kFound : (free_slot ? kAbsent : kUndecided);
+    if (visit(key, idx)) break;
   }
 }
 
-// Decision for ONE window, given its packed key, the number of bytes in
+// Decision for ONE window, given its natural key, the number of bytes in
 // it that are not A/C/G/T (`nbad`), the position of the single bad byte (`bad_pos`) and
 // whether that byte is the wildcard ('N' as seen by the lookup).
-//   nbad == 0: the token is a library member or a stored unambiguous variant -> its index
-//   nbad == 1 and wildcard and permuter on: the parents are the library members equal to the
-//              token with the wildcard replaced by A/C/G/T -> match iff exactly one exists
-//   otherwise: no match at this position
-// Returns the guide index or kMiss; *kind = 1 library member, 2 variant.
-__device__ __forceinline__ int32_t window_lookup(const TableView& t, bool with_perm, uint64_t key, int nbad,
-                                                 int bad_pos, bool bad_is_wild, int* kind) {
+// Returns the guide index or kMiss; *kind = 1 library member, 2 one-mismatch variant.
+template <bool WIDE>
+__device__ __forceinline__ int32_t window_lookup_t(const LibView& v, bool with_perm, uint64_t key, int nbad,
+                                                   int bad_pos, bool bad_is_wild, int* kind, uint64_t policy) {
   if (nbad == 0) {
-    uint64_t m = table_find(t, key);
-    if (m == 0) return kMiss;
-    uint32_t idx = meta_idx(m);
-    if (meta_variant(m)) {
-      if (idx == kAmbig) return kMiss;
-      if (kind) *kind = 2;
-      return (int32_t)idx;
+    // the three directory entries are fetched together; without a Permuter only the first is
+    // needed (a member sits in every list)
+    uint32_t bucket[kSeeds], entry[kSeeds];
+#pragma unroll
+    for (int i = 0; i < kSeeds; ++i) {
+      bucket[i] = seed_hash(key & v.keep[i]) >> v.dir_shift;
+      entry[i] = (i == 0 || with_perm) ? ldg_u32(v.dir[i] + bucket[i], policy) : 0u;
     }
-    if (kind) *kind = 1;
-    return (int32_t)idx;
+    int32_t found = kMiss;
+    int parents = 0;
+    bool member = false;
+#pragma unroll 1
+    for (int i = 0; i < kSeeds; ++i) {
+      const uint32_t e = i == 0 ? entry[0] : (i == 1 ? entry[1] : entry[2]);
+      const uint32_t b = i == 0 ? bucket[0] : (i == 1 ? bucket[1] : bucket[2]);
+      const uint64_t keep = v.keep[i];
+      walk_postings<WIDE>(v, i, b, e, policy, [&](uint64_t mk, uint32_t idx) {
+        const uint64_t x = mk ^ key;
+        if ((x & keep) != 0) return false;  // another seed hashed to this bucket
+        if (x == 0) {                       // Library::contains (counter.rs:111-112)
+          member = true;
+          found = (int32_t)idx;
+          return true;
+        }
+        if (one_base_differs(x)) {  // the difference lies inside part i
+          ++parents;
+          found = (int32_t)idx;
+        }
+        return false;
+      });
+      if (member || !with_perm) break;
+    }
+    if (member) {
+      if (kind) *kind = 1;
+      return found;
+    }
+    if (with_perm && parents == 1) {  // Permuter::contains -> Library::alias (counter.rs:113-116)
+      if (kind) *kind = 2;
+      return found;
+    }
+    return kMiss;  // no parent, or the Permuter's null set (permutes.rs:149-152)
   }
   if (nbad == 1 && bad_is_wild && with_perm) {
-    // parents = library members equal to the token with the wildcard replaced: the front table
-    // (members only) answers it; the four buckets are fetched together
-    const uint64_t base = key & ~(3ull << (2 * bad_pos));
-    int hits = 0;
+    // parents = members equal to the token everywhere but at the wildcard: the list of the
+    // part the wildcard is in
+    int i = 0;
+    while (i < kSeeds - 1 && (uint32_t)bad_pos >= v.part_end[i]) ++i;
+    const uint64_t hole = ~(3ull << (2 * bad_pos));
+    const uint32_t b = seed_hash(key & v.keep[i]) >> v.dir_shift;
+    const uint32_t e = ldg_u32(v.dir[i] + b, policy);
     int32_t found = kMiss;
-#pragma unroll
-    for (int pair = 0; pair < 2; ++pair) {  // two buckets in flight at a time
-      uint64_t w[2][4];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint64_t kc = base | ((uint64_t)(2 * pair + c) << (2 * bad_pos));
-        load_bucket(t.front_slots + (size_t)bucket_of(kc, t.front_buckets) * 4, w[c]);
+    int parents = 0;
+    walk_postings<WIDE>(v, i, b, e, policy, [&](uint64_t mk, uint32_t idx) {
+      if (((mk ^ key) & hole) == 0) {
+        ++parents;
+        found = (int32_t)idx;
       }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint64_t kc = base | ((uint64_t)(2 * pair + c) << (2 * bad_pos));
-        uint64_t m;
-        const int r = t.wide ? bucket_match<true>(w[c], kc, m) : bucket_match<false>(w[c], kc, m);
-        if (r == kUndecided)
-          m = t.wide ? table_find_t<true>(t.front_slots, t.front_buckets, kc)
-                     : table_find_t<false>(t.front_slots, t.front_buckets, kc);
-        if (m != 0 && !meta_variant(m)) {
-          ++hits;
-          found = (int32_t)meta_idx(m);
-        }
-      }
-    }
-    if (hits == 1) {
+      return false;
+    });
+    if (parents == 1) {
       if (kind) *kind = 2;
       return found;
     }
   }
   return kMiss;
+}
+__device__ __forceinline__ int32_t window_lookup(const LibView& v, bool with_perm, uint64_t key, int nbad, int bad_pos,
+                                                 bool bad_is_wild, int* kind, uint64_t policy) {
+  return v.wide ? window_lookup_t<true>(v, with_perm, key, nbad, bad_pos, bad_is_wild, kind, policy)
+                : window_lookup_t<false>(v, with_perm, key, nbad, bad_pos, bad_is_wild, kind, policy);
 }
 
 // A span of up to 32 consecutive bases around the guide window, packed from the read in
@@ -233,21 +265,20 @@ __device__ __forceinline__ uint64_t revcomp_codes(uint64_t x, int m) {
 }
 __device__ __forceinline__ uint32_t reverse_bits(uint32_t x, int m) { return __brev(x) >> (32 - m); }
 
-// The per-read walk of Counter::assign (counter.rs:96-140) over a span that starts at
-// oriented position `span_lo` = max(offset,1)-1 ... see count.cu for how spans are cut.
+// The per-read walk of Counter::assign (counter.rs:96-140) over a span.
 //   n        : read length
 //   offset   : Offset index;  recursion: Centered -> Plus -> Minus, else Null only
 // The span must cover oriented positions [offset-1, offset+k+1) (clipped to the read);
 // `span_base` is the oriented position of span base 0.
-// `first_pos` > 0 resumes the walk after positions a caller already tried and missed.
-__device__ __forceinline__ int32_t assign_span(const TableView& t, bool with_perm, const Span& sp, int span_base,
-                                               int n, int offset, bool recursion, int* kind, int first_pos = 0) {
-  const int k = (int)t.k;
-  const uint64_t kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
-  const uint32_t wmask = (k == 32) ? ~0u : ((1u << k) - 1);
+template <bool WIDE>
+__device__ __forceinline__ int32_t assign_span_t(const LibView& v, bool with_perm, const Span& sp, int span_base, int n,
+                                                 int offset, bool recursion, int* kind, uint64_t policy) {
+  const int k = (int)v.k;
+  const uint64_t kmask = (1ull << (2 * k)) - 1;
+  const uint32_t wmask = (1u << k) - 1;
   const int npos = recursion ? 3 : 1;
 #pragma unroll 1
-  for (int p = first_pos; p < npos; ++p) {
+  for (int p = 0; p < npos; ++p) {
     // Centered/Null: offset; Plus: offset+1; Minus: offset-1 (counter.rs:164-174)
     int lo;
     if (p == 0) {
@@ -269,10 +300,16 @@ __device__ __forceinline__ int32_t assign_span(const TableView& t, bool with_per
       bad_pos = __ffs(badw) - 1;
       wild = ((sp.wild >> sh) >> bad_pos) & 1u;
     }
-    int32_t hit = window_lookup(t, with_perm, key, nbad, bad_pos, wild, kind);
+    if (nbad > 1 || (nbad == 1 && !(wild && with_perm))) continue;  // a lookup miss, not a trim failure
+    const int32_t hit = window_lookup_t<WIDE>(v, with_perm, key, nbad, bad_pos, wild, kind, policy);
     if (hit != kMiss) return hit;
   }
   return kMiss;
+}
+__device__ __forceinline__ int32_t assign_span(const LibView& v, bool with_perm, const Span& sp, int span_base, int n,
+                                               int offset, bool recursion, int* kind, uint64_t policy) {
+  return v.wide ? assign_span_t<true>(v, with_perm, sp, span_base, n, offset, recursion, kind, policy)
+                : assign_span_t<false>(v, with_perm, sp, span_base, n, offset, recursion, kind, policy);
 }
 
 #endif  // __CUDACC__

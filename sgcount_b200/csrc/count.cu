@@ -2,14 +2,19 @@
 //
 // Replaces /root/reference/src/counter.rs:36-236 (Counter::new/count/assign/bounds/trim_*).
 //
-// Two kernels share one decision procedure (common.cuh assign_span):
-//   count_stream_kernel  : fixed-stride sequence lines.  Persistent warps stream tiles of reads
-//                          HBM -> shared memory with 1-D bulk async copies (TMA engine,
-//                          cp.async.bulk + mbarrier complete_tx) through a multi-stage ring;
-//                          each thread lifts the 4-byte words that cover its read's guide
-//                          span out of shared memory, the stage is handed back to the copy
-//                          engine at once, and the table probe + count atomics run from
-//                          registers while the next tiles are in flight.
+//   count_stream_kernel  : fixed-stride sequence lines.  Persistent warps stream tiles of 32
+//                          reads HBM -> shared memory with 1-D bulk async copies (TMA engine,
+//                          cp.async.bulk + mbarrier complete_tx) through a warp-private
+//                          multi-stage ring.  Each lane lifts the words that cover its read's
+//                          guide window out of shared memory, the stage goes straight back to
+//                          the copy engine, and everything else runs from registers:
+//                            fast path  window -> interleaved 2-bit key + ASCII validity ->
+//                                       ONE 32-byte front-table bucket -> RED.64 on the guide;
+//                            slow path  reads the fast path cannot settle (a mismatch, an N,
+//                                       a shifted guide, junk; 10-20 %) are parked in a
+//                                       warp-private shared-memory queue and, 32 at a time,
+//                                       walk Counter::assign over the seed index with every
+//                                       lane busy.
 //   count_generic_kernel : any layout (variable-length lines via u32 offsets, unaligned
 //                          buffers, tile remainders); one thread per read, byte loads.
 // Per-guide counts are 64-bit atomics in the L2-resident state vector; matched reads are
@@ -24,7 +29,7 @@ namespace sgc {
 namespace {
 
 struct CountParams {
-  TableView table;
+  LibView lib;
   const uint8_t* lines;
   const uint32_t* line_off;  // NULL => fixed stride
   uint64_t n_reads;
@@ -35,19 +40,17 @@ struct CountParams {
   unsigned long long* state;  // counts[n_guides], total, matched
   uint32_t n_guides;
   int32_t* assign_out;
-  // reads the streaming kernel could not settle, as structure-of-arrays records of park_cap
-  // entries each: window words [NW], misc, read index (see WarpQueueT)
-  uint32_t* park_rec;
-  unsigned int* park_count;
-  uint32_t park_cap;
   uint32_t debug;  // SGC_DEBUG bit mask (tuning only): 1 no count atomics, 2 no table probe, 4 no slow path
 };
 
+// MODE 0: production (no per-read output, no tuning switches); 1: also writes the per-read
+// assignment; 2: tuning build that honours SGC_DEBUG as well.
+template <int MODE = 2>
 __device__ __forceinline__ void record_hit(const CountParams& p, int32_t hit, uint64_t read_idx, uint32_t& matched) {
-  if (p.assign_out) p.assign_out[read_idx] = hit;
+  if (MODE >= 1 && p.assign_out) p.assign_out[read_idx] = hit;
   if (hit >= 0) {
     ++matched;
-    if (!(p.debug & 1u)) atomicAdd(p.state + hit, 1ull);  // counter.rs:232-235
+    if (MODE < 2 || !(p.debug & 1u)) atomicAdd(p.state + hit, 1ull);  // counter.rs:232-235
   }
 }
 
@@ -87,6 +90,7 @@ __device__ __forceinline__ void orient(Span& sp, int m, bool reverse) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
   uint32_t matched = 0;
+  const uint64_t policy = l2_evict_last_policy();
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_reads; i += nthreads) {
     const uint64_t r = p.first_read + i;
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
       start = r * p.stride;
       n = (int)p.read_len;
     }
-    const SpanGeom g = span_geom(n, p.offset, (int)p.table.k, p.reverse);
+    const SpanGeom g = span_geom(n, p.offset, (int)p.lib.k, p.reverse);
     Span sp{0, 0, 0};
     const uint8_t* s = p.lines + start + g.src;
     for (int j = 0; j < g.m; ++j) {
@@ -111,25 +115,19 @@ __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
       }
     }
     orient(sp, g.m, p.reverse);
-    int32_t hit = assign_span(p.table, p.with_perm, sp, g.base, n, p.offset, p.recursion, nullptr);
+    int32_t hit = assign_span(p.lib, p.with_perm, sp, g.base, n, p.offset, p.recursion, nullptr, policy);
     record_hit(p, hit, r, matched);
   }
   flush_matched(p, matched);
 }
 
 // ------------------------------------------------------------------------------------------
-// staged kernel: warp-private streaming rings
+// streaming kernel: warp-private rings
 //
 // Every warp owns a ring of kStages shared-memory buffers of ONE warp tile (32 reads =
 // 32*stride bytes, always a multiple of 16) and one mbarrier per buffer; lane 0 keeps the
 // ring full with 1-D bulk async copies, so warps never synchronise with each other and each
-// SM keeps (warps x (kStages-1)) tiles in flight.  Per read the hot path is
-//   LDS the span words -> funnel-align -> 2-bit pack + ASCII round-trip validity check ->
-//   one 32-byte table probe for the Centered window -> RED.64 on the guide's counter.
-// Reads the Centered probe does not settle (mismatch beyond the table, N, other bytes; about
-// 10-20 %) are parked in a warp-private shared-memory queue and walked 32 at a time through
-// the full Counter::assign procedure, so the rare path runs with full warps instead of
-// dragging every warp through it.
+// SM keeps (warps x (kStages-1)) tiles in flight.
 // ------------------------------------------------------------------------------------------
 constexpr int kWarpReads = 32;
 constexpr int kMaxStages = 4;
@@ -156,16 +154,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ uint64_t l2_evict_last_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
 // 1-D bulk async copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
   asm volatile(
@@ -175,166 +163,95 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
       : "memory");
 }
 
-// 2-bit pack NW window-aligned words (4 bases each).  `xs[i]` receives each word's XOR against
-// the ASCII its codes stand for (A 41, C 43, T 54, G 47), masked to the bytes that belong to
-// the window: all zero iff every window byte is A/C/G/T.  Returns the OR of xs.
-template <int NW>
-__device__ __forceinline__ uint32_t pack_window(const uint32_t (&aw)[NW], uint32_t last_mask, int n_words,
-                                                uint64_t& codes, uint32_t (&xs)[NW]) {
-  uint32_t lo = 0, hi = 0, any = 0;
-#pragma unroll
-  for (int i = 0; i < NW; ++i) {
-    const uint32_t w = aw[i];
-    const uint32_t c = (w >> 1) & 0x03030303u;
-    const uint32_t packed = (c * 0x01041040u) >> 24;  // gather 4 x 2 bits
-    if (i < 4) lo |= packed << (8 * i); else hi |= packed << (8 * (i - 4));
-    const uint32_t b0 = c & 0x01010101u, b1 = (c >> 1) & 0x01010101u;
-    const uint32_t expect = 0x41414141u + 2u * b0 + 0x13u * b1 - 0x0Fu * (b0 & b1);
-    // NW is the compile-time bound; words at or past n_words hold no window byte
-    const uint32_t m = (NW == 5 || i < n_words - 1) ? ((i == NW - 1 && NW == 5) ? last_mask : ~0u)
-                                                    : (i == n_words - 1 ? last_mask : 0u);
-    xs[i] = (w ^ expect) & m;
-    any |= xs[i];
-  }
-  codes = ((uint64_t)hi << 32) | lo;
-  return any;
-}
-
 // 4-bit mask of the non-zero bytes of x
 __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) {
   const uint32_t nz = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
   return ((nz >> 7) * 0x10204080u) >> 28;
 }
 
-// Parked reads keep the raw window words; everything else is re-derived when a full warp of
+// XOR of a word of four sequence bytes against the ASCII its 2-bit codes stand for
+// (A 41, C 43, G 47: 41 | code << 1;  T 54: the same ^ 11): zero iff all four are A/C/G/T.
+__device__ __forceinline__ uint32_t ascii_residue(uint32_t w) {
+  const uint32_t is_t = (w >> 2) & ~(w >> 1) & 0x01010101u;  // code 2
+  return ((w & 0xF9F9F9F9u) ^ (is_t * 0x11u)) ^ 0x41414141u;
+}
+
+// Parked reads keep the raw span words; everything else is re-derived when a full warp of
 // them is drained, so parking costs a handful of shared-memory stores.
-// Layout per warp (words): w[NW][kQueueCap] | misc[kQueueCap] | read[kQueueCap]
-//   misc = before | after << 8 | flags << 16   (flag 1: the Centered probe was a definite miss)
+// Layout per warp (words): w[NW + 2][kQueueCap] | read[kQueueCap]
 template <int NW>
 struct WarpQueueT {
-  uint32_t w[NW][kQueueCap];
-  uint32_t misc[kQueueCap];
+  uint32_t w[NW + 2][kQueueCap];
   uint32_t read[kQueueCap];  // read index relative to the launch's first read
 };
 
-// Everything a parked read needs, uniform across the warp.
-struct WalkGeom {
+// Geometry of the streaming kernel: every read has the same length, so it is warp uniform.
+struct StreamGeom {
   int k, n, o;
-  bool reverse, recursion, with_perm, has_before, has_after;
-  uint32_t last_mask, wild_byte;
-  int n_words;
+  bool reverse, recursion, with_perm;
+  int lead;       // stored bytes kept before the window (1 if the neighbouring position can be tried)
+  int m;          // span bytes: lead + k + trail
+  int span_base;  // oriented position of the first oriented span base
+  int n_words;    // words holding the k window bytes
+  uint32_t last_mask;
+  uint32_t wild_byte;
 };
 
-__device__ __forceinline__ WalkGeom make_geom(const CountParams& p) {
-  WalkGeom g;
-  g.k = (int)p.table.k;
+__device__ __forceinline__ StreamGeom make_geom(const CountParams& p) {
+  StreamGeom g;
+  g.k = (int)p.lib.k;
   g.n = (int)p.read_len;
   g.o = p.offset;
   g.reverse = p.reverse;
   g.recursion = p.recursion;
   g.with_perm = p.with_perm;
-  // stored (as-read) coordinates of the Centered window: forward [o, o+k), reverse [n-o-k, n-o)
-  const int win_src = g.reverse ? g.n - g.o - g.k : g.o;
-  g.has_before = win_src > 0;         // the bytes just outside the window are needed
-  g.has_after = win_src + g.k < g.n;  // only by the Plus / Minus positions
+  const bool before = g.o > 0, after = g.o + g.k < g.n;  // oriented neighbours (Minus / Plus)
+  g.lead = (g.reverse ? after : before) ? 1 : 0;
+  g.m = g.k + (before ? 1 : 0) + (after ? 1 : 0);
+  g.span_base = g.o - (before ? 1 : 0);
   g.n_words = (g.k + 3) >> 2;
   g.last_mask = (g.k & 3) ? ((1u << (8 * (g.k & 3))) - 1) : ~0u;
   g.wild_byte = p.wild_byte;
   return g;
 }
 
-// Full Counter::assign (counter.rs:96-140) for one parked read.
+// Full Counter::assign (counter.rs:96-140) for one parked read.  W holds the span words as
+// they sat in the tile; the span starts `off` bytes into W[0].
 template <int NW, bool WIDE>
-__device__ __forceinline__ int32_t walk_parked(const TableView& t, const WalkGeom& g, const uint32_t (&aw)[NW],
-                                               uint32_t misc) {
-  uint32_t xs[NW];
-  uint64_t codes;
-  const uint32_t any = pack_window<NW>(aw, g.last_mask, g.n_words, codes, xs);
-  const uint64_t kmask = (1ull << (2 * g.k)) - 1;
-  codes &= kmask;
-  if (g.reverse) codes = revcomp_codes(codes, g.k);
-  const uint32_t b_before = misc & 0xFFu, b_after = (misc >> 8) & 0xFFu;
-  const int first_pos = (misc >> 16) & 1u;
-  // oriented neighbours: reverse swaps and complements them
-  const uint32_t prev = g.reverse ? b_after : b_before, next = g.reverse ? b_before : b_after;
-  const bool has_prev = g.reverse ? g.has_after : g.has_before, has_next = g.reverse ? g.has_before : g.has_after;
-  const uint32_t cflip = g.reverse ? 2u : 0u;
-  const bool prev_bad = !has_prev || !is_acgt((uint8_t)prev), next_bad = !has_next || !is_acgt((uint8_t)next);
-  Span sp;
-  sp.codes = (uint64_t)(code_of((uint8_t)prev) ^ cflip) | (codes << 2) |
-             ((uint64_t)(code_of((uint8_t)next) ^ cflip) << (2 * g.k + 2));
-  if (any == 0 && !(has_prev && prev_bad) && !(has_next && next_bad) && t.bloom != nullptr) {
-    // Clean bases (the common parked read).  Everything the walk may consult that lives in
-    // L2 -- the Bloom words of the three windows and the front-table buckets of Plus and
-    // Minus -- is fetched in one go; the main table is touched only for keys the filter
-    // cannot rule out.  Resolution keeps the reference's order: Centered, Plus, Minus, a
-    // library member before a variant at each (counter.rs:111-135); a window whose trim
-    // would fail is never consulted.
-    const bool try_c = first_pos == 0;
-    const bool front_c_open = (misc >> 17) & 1u;  // the streaming probe could not decide membership
-    const bool try_p = g.recursion && g.o + 1 + g.k <= g.n;
-    const bool try_m = try_p && g.o > 0;
-    const uint64_t key_c = (sp.codes >> 2) & kmask, key_p = (sp.codes >> 4) & kmask, key_m = sp.codes & kmask;
-    uint64_t fp[4], fm[4], bc = 0, bp = 0, bm = 0, mc, mp, mm, meta;
-    uint32_t wc, wp, wm;
-    bloom_locate(key_c, t.n_bloom_words, wc, mc);
-    bloom_locate(key_p, t.n_bloom_words, wp, mp);
-    bloom_locate(key_m, t.n_bloom_words, wm, mm);
-    if (try_c) bc = __ldg(t.bloom + wc);
-    if (try_p) {
-      load_bucket(t.front_slots + (size_t)bucket_of(key_p, t.front_buckets) * 4, fp);
-      bp = __ldg(t.bloom + wp);
-    }
-    if (try_m) {
-      load_bucket(t.front_slots + (size_t)bucket_of(key_m, t.front_buckets) * 4, fm);
-      bm = __ldg(t.bloom + wm);
-    }
-    if (try_c) {
-      if (front_c_open) {
-        const int32_t hit = meta_hit(table_find_t<WIDE>(t.front_slots, t.front_buckets, key_c));
-        if (hit != kMiss) return hit;
-      }
-      if ((bc & mc) == mc) {
-        const int32_t hit = meta_hit(table_find_t<WIDE>(t.slots, t.n_buckets, key_c));
-        if (hit != kMiss) return hit;
-      }
-    }
-    if (!try_p) return kMiss;  // no recursion, or the Plus trim fails: return (counter.rs:105-108)
-    // one window: member in the front table, else (filter permitting) the main table
-    auto settle = [&](const uint64_t (&f)[4], bool maybe, uint64_t key) -> int32_t {
-      const int r = bucket_match<WIDE>(f, key, meta);
-      if (r == kFound) return meta_hit(meta);
-      if (!maybe) return kMiss;
-      return meta_hit(table_find_t<WIDE>(t.slots, t.n_buckets, key));
-    };
-    const int32_t hit_p = settle(fp, (bp & mp) == mp, key_p);
-    if (hit_p != kMiss) return hit_p;
-    if (!try_m) return kMiss;  // checked_sub(1) -> None
-    return settle(fm, (bm & mm) == mm, key_m);
-  }
-  uint32_t badw = 0, wildw = 0;
-  if (any) {
-    const uint32_t wild4 = 0x01010101u * g.wild_byte;
+__device__ __forceinline__ int32_t walk_parked(const LibView& v, const StreamGeom& g, const uint32_t (&W)[NW + 2],
+                                               uint32_t off_bits, uint64_t policy) {
+  constexpr int kSpanWords = NW + 1 < 8 ? NW + 1 : 8;  // m <= 32 bases
+  Span sp{0, 0, 0};
+  const uint32_t wild4 = 0x01010101u * g.wild_byte;
+  uint32_t any = 0;
+  uint32_t xs[kSpanWords], aw[kSpanWords];
 #pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      badw |= nonzero_bytes(xs[i]) << (4 * i);
-      wildw |= (nonzero_bytes(aw[i] ^ wild4) ^ 0xFu) << (4 * i);
-    }
-    wildw &= badw;
-    if (g.reverse) {
-      badw = reverse_bits(badw, g.k);
-      wildw = reverse_bits(wildw, g.k);
-    }
+  for (int i = 0; i < kSpanWords; ++i) {
+    aw[i] = __funnelshift_r(W[i], W[i + 1], off_bits);
+    const uint32_t c = (aw[i] >> 1) & 0x03030303u;
+    const uint32_t packed = (c * 0x01041040u) >> 24;  // gather 4 x 2 bits, base order
+    sp.codes |= (uint64_t)packed << (8 * i);
+    xs[i] = ascii_residue(aw[i]);
+    any |= xs[i];
   }
-  sp.bad = (prev_bad ? 1u : 0u) | (badw << 1) | ((next_bad ? 1u : 0u) << (g.k + 1));
-  sp.wild = ((has_prev && prev == g.wild_byte) ? 1u : 0u) | (wildw << 1) |
-            (((has_next && next == g.wild_byte) ? 1u : 0u) << (g.k + 1));
-  return assign_span(t, g.with_perm, sp, g.o - 1, g.n, g.o, g.recursion, nullptr, first_pos);
+  const uint32_t mmask = g.m >= 32 ? ~0u : ((1u << g.m) - 1);
+  // `any` may come from bytes past the span; the masks below are exact
+  if (any) {
+#pragma unroll
+    for (int i = 0; i < kSpanWords; ++i) {
+      sp.bad |= nonzero_bytes(xs[i]) << (4 * i);
+      sp.wild |= (nonzero_bytes(aw[i] ^ wild4) ^ 0xFu) << (4 * i);
+    }
+    sp.bad &= mmask;
+    sp.wild &= sp.bad;
+  }
+  orient(sp, g.m, g.reverse);
+  return assign_span_t<WIDE>(v, g.with_perm, sp, g.span_base, g.n, g.o, g.recursion, nullptr, policy);
 }
 
-// Pass 1.  NW = words that hold the k window bytes: 5 (k = 17..20, the common guide lengths) or 8.
-template <int NW, bool WIDE>
-__global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams p, uint64_t n_wtiles, int n_stages,
+// NW = words that hold the k window bytes: 5 (k = 17..20, the common guide lengths) or 8.
+template <int NW, bool WIDE, int MODE>
+__global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams p, uint32_t n_wtiles, int n_stages,
                                                               uint32_t stage_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -347,13 +264,13 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   WarpQueueT<NW>* q = reinterpret_cast<WarpQueueT<NW>*>(bars + warps_per_cta * kMaxStages) + warp;
 
   const uint32_t tile_bytes = kWarpReads * p.stride;  // multiple of 16
-  const uint64_t gwarp = (uint64_t)blockIdx.x * warps_per_cta + warp;
-  const uint64_t gwarps = (uint64_t)gridDim.x * warps_per_cta;
-  const uint64_t src_step = gwarps * tile_bytes;
-  const uint8_t* next_src = p.lines + gwarp * tile_bytes;  // source of the next tile to request
+  const uint32_t gwarp = blockIdx.x * warps_per_cta + warp;
+  const uint32_t gwarps = gridDim.x * warps_per_cta;
+  const uint64_t src_step = (uint64_t)gwarps * tile_bytes;
+  const uint8_t* next_src = p.lines + (uint64_t)gwarp * tile_bytes;  // source of the next tile to request
 
   uint64_t policy = 0;
-  uint64_t requested = gwarp;  // tile index of the next request
+  uint32_t requested = gwarp;  // tile index of the next request (n_wtiles + gwarps < 2^32)
   if (lane == 0) {
     for (int s = 0; s < n_stages; ++s) mbar_init(&my_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -370,151 +287,156 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   }
   __syncwarp();
 
-  // every read has the same length n, so the geometry is uniform
-  const WalkGeom g = make_geom(p);
-  const int k = g.k;
-  const bool centered_fits = g.o + k <= g.n;  // else every read fails its first trim (counter.rs:105-108)
-  const int win_src = g.reverse ? g.n - g.o - k : g.o;
-  const uint32_t wbyte = (uint32_t)lane * p.stride + (uint32_t)(centered_fits ? win_src : 0);
-  const uint32_t word0 = wbyte >> 2;
-  const uint32_t shift = (wbyte & 3u) * 8;
-  const uint64_t kmask = (1ull << (2 * k)) - 1;
-  const uint64_t* __restrict__ front = p.table.front_slots;
-  const uint32_t front_buckets = p.table.front_buckets;
-  const bool park_misses = g.recursion;
+  // every read has the same length n, so the geometry is uniform; the host sends reads whose
+  // Centered window does not fit (every one of them fails its first trim) to the generic kernel
+  const StreamGeom g = make_geom(p);
+  const int win_src = g.reverse ? g.n - g.o - g.k : g.o;  // stored position of the Centered window
+  const uint32_t sbyte = (uint32_t)lane * p.stride + (uint32_t)(win_src - g.lead);  // first span byte
+  const uint32_t word0 = sbyte >> 2;
+  const uint32_t off_bits = (sbyte & 3u) * 8;
+  const uint32_t win_bits = off_bits + 8u * (uint32_t)g.lead;  // 0..32: where the window starts in W
+  const uint64_t* __restrict__ front = g.reverse ? p.lib.front_rev : p.lib.front;
+  const uint32_t front_shift = p.lib.front_shift;
   const uint64_t table_policy = l2_evict_last_policy();
+  const bool settle_miss = !g.with_perm && !g.recursion;  // a definite Centered miss is final
+  const uint32_t debug = MODE == 2 ? p.debug : 0u;
 
   uint32_t matched = 0;
   uint32_t qn = 0;  // parked reads (warp-uniform)
-
-  // Parked reads leave the streaming loop: `count` queue entries starting at `from` are
-  // appended to the global record buffer (coalesced, one reservation per flush) and walked
-  // later by count_parked_kernel at full occupancy.
-  auto flush = [&](uint32_t from, uint32_t count) {
-    unsigned int base = 0;
-    if (lane == 0) base = atomicAdd(p.park_count, count);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if ((uint32_t)lane < count) {
-      const uint32_t e = from + lane;
-      uint32_t* dst = p.park_rec + base + lane;
-#pragma unroll
-      for (int i = 0; i < NW; ++i) dst[(size_t)i * p.park_cap] = q->w[i][e];
-      dst[(size_t)NW * p.park_cap] = q->misc[e];
-      dst[(size_t)(NW + 1) * p.park_cap] = q->read[e];
-    }
-  };
-
   int s = 0;
   uint32_t parity = 0;
-  uint32_t read_idx = (uint32_t)(gwarp * kWarpReads) + lane;
-  const uint32_t read_step = (uint32_t)(gwarps * kWarpReads);
-  for (uint64_t t = gwarp; t < n_wtiles; t += gwarps, read_idx += read_step) {
-    // wait for the tile, lift this lane's window out of shared memory, hand the buffer back
-    mbar_wait(&my_bar[s], parity);
-    const uint8_t* tile8 = my_tiles + (size_t)s * stage_bytes;
-    const uint32_t* tile = reinterpret_cast<const uint32_t*>(tile8);
-    uint32_t raw[NW + 1];
+  uint32_t read_idx = gwarp * kWarpReads + lane;
+  const uint32_t read_step = gwarps * kWarpReads;
+  uint32_t t = gwarp;
+  for (;;) {
+    const bool have_tile = t < n_wtiles;
+    if (have_tile) {
+      // wait for the tile, lift this lane's span out of shared memory, hand the buffer back
+      mbar_wait(&my_bar[s], parity);
+      uint8_t* stage = my_tiles + (size_t)s * stage_bytes;
+      const uint32_t* tile = reinterpret_cast<const uint32_t*>(stage);
+      uint32_t W[NW + 2];
 #pragma unroll
-    for (int i = 0; i <= NW; ++i) raw[i] = tile[word0 + i];
-    uint32_t misc = 0;
-    if (g.has_before) misc = tile8[wbyte - 1];
-    if (g.has_after) misc |= (uint32_t)tile8[wbyte + k] << 8;
-    __syncwarp();  // the whole warp has its bytes in registers: refill this buffer
-    if (lane == 0 && requested < n_wtiles) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&my_bar[s], tile_bytes);
-      bulk_load(my_tiles + (size_t)s * stage_bytes, next_src, tile_bytes, &my_bar[s], policy);
-      requested += gwarps;
-      next_src += src_step;
-    }
-    if (++s == n_stages) {
-      s = 0;
-      parity ^= 1u;
-    }
-    if (!centered_fits) {  // every read fails its first trim: nothing is tried (counter.rs:105-108)
-      if (p.assign_out) p.assign_out[read_idx] = kMiss;
-      continue;
-    }
+      for (int i = 0; i < NW + 2; ++i) W[i] = tile[word0 + i];
+      {
+        // The buffer may be refilled once every lane's loads have RETURNED.  A warp vote on a
+        // value computed from all of them is that point: it cannot issue before the data is
+        // in registers, which orders the generic-proxy reads before the async-proxy write
+        // without a CTA-wide membar per tile.
+        uint32_t allw = W[0];
+#pragma unroll
+        for (int i = 1; i < NW + 2; ++i) allw &= W[i];
+        uint32_t vote;
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\nvote.sync.ballot.b32 %0, p, 0xffffffff;\n}\n"
+            : "=r"(vote)
+            : "r"(allw)
+            : "memory");
+        (void)vote;
+      }
+      if (lane == 0 && requested < n_wtiles) {
+        mbar_expect_tx(&my_bar[s], tile_bytes);
+        bulk_load(stage, next_src, tile_bytes, &my_bar[s], policy);
+        requested += gwarps;
+        next_src += src_step;
+      }
+      if (++s == n_stages) {
+        s = 0;
+        parity ^= 1u;
+      }
 
-    uint32_t aw[NW], xs[NW];
+      // window-aligned words -> interleaved key + validity of the k window bytes
+      uint32_t lo = 0, hi = 0, any = 0;
 #pragma unroll
-    for (int i = 0; i < NW; ++i) aw[i] = __funnelshift_r(raw[i], raw[i + 1], shift);
-    uint64_t codes;
-    const uint32_t any = pack_window<NW>(aw, g.last_mask, g.n_words, codes, xs);
-    codes &= kmask;
-    if (g.reverse) codes = revcomp_codes(codes, k);
+      for (int i = 0; i < NW; ++i) {
+        uint32_t w = __funnelshift_rc(W[i], W[i + 1], win_bits);
+        uint32_t x = ascii_residue(w);
+        uint32_t c = (w >> 1) & 0x03030303u;
+        if (NW != 5 || i == NW - 1) {  // bytes past the window (NW = 5: only the last word can have any)
+          const uint32_t mk = i < g.n_words - 1 ? ~0u : (i == g.n_words - 1 ? g.last_mask : 0u);
+          x &= mk;
+          c &= mk;
+        }
+        any |= x;
+        if (i < 4)
+          lo += c << (2 * i);
+        else
+          hi += c << (2 * (i - 4));
+      }
+      if (!WIDE) hi = (hi * 0x01041040u) >> 24;
 
-    // Centered window against the FRONT table (library members only, L2 resident), one
-    // bucket: settles every exact read whose guide sits in its home bucket.  Everything else
-    // is parked for the full walk over the unified table.
-    bool park = true;
-    if (any == 0) {
-      int32_t hit;
-      int r;
-      if (p.debug & 2u) {
-        hit = (int32_t)(codes % p.n_guides);
-        r = kFound;
-      } else {
-        uint64_t w[4], meta;
-        load_bucket(front + (size_t)bucket_of(codes, front_buckets) * 4, w, table_policy);
-        r = bucket_match<WIDE>(w, codes, meta);
-        hit = meta_hit(meta);
-      }
-      if (r == kFound) {
-        park = false;
-        record_hit(p, hit, (uint64_t)read_idx, matched);
-      } else if (r == kUndecided) {
-        misc |= 1u << 17;  // the member may sit in a later bucket: the walk re-probes the front table
-      } else if (!g.with_perm) {
-        // no Permuter: the front table is the whole table, Centered is decided
-        misc |= 1u << 16;
-        park = park_misses;
-        if (!park) record_hit(p, kMiss, (uint64_t)read_idx, matched);
-      }
-    }
-    if (p.debug & 4u) park = false;
-    const uint32_t pm = __ballot_sync(0xffffffffu, park);
-    if (pm) {
-      if (park) {
-        const uint32_t e = qn + __popc(pm & ((1u << lane) - 1));
+      bool park = true;
+      if (any == 0) {
+        bool found, flagged;
+        int32_t hit;
+        if (MODE == 2 && (debug & 2u)) {
+          found = true;
+          flagged = false;
+          hit = (int32_t)((lo ^ hi) % p.n_guides);
+        } else {
+          uint64_t w[4];
+          load_bucket(front + (size_t)(front_hash(lo, hi) >> front_shift) * 4, w, table_policy);
+          if (!WIDE) {
+            // the slot whose lo word matches (the build keeps them distinct within a bucket)
+            uint32_t sel = 0;
 #pragma unroll
-        for (int i = 0; i < NW; ++i) q->w[i][e] = aw[i];
-        q->misc[e] = misc;
-        q->read[e] = read_idx;
+            for (int j = 3; j >= 0; --j)
+              if ((uint32_t)w[j] == lo) sel = (uint32_t)(w[j] >> 32);
+            const uint32_t want = hi | (uint32_t)(kFrontOccupied >> 32);
+            found = ((sel ^ want) & (0xFFu | (uint32_t)(kFrontOccupied >> 32))) == 0;
+            hit = (int32_t)(sel >> (kFrontIdxShift - 32));
+            flagged = (w[0] & kFrontFlag) != 0;
+          } else {
+            const uint64_t probe = ((uint64_t)hi << 32) | lo;
+            const bool m0 = w[0] == probe && (w[1] & kFrontOccupied), m1 = w[2] == probe && (w[3] & kFrontOccupied);
+            found = m0 || m1;
+            hit = (int32_t)((m0 ? w[1] : w[3]) >> kFrontIdxShift);
+            flagged = (w[1] & kFrontFlag) != 0;
+          }
+        }
+        if (found) {
+          park = false;
+          record_hit<MODE>(p, hit, (uint64_t)read_idx, matched);
+        } else if (!flagged && settle_miss) {
+          park = false;
+          record_hit<MODE>(p, kMiss, (uint64_t)read_idx, matched);
+        }
       }
-      qn += __popc(pm);
-      __syncwarp();
-      if (qn >= 32) {
-        qn -= 32;
-        flush(qn, 32);
+      if (MODE == 2 && (debug & 4u)) park = false;
+      const uint32_t pm = __ballot_sync(0xffffffffu, park);
+      if (pm) {
+        if (park) {
+          const uint32_t e = qn + __popc(pm & ((1u << lane) - 1));
+#pragma unroll
+          for (int i = 0; i < NW + 2; ++i) q->w[i][e] = W[i];
+          q->read[e] = read_idx;
+        }
+        qn += __popc(pm);
         __syncwarp();
       }
     }
-  }
-  if (qn) flush(0, qn);
-  flush_matched(p, matched);
-}
-
-// Pass 2: one thread per parked read, the full Counter::assign walk (walk_parked).  Plain
-// grid-stride kernel at full occupancy: the dependent table lookups of the rare reads are
-// hidden by thread-level parallelism instead of stalling the streaming warps.
-template <int NW, bool WIDE>
-__global__ void __launch_bounds__(256) count_parked_kernel(CountParams p) {
-  const WalkGeom g = make_geom(p);
-  const unsigned int n = *p.park_count;
-  uint32_t matched = 0;
-  for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const uint32_t* src = p.park_rec + e;
-    uint32_t aw[NW];
+    // drain the queue a full warp at a time (and whatever is left once the tiles are done)
+    if (qn >= 32 || (!have_tile && qn > 0)) {
+      const uint32_t cnt = qn < 32 ? qn : 32;
+      qn -= cnt;
+      if ((uint32_t)lane < cnt) {
+        const uint32_t e = qn + lane;
+        uint32_t W[NW + 2];
 #pragma unroll
-    for (int i = 0; i < NW; ++i) aw[i] = src[(size_t)i * p.park_cap];
-    const uint32_t misc = src[(size_t)NW * p.park_cap];
-    const uint32_t read = src[(size_t)(NW + 1) * p.park_cap];
-    const int32_t hit = walk_parked<NW, WIDE>(p.table, g, aw, misc);
-    record_hit(p, hit, (uint64_t)read, matched);
+        for (int i = 0; i < NW + 2; ++i) W[i] = q->w[i][e];
+        const uint32_t ridx = q->read[e];
+        // the span's byte offset inside W[0] is that of the lane that parked the read
+        const uint32_t poff = (((ridx & 31u) * p.stride + (uint32_t)(win_src - g.lead)) & 3u) * 8;
+        const int32_t hit = walk_parked<NW, WIDE>(p.lib, g, W, poff, table_policy);
+        record_hit<MODE>(p, hit, (uint64_t)ridx, matched);
+      }
+      __syncwarp();
+    }
+    if (!have_tile) break;
+    t += gwarps;
+    read_idx += read_step;
   }
-  matched = __reduce_add_sync(0xffffffffu, matched);
-  if ((threadIdx.x & 31) == 0 && matched) atomicAdd(p.state + p.n_guides + 1, (unsigned long long)matched);
+  flush_matched(p, matched);
 }
 
 }  // namespace
@@ -539,10 +461,6 @@ struct sgc_counter {
   size_t stage_cap = 0, stage_off_cap = 0;
   cudaEvent_t copy_done[2] = {nullptr, nullptr}, kernel_done[2] = {nullptr, nullptr};
   uint64_t chunks_submitted = 0;
-  // parked-read records of the streaming kernel (pass 1 -> pass 2)
-  uint32_t* d_park = nullptr;
-  unsigned int* d_park_count = nullptr;
-  size_t park_cap = 0;  // entries
   sgc_launch_info last{};
 };
 
@@ -567,7 +485,7 @@ uint8_t wild_byte_for(const sgc_counter* c) {
 CountParams make_params(const sgc_counter* c, const uint8_t* d_lines, const uint32_t* d_off, uint32_t stride,
                         uint32_t read_len, int32_t* d_assign) {
   CountParams p{};
-  p.table = c->lib->view();
+  p.lib = c->lib->view();
   p.lines = d_lines;
   p.line_off = d_off;
   p.stride = stride;
@@ -620,36 +538,26 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
   c->last = sgc_launch_info{};
   c->last.launches_total = launches_before;
   c->last.kernel = 1;
-  // staged kernel: fixed stride, 16-byte aligned base, whole warp tiles, < 2^32 reads per launch
+  // streaming kernel: fixed stride, 16-byte aligned base, whole warp tiles, < 2^32 reads per
+  // launch, and a Centered window that fits (otherwise every read fails its first trim)
   const uint32_t tile_bytes = kWarpReads * stride;
   const uint32_t stage_bytes = (tile_bytes + 48 + 15) & ~15u;  // +48: span words may run past the tile
-  const bool stageable = d_off == nullptr && ((uintptr_t)d_lines & 15u) == 0 && stride >= read_len;
+  const bool stageable = d_off == nullptr && ((uintptr_t)d_lines & 15u) == 0 && stride >= read_len &&
+                         (uint64_t)c->offset + c->lib->k <= read_len;
   const bool nw5 = !c->lib->wide && c->lib->k > 16;
   const size_t queue_bytes = nw5 ? sizeof(WarpQueueT<5>) : sizeof(WarpQueueT<8>);
   StreamConfig cfg = stageable ? pick_stream_config(stage_bytes, queue_bytes) : StreamConfig{};
   // whole tiles only, and never a bulk copy that would run past n_bytes
   uint64_t n_wtiles = stageable && cfg.stages ? std::min(n_reads / kWarpReads, n_bytes / tile_bytes) : 0;
-  n_wtiles = std::min<uint64_t>(n_wtiles, 0xFFFFFFFFull / kWarpReads);
+  n_wtiles = std::min<uint64_t>(n_wtiles, 0xFFFFFFFFull / kWarpReads - 65536);  // 32-bit tile and read counters
   if (n_wtiles > 0) {
-    auto kernel = c->lib->wide ? count_stream_kernel<8, true>
-                               : (nw5 ? count_stream_kernel<5, false> : count_stream_kernel<8, false>);
-    auto parked = c->lib->wide ? count_parked_kernel<8, true>
-                               : (nw5 ? count_parked_kernel<5, false> : count_parked_kernel<8, false>);
-    // worst case every read is parked: (NW + 2) words per read
-    const size_t need = n_wtiles * kWarpReads;
-    const size_t rec_words = (nw5 ? 5 : 8) + 2;
-    if (need > c->park_cap) {
-      SGC_CUDA_TRY(cudaStreamSynchronize(stream));
-      cudaFree(c->d_park);
-      c->d_park = nullptr;
-      SGC_CUDA_TRY(cudaMalloc(&c->d_park, need * rec_words * sizeof(uint32_t)));
-      c->park_cap = need;
-    }
-    if (!c->d_park_count) SGC_CUDA_TRY(cudaMalloc(&c->d_park_count, sizeof(unsigned int)));
-    SGC_CUDA_TRY(cudaMemsetAsync(c->d_park_count, 0, sizeof(unsigned int), stream));
-    p.park_rec = c->d_park;
-    p.park_count = c->d_park_count;
-    p.park_cap = (uint32_t)c->park_cap;
+    const int mode = p.debug ? 2 : (d_assign ? 1 : 0);
+    using Kernel = void (*)(const CountParams, uint32_t, int, uint32_t);
+    static const Kernel kernels[3][3] = {
+        {count_stream_kernel<5, false, 0>, count_stream_kernel<5, false, 1>, count_stream_kernel<5, false, 2>},
+        {count_stream_kernel<8, false, 0>, count_stream_kernel<8, false, 1>, count_stream_kernel<8, false, 2>},
+        {count_stream_kernel<8, true, 0>, count_stream_kernel<8, true, 1>, count_stream_kernel<8, true, 2>}};
+    Kernel kernel = kernels[c->lib->wide ? 2 : (nw5 ? 0 : 1)][mode];
     const size_t smem = stream_smem_bytes(cfg, stage_bytes, queue_bytes);
     SGC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint64_t grid = (uint64_t)c->lib->sm_count * cfg.ctas_per_sm;  // persistent: every CTA resident
@@ -657,13 +565,8 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
     if (grid > ctas_needed) grid = ctas_needed;
     p.n_reads = n_wtiles * kWarpReads;
     p.first_read = 0;
-    kernel<<<(unsigned)grid, cfg.warps * 32, smem, stream>>>(p, n_wtiles, cfg.stages, stage_bytes);
+    kernel<<<(unsigned)grid, cfg.warps * 32, smem, stream>>>(p, (uint32_t)n_wtiles, cfg.stages, stage_bytes);
     SGC_CUDA_TRY(cudaGetLastError());
-    if (!(p.debug & 4u)) {
-      parked<<<c->lib->sm_count * 8, 256, 0, stream>>>(p);
-      SGC_CUDA_TRY(cudaGetLastError());
-      c->last.launches_total += 1;
-    }
     done = n_wtiles * kWarpReads;
     c->last.grid = (uint32_t)grid;
     c->last.block = cfg.warps * 32;
@@ -754,8 +657,6 @@ void sgc_counter_destroy(sgc_counter* c) {
     if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
     if (c->kernel_done[i]) cudaEventDestroy(c->kernel_done[i]);
   }
-  cudaFree(c->d_park);
-  cudaFree(c->d_park_count);
   if (c->own_state) cudaFree(c->d_state);
   delete c;
 }

@@ -48,18 +48,38 @@ struct sgc_library {
   uint32_t n = 0, k = 0;
   bool with_perm = false;
   bool wide = false;
-  uint64_t* d_slots = nullptr;
-  uint32_t n_buckets = 0;
-  uint64_t* d_front = nullptr;  // library members only (== d_slots when there is no Permuter)
-  uint32_t front_buckets = 0;
-  uint64_t* d_bloom = nullptr;  // Bloom filter over the main table's keys (Permuter only)
-  uint32_t n_bloom_words = 0;
-  uint64_t* d_keys = nullptr;      // n packed guides, library order
+  // seed index (common.cuh)
+  uint32_t part_end[sgc::kSeeds] = {};
+  uint64_t keep[sgc::kSeeds] = {};
+  uint32_t* d_dir[sgc::kSeeds] = {};
+  uint32_t* d_dir_count[sgc::kSeeds] = {};
+  uint64_t* d_post[sgc::kSeeds] = {};
+  uint32_t dir_shift = 0;
+  // front tables of the streaming kernel, one per read orientation
+  uint64_t* d_front = nullptr;
+  uint64_t* d_front_rev = nullptr;
+  uint32_t front_shift = 0;
+  uint64_t* d_keys = nullptr;      // n natural keys, library order
   uint32_t* d_lib_hist = nullptr;  // k*4 positional counts over guides 1..n-1 (offsetter.rs:190-191)
   int sm_count = 0;
   sgc_library_info info{};
 
-  sgc::TableView view() const {
-    return sgc::TableView{d_slots, n_buckets, k, wide ? 1u : 0u, d_front, front_buckets, d_bloom, n_bloom_words};
+  sgc::LibView view() const {
+    sgc::LibView v{};
+    v.k = k;
+    v.n = n;
+    v.wide = wide ? 1u : 0u;
+    for (int i = 0; i < sgc::kSeeds; ++i) {
+      v.part_end[i] = part_end[i];
+      v.keep[i] = keep[i];
+      v.dir[i] = d_dir[i];
+      v.dir_count[i] = d_dir_count[i];
+      v.post[i] = d_post[i];
+    }
+    v.dir_shift = dir_shift;
+    v.front = d_front;
+    v.front_rev = d_front_rev;
+    v.front_shift = front_shift;
+    return v;
   }
 };

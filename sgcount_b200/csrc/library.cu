@@ -36,12 +36,11 @@ int cuda_error(cudaError_t e, const char* what, const char* file, int line) {
 
 namespace {
 
-constexpr uint64_t kWideEmptyKey = ~0ull;
-
 struct BuildStatus {
   unsigned int bad_guide;   // smallest guide index holding a non-ACGT byte, or 0xFFFFFFFF
-  unsigned int dup_guide;   // smallest guide index that duplicates another sequence
+  unsigned int dup_guide;   // smallest guide index that duplicates an earlier sequence
   unsigned long long n_variants, n_ambiguous;
+  unsigned int front_left_out;  // members that did not fit their front-table bucket
 };
 
 // K2a: one thread per guide.
@@ -61,148 +60,264 @@ __global__ void pack_library_kernel(const uint8_t* __restrict__ seqs, uint32_t n
   if (bad) atomicMin(&st->bad_guide, i);
 }
 
-// ---- narrow table (k <= 20): key and meta share one word, one CAS claims a slot ---------
-__device__ __forceinline__ void narrow_insert(uint64_t* slots, uint32_t n_buckets, uint64_t key, uint32_t idx,
-                                              bool variant, BuildStatus* st) {
-  const uint64_t val = make_meta(idx, variant) | key;
-  uint32_t b = bucket_of(key, n_buckets);
-  for (;;) {
-    unsigned long long* base = reinterpret_cast<unsigned long long*>(slots + (size_t)b * 4);
-    for (int s = 0; s < 4; ++s) {
-      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(base + s);
-      if (cur == 0) {
-        cur = atomicCAS(base + s, 0ull, (unsigned long long)val);
-        if (cur == 0) return;  // claimed
-      }
-      if ((cur & kKeyMaskNarrow) == key) {
-        if (!variant) {
-          atomicMin(&st->dup_guide, idx);  // library.rs:92
-        } else if (meta_variant(cur) && meta_idx(cur) != idx) {
-          atomicOr(base + s, (unsigned long long)kAmbig << kMetaShift);  // permutes.rs:149-152
-        }
-        // a variant that equals a library member is never stored (unreachable in the reference)
-        return;
-      }
-    }
-    b = (b + 1 == n_buckets) ? 0 : b + 1;
-  }
+// ---- seed index ---------------------------------------------------------------------------
+struct SeedGeom {
+  uint64_t keep[kSeeds];
+  uint32_t dir_shift;
+};
+__device__ __forceinline__ uint32_t bucket_of_seed(uint64_t key, const SeedGeom& g, int i) {
+  return seed_hash(key & g.keep[i]) >> g.dir_shift;
 }
+struct SeedArrays {
+  uint32_t* a[kSeeds];
+};
+struct PostArrays {
+  uint64_t* a[kSeeds];
+};
 
-// ---- wide table (k = 21..30): two words per slot, built in two passes -------------------
-// pass 1 claims key words, pass 2 (a later launch, so every key is visible) fills metas.
-__device__ __forceinline__ unsigned long long* wide_claim(uint64_t* slots, uint32_t n_buckets, uint64_t key,
-                                                          bool insert) {
-  uint32_t b = bucket_of(key, n_buckets);
-  for (;;) {
-    unsigned long long* base = reinterpret_cast<unsigned long long*>(slots + (size_t)b * 4);
-    for (int s = 0; s < 2; ++s) {
-      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(base + 2 * s);
-      if (cur == kWideEmptyKey) {
-        if (!insert) return nullptr;
-        cur = atomicCAS(base + 2 * s, (unsigned long long)kWideEmptyKey, (unsigned long long)key);
-        if (cur == kWideEmptyKey) return base + 2 * s + 1;
-      }
-      if (cur == key) return base + 2 * s + 1;
-    }
-    b = (b + 1 == n_buckets) ? 0 : b + 1;
-  }
-}
-
-__device__ __forceinline__ void wide_set_meta(unsigned long long* meta, uint32_t idx, bool variant, BuildStatus* st) {
-  unsigned long long old = atomicCAS(meta, 0ull, (unsigned long long)make_meta(idx, variant));
-  if (old == 0) return;
-  if (!variant) {
-    atomicMin(&st->dup_guide, idx);
-  } else if (meta_variant(old) && meta_idx(old) != idx) {
-    atomicOr(meta, (unsigned long long)kAmbig << kMetaShift);
-  }
-}
-
-__global__ void wide_init_kernel(uint64_t* slots, size_t n_slots) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_slots) {
-    slots[2 * i] = kWideEmptyKey;
-    slots[2 * i + 1] = 0;
-  }
-}
-
-// mode 0: narrow insert; 1: wide pass 1 (claim keys); 2: wide pass 2 (metas)
-template <int MODE>
-__global__ void insert_exact_kernel(uint64_t* slots, uint32_t n_buckets, const uint64_t* __restrict__ keys,
-                                    uint32_t n, BuildStatus* st) {
+// pass 1: members per bucket
+__global__ void seed_count_kernel(const uint64_t* __restrict__ keys, uint32_t n, SeedGeom g, SeedArrays cnt) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (MODE == 0) narrow_insert(slots, n_buckets, keys[i], i, false, st);
-  if (MODE == 1) wide_claim(slots, n_buckets, keys[i], true);
-  if (MODE == 2) wide_set_meta(wide_claim(slots, n_buckets, keys[i], false), i, false, st);
+  const uint64_t key = keys[i];
+#pragma unroll
+  for (int s = 0; s < kSeeds; ++s) atomicAdd(cnt.a[s] + bucket_of_seed(key, g, s), 1u);
 }
 
-// K2b: one thread per (guide, position): the three ACGT substitutions at that position
-// (permutes.rs:78-107 restricted to A,C,G,T; the N variants need no storage).
-template <int MODE>
-__global__ void insert_variants_kernel(uint64_t* slots, uint32_t n_buckets, const uint64_t* __restrict__ keys,
-                                       uint32_t n, uint32_t k, BuildStatus* st) {
-  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint64_t)n * k) return;
-  uint32_t i = (uint32_t)(t / k), pos = (uint32_t)(t % k);
-  uint64_t key = keys[i];
-  for (uint64_t d = 1; d < 4; ++d) {
-    uint64_t v = key ^ (d << (2 * pos));
-    if (MODE == 0) narrow_insert(slots, n_buckets, v, i, true, st);
-    if (MODE == 1) wide_claim(slots, n_buckets, v, true);
-    if (MODE == 2) wide_set_meta(wide_claim(slots, n_buckets, v, false), i, true, st);
+// pass 2: exclusive prefix sum of the counts (three small kernels: tile sums, scan of the
+// tile sums by one block, tile scan + carry-in)
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 8;
+constexpr int kScanTile = kScanThreads * kScanPerThread;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+    uint32_t winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += t;
+    }
+    warp_sums[lane] = winc - w;  // exclusive
+    if (lane == 31 && total) *total = winc;
+  }
+  __syncthreads();
+  const uint32_t r = warp_sums[warp] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t* __restrict__ cnt, uint32_t n,
+                                                                      uint32_t* __restrict__ tile_sums) {
+  const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanPerThread;
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanPerThread; ++j)
+    if (base + j < n) s += cnt[base + j];
+  __shared__ uint32_t total;
+  block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// one block: exclusive scan of the tile sums, in place
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(uint32_t* sums, uint32_t n_tiles) {
+  __shared__ uint32_t carry, total;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_tiles; base += kScanThreads) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < n_tiles ? sums[i] : 0;
+    const uint32_t ex = block_exclusive_scan(v, &total);
+    if (i < n_tiles) sums[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
   }
 }
 
-__global__ void table_stats_kernel(const uint64_t* __restrict__ slots, size_t n_slots, bool wide, BuildStatus* st) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long var = 0, amb = 0;
-  if (i < n_slots) {
-    uint64_t m = wide ? slots[2 * i + 1] : slots[i];
-    if (m != 0 && meta_variant(m)) {
-      if (meta_idx(m) == kAmbig)
-        amb = 1;
-      else
-        var = 1;
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const uint32_t* __restrict__ cnt, uint32_t n,
+                                                                  const uint32_t* __restrict__ tile_sums,
+                                                                  uint32_t* __restrict__ start) {
+  const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanPerThread;
+  uint32_t v[kScanPerThread], s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanPerThread; ++j) {
+    v[j] = base + j < n ? cnt[base + j] : 0;
+    s += v[j];
+  }
+  uint32_t run = tile_sums[blockIdx.x] + block_exclusive_scan(s, nullptr);
+#pragma unroll
+  for (int j = 0; j < kScanPerThread; ++j) {
+    if (base + j < n) start[base + j] = run;
+    run += v[j];
+  }
+}
+
+// pass 3: postings.  `cursor` starts as a copy of `start`; the order inside one bucket is
+// whatever the atomics give, which no lookup depends on.
+template <bool WIDE>
+__global__ void seed_fill_kernel(const uint64_t* __restrict__ keys, uint32_t n, SeedGeom g, SeedArrays cursor,
+                                 PostArrays post) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = keys[i];
+#pragma unroll
+  for (int s = 0; s < kSeeds; ++s) {
+    const uint32_t a = atomicAdd(cursor.a[s] + bucket_of_seed(key, g, s), 1u);
+    if (WIDE) {
+      post.a[s][2 * (size_t)a] = key;
+      post.a[s][2 * (size_t)a + 1] = i;
+    } else {
+      post.a[s][a] = key | ((uint64_t)i << kPostIdxShift);
     }
   }
-  var = __reduce_add_sync(0xffffffffu, (unsigned)var);
-  amb = __reduce_add_sync(0xffffffffu, (unsigned)amb);
+}
+
+// pass 4: directory entry = start | min(count, saturation) << 22
+__global__ void seed_dir_kernel(const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt,
+                                uint32_t* __restrict__ dir, uint32_t n_entries) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_entries) return;
+  const uint32_t c = cnt[i];
+  dir[i] = start[i] | ((c < kDirCountSat ? c : kDirCountSat) << kDirCountShift);
+}
+
+// ---- checks and statistics through the finished index ---------------------------------------
+// duplicate sequences (library.rs:91-95): the later of two equal records reports itself
+template <bool WIDE>
+__global__ void duplicate_check_kernel(LibView v, const uint64_t* __restrict__ keys, BuildStatus* st) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n) return;
+  const uint64_t key = keys[i];
+  const uint64_t pol = l2_evict_last_policy();
+  const uint32_t b = seed_hash(key & v.keep[0]) >> v.dir_shift;
+  bool dup = false;
+  walk_postings<WIDE>(v, 0, b, v.dir[0][b], pol, [&](uint64_t mk, uint32_t idx) {
+    if (mk == key && idx < i) dup = true;
+    return dup;
+  });
+  if (dup) atomicMin(&st->dup_guide, i);
+}
+
+// Permuter statistics: one thread per (guide, position) enumerates the three ACGT
+// substitutions (permutes.rs:78-107 without the N column, which needs no storage) and asks
+// the index who their parents are.  A variant that is itself a member is unreachable in the
+// reference; one parent = map entry; two or more = null set, counted once by
+// its smallest parent.
+template <bool WIDE>
+__global__ void variant_stats_kernel(LibView v, const uint64_t* __restrict__ keys, BuildStatus* st) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned var = 0, amb = 0;
+  const uint64_t pol = l2_evict_last_policy();
+  if (t < (uint64_t)v.n * v.k) {
+    const uint32_t i = (uint32_t)(t / v.k), pos = (uint32_t)(t % v.k);
+    const uint64_t key = keys[i];
+    for (uint64_t d = 1; d < 4; ++d) {
+      const uint64_t q = key ^ (d << (2 * pos));
+      bool member = false;
+      uint32_t parents = 0, smallest = 0xFFFFFFFFu;
+      for (int s = 0; s < kSeeds && !member; ++s) {
+        const uint64_t keep = v.keep[s];
+        const uint32_t b = seed_hash(q & keep) >> v.dir_shift;
+        walk_postings<WIDE>(v, s, b, v.dir[s][b], pol, [&](uint64_t mk, uint32_t idx) {
+          const uint64_t x = mk ^ q;
+          if ((x & keep) != 0) return false;
+          if (x == 0) member = true;
+          if (one_base_differs(x)) {
+            ++parents;
+            smallest = min(smallest, idx);
+          }
+          return member;
+        });
+      }
+      if (member) continue;
+      if (parents == 1) ++var;
+      if (parents > 1 && smallest == i) ++amb;
+    }
+  }
+  var = __reduce_add_sync(0xffffffffu, var);
+  amb = __reduce_add_sync(0xffffffffu, amb);
   if ((threadIdx.x & 31) == 0) {
-    if (var) atomicAdd(&st->n_variants, var);
-    if (amb) atomicAdd(&st->n_ambiguous, amb);
+    if (var) atomicAdd(&st->n_variants, (unsigned long long)var);
+    if (amb) atomicAdd(&st->n_ambiguous, (unsigned long long)amb);
   }
 }
 
-// one thread per slot: every occupied key sets its four bits
-__global__ void bloom_build_kernel(const uint64_t* __restrict__ slots, size_t n_slots, bool wide,
-                                   unsigned long long* bloom, uint32_t n_words) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_slots) return;
-  uint64_t key;
-  if (wide) {
-    if (slots[2 * i + 1] == 0) return;
-    key = slots[2 * i];
+// ---- front table ------------------------------------------------------------------------------
+// One thread per guide and orientation.  A member goes into the first free slot of its home
+// bucket; if the bucket is full, or already holds a member with the same `lo` word (the
+// streaming kernel selects a slot by `lo` alone), it is left out and the bucket is flagged.
+__device__ __forceinline__ uint64_t revcomp_key(uint64_t x, uint32_t k) {
+  uint64_t r = __brevll(x);
+  r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+  r >>= (64 - 2 * k);
+  return r ^ (0xAAAAAAAAAAAAAAAAull >> (64 - 2 * k));
+}
+
+template <bool WIDE>
+__global__ void front_insert_kernel(uint64_t* fwd, uint64_t* rev, uint32_t front_shift,
+                                    const uint64_t* __restrict__ keys, uint32_t n, uint32_t k, BuildStatus* st) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * n) return;
+  const uint32_t i = t >> 1;
+  const bool reverse = t & 1u;
+  unsigned long long* table = reinterpret_cast<unsigned long long*>(reverse ? rev : fwd);
+  const uint64_t key = reverse ? revcomp_key(keys[i], k) : keys[i];
+  uint32_t lo, hi;
+  interleave_key(key, k, WIDE, lo, hi);
+  const uint32_t b = front_hash(lo, hi) >> front_shift;
+  unsigned long long* bucket = table + (size_t)b * 4;
+  const uint64_t meta = kFrontOccupied | ((uint64_t)i << kFrontIdxShift);
+  bool placed = false;
+  if (!WIDE) {
+    const uint64_t val = meta | ((uint64_t)hi << 32) | lo;
+    for (int s = 0; s < 4 && !placed; ++s) {
+      unsigned long long cur = atomicCAS(bucket + s, 0ull, (unsigned long long)val);
+      if (cur == 0) {
+        placed = true;
+      } else if ((uint32_t)cur == lo) {
+        break;  // same lo word as an earlier member: leave this one out
+      }
+    }
   } else {
-    if (slots[i] == 0) return;
-    key = slots[i] & kKeyMaskNarrow;
+    const uint64_t w0 = ((uint64_t)hi << 32) | lo;
+    for (int s = 0; s < 2 && !placed; ++s) {
+      // the meta word claims the slot; the key word is written by the claimer and read by
+      // nobody until the build has finished, except for the `lo` comparison below
+      unsigned long long cur = atomicCAS(bucket + 2 * s + 1, 0ull, (unsigned long long)meta);
+      if (cur == 0) {
+        bucket[2 * s] = w0;
+        placed = true;
+      }
+    }
   }
-  uint32_t word;
-  uint64_t mask;
-  bloom_locate(key, n_words, word, mask);
-  atomicOr(bloom + word, (unsigned long long)mask);
+  if (!placed) {
+    atomicOr(bucket + (WIDE ? 1 : 0), (unsigned long long)kFrontFlag);
+    atomicAdd(&st->front_left_out, 1u);
+  }
 }
 
 // composed lookup of raw k-byte tokens (sgc_library_lookup)
-__global__ void lookup_tokens_kernel(TableView t, bool with_perm, const uint8_t* __restrict__ tokens,
+__global__ void lookup_tokens_kernel(LibView v, bool with_perm, const uint8_t* __restrict__ tokens,
                                      uint64_t n_tokens, int32_t* __restrict__ idx_out, uint8_t* __restrict__ kind_out) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_tokens) return;
-  const uint8_t* s = tokens + i * t.k;
+  const uint8_t* s = tokens + i * v.k;
   uint64_t key = 0;
   int nbad = 0, bad_pos = 0;
   bool wild = false;
-  for (uint32_t j = 0; j < t.k; ++j) {
+  for (uint32_t j = 0; j < v.k; ++j) {
     uint8_t c = s[j];
     key |= (uint64_t)code_of(c) << (2 * j);
     if (!is_acgt(c)) {
@@ -212,7 +327,8 @@ __global__ void lookup_tokens_kernel(TableView t, bool with_perm, const uint8_t*
     }
   }
   int kind = 0;
-  int32_t hit = window_lookup(t, with_perm, key, nbad, bad_pos, wild, &kind);
+  if (nbad == 1) key &= ~(3ull << (2 * bad_pos));
+  int32_t hit = window_lookup(v, with_perm, key, nbad, bad_pos, wild, &kind, l2_evict_last_policy());
   idx_out[i] = hit;
   if (kind_out) kind_out[i] = hit == kMiss ? 0 : (uint8_t)kind;
 }
@@ -257,13 +373,75 @@ int sgc_host_free(void* ptr) {
 void sgc_library_destroy(sgc_library* lib) {
   if (!lib) return;
   DeviceGuard g(lib->device);
-  if (lib->d_front != lib->d_slots) cudaFree(lib->d_front);
-  cudaFree(lib->d_bloom);
-  cudaFree(lib->d_slots);
+  for (int i = 0; i < kSeeds; ++i) {
+    cudaFree(lib->d_dir[i]);
+    cudaFree(lib->d_dir_count[i]);
+    cudaFree(lib->d_post[i]);
+  }
+  cudaFree(lib->d_front);
+  cudaFree(lib->d_front_rev);
   cudaFree(lib->d_keys);
   cudaFree(lib->d_lib_hist);
   delete lib;
 }
+
+}  // extern "C"
+
+namespace {
+
+// exclusive prefix sum of cnt[0..n) into start[0..n) on the default stream
+int exclusive_scan(const uint32_t* d_cnt, uint32_t n, uint32_t* d_start, uint32_t* d_tile_sums) {
+  const uint32_t tiles = (n + kScanTile - 1) / kScanTile;
+  scan_tile_sums_kernel<<<tiles, kScanThreads>>>(d_cnt, n, d_tile_sums);
+  scan_sums_kernel<<<1, kScanThreads>>>(d_tile_sums, tiles);
+  scan_tiles_kernel<<<tiles, kScanThreads>>>(d_cnt, n, d_tile_sums, d_start);
+  SGC_CUDA_TRY(cudaGetLastError());
+  return SGC_OK;
+}
+
+template <bool WIDE>
+int build_tables(sgc_library* lib, BuildStatus* d_st) {
+  const uint32_t n = lib->n, k = lib->k;
+  const unsigned T = 256;
+  const uint32_t entries = 1u << (32 - lib->dir_shift);
+  SeedGeom g;
+  SeedArrays cnt, cursor;
+  PostArrays post;
+  DeviceBuffer<uint32_t> start[kSeeds], cur[kSeeds], sums;
+  SGC_CUDA_TRY(sums.alloc((entries + kScanTile - 1) / kScanTile + 1));
+  g.dir_shift = lib->dir_shift;
+  for (int i = 0; i < kSeeds; ++i) {
+    g.keep[i] = lib->keep[i];
+    SGC_CUDA_TRY(start[i].alloc(entries));
+    SGC_CUDA_TRY(cur[i].alloc(entries));
+    SGC_CUDA_TRY(cudaMemsetAsync(lib->d_dir_count[i], 0, (size_t)entries * 4, 0));
+    cnt.a[i] = lib->d_dir_count[i];
+    cursor.a[i] = cur[i].p;
+    post.a[i] = lib->d_post[i];
+  }
+  seed_count_kernel<<<blocks_for(n, T), T>>>(lib->d_keys, n, g, cnt);
+  for (int i = 0; i < kSeeds; ++i) {
+    int rc = exclusive_scan(lib->d_dir_count[i], entries, start[i].p, sums.p);
+    if (rc) return rc;
+    SGC_CUDA_TRY(cudaMemcpyAsync(cur[i].p, start[i].p, (size_t)entries * 4, cudaMemcpyDeviceToDevice, 0));
+  }
+  seed_fill_kernel<WIDE><<<blocks_for(n, T), T>>>(lib->d_keys, n, g, cursor, post);
+  for (int i = 0; i < kSeeds; ++i)
+    seed_dir_kernel<<<blocks_for(entries, T), T>>>(start[i].p, lib->d_dir_count[i], lib->d_dir[i], entries);
+  const LibView v = lib->view();
+  duplicate_check_kernel<WIDE><<<blocks_for(n, T), T>>>(v, lib->d_keys, d_st);
+  if (lib->with_perm)
+    variant_stats_kernel<WIDE><<<blocks_for((uint64_t)n * k, T), T>>>(v, lib->d_keys, d_st);
+  front_insert_kernel<WIDE><<<blocks_for(2ull * n, T), T>>>(lib->d_front, lib->d_front_rev, lib->front_shift,
+                                                            lib->d_keys, n, k, d_st);
+  SGC_CUDA_TRY(cudaGetLastError());
+  SGC_CUDA_TRY(cudaDeviceSynchronize());  // the temporaries above are freed on return
+  return SGC_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, int with_permutations,
                        sgc_library** out) {
@@ -291,81 +469,59 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   } cleanup{lib};
   SGC_CUDA_TRY(cudaDeviceGetAttribute(&lib->sm_count, cudaDevAttrMultiProcessorCount, device));
 
-  // table geometry: <= 50 % load, whole 32-byte buckets
-  const uint64_t entries = lib->with_perm ? (uint64_t)n * (1 + 3ull * k) : n;
-  const uint32_t per_bucket = lib->wide ? 2 : 4;
-  uint64_t n_buckets = (entries * 2 + per_bucket - 1) / per_bucket;
-  if (n_buckets < 64) n_buckets = 64;
-  if (n_buckets > 0xFFFFFFF0ull) return set_error(SGC_ERR_TOO_MANY_GUIDES, "table too large");
-  lib->n_buckets = (uint32_t)n_buckets;
-  const size_t n_slots = (size_t)n_buckets * per_bucket;
-  const size_t table_bytes = (size_t)n_buckets * 32;
+  // seed geometry: three contiguous parts; seed i keeps every base outside part i.  Each
+  // directory has a power of two of buckets, at least four per member.
+  const uint64_t kmask = (1ull << (2 * k)) - 1;
+  uint32_t prev = 0;
+  for (int i = 0; i < kSeeds; ++i) {
+    lib->part_end[i] = i == kSeeds - 1 ? k : (uint32_t)((uint64_t)k * (i + 1) / kSeeds);
+    const uint32_t len = lib->part_end[i] - prev;
+    const uint64_t part = len ? (((1ull << (2 * len)) - 1) << (2 * prev)) : 0ull;
+    lib->keep[i] = kmask & ~part;
+    prev = lib->part_end[i];
+  }
+  uint32_t dir_bits = 6;
+  while (((uint64_t)1 << dir_bits) < 4ull * n) ++dir_bits;
+  lib->dir_shift = 32 - dir_bits;
+  const size_t dir_entries = (size_t)1 << dir_bits;
+  const size_t post_words = (size_t)n * (lib->wide ? 2 : 1);
+  // front table: 32-byte buckets, a power of two of them, about one member per bucket
+  // (narrow, 4 slots) or one per two buckets (wide, 2 slots)
+  uint32_t log_buckets = 6;
+  while (((uint64_t)1 << log_buckets) < (uint64_t)n * (lib->wide ? 2 : 1)) ++log_buckets;
+  lib->front_shift = 32 - log_buckets;
+  const size_t front_bytes = ((size_t)1 << log_buckets) * 32;
 
   DeviceBuffer<uint8_t> d_seqs;
   DeviceBuffer<BuildStatus> d_st;
   SGC_CUDA_TRY(d_seqs.alloc((size_t)n * k));
   SGC_CUDA_TRY(d_st.alloc(1));
   SGC_CUDA_TRY(cudaMalloc(&lib->d_keys, (size_t)n * sizeof(uint64_t)));
-  SGC_CUDA_TRY(cudaMalloc(&lib->d_slots, table_bytes));
+  for (int i = 0; i < kSeeds; ++i) {
+    SGC_CUDA_TRY(cudaMalloc(&lib->d_dir[i], dir_entries * 4));
+    SGC_CUDA_TRY(cudaMalloc(&lib->d_dir_count[i], dir_entries * 4));
+    SGC_CUDA_TRY(cudaMalloc(&lib->d_post[i], post_words * 8));
+  }
+  SGC_CUDA_TRY(cudaMalloc(&lib->d_front, front_bytes));
+  SGC_CUDA_TRY(cudaMalloc(&lib->d_front_rev, front_bytes));
   SGC_CUDA_TRY(cudaMalloc(&lib->d_lib_hist, (size_t)k * 4 * sizeof(uint32_t)));
   SGC_CUDA_TRY(cudaMemcpy(d_seqs.p, seqs, (size_t)n * k, cudaMemcpyHostToDevice));
-  BuildStatus st0{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0};
+  BuildStatus st0{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
   SGC_CUDA_TRY(cudaMemcpy(d_st.p, &st0, sizeof st0, cudaMemcpyHostToDevice));
 
   cudaEvent_t e0, e1;
   SGC_CUDA_TRY(cudaEventCreate(&e0));
   SGC_CUDA_TRY(cudaEventCreate(&e1));
   SGC_CUDA_TRY(cudaEventRecord(e0, 0));
-  const unsigned T = 256;
-  if (lib->wide)
-    wide_init_kernel<<<blocks_for(n_slots, T), T>>>(lib->d_slots, n_slots);
-  else
-    SGC_CUDA_TRY(cudaMemsetAsync(lib->d_slots, 0, table_bytes, 0));
-  pack_library_kernel<<<blocks_for(n, T), T>>>(d_seqs.p, n, k, lib->d_keys, d_st.p);
-  const uint64_t nv = (uint64_t)n * k;
-  if (!lib->wide) {
-    insert_exact_kernel<0><<<blocks_for(n, T), T>>>(lib->d_slots, lib->n_buckets, lib->d_keys, n, d_st.p);
-    if (lib->with_perm)
-      insert_variants_kernel<0><<<blocks_for(nv, T), T>>>(lib->d_slots, lib->n_buckets, lib->d_keys, n, k, d_st.p);
-  } else {
-    insert_exact_kernel<1><<<blocks_for(n, T), T>>>(lib->d_slots, lib->n_buckets, lib->d_keys, n, d_st.p);
-    if (lib->with_perm)
-      insert_variants_kernel<1><<<blocks_for(nv, T), T>>>(lib->d_slots, lib->n_buckets, lib->d_keys, n, k, d_st.p);
-    insert_exact_kernel<2><<<blocks_for(n, T), T>>>(lib->d_slots, lib->n_buckets, lib->d_keys, n, d_st.p);
-    if (lib->with_perm)
-      insert_variants_kernel<2><<<blocks_for(nv, T), T>>>(lib->d_slots, lib->n_buckets, lib->d_keys, n, k, d_st.p);
-  }
-  table_stats_kernel<<<blocks_for(n_slots, T), T>>>(lib->d_slots, n_slots, lib->wide, d_st.p);
-  // front table: members only, <= 25 % load (skipped when the main table already is that)
-  if (lib->with_perm) {
-    uint64_t fb = ((uint64_t)n * 4 + per_bucket - 1) / per_bucket;
-    if (fb < 64) fb = 64;
-    lib->front_buckets = (uint32_t)fb;
-    const size_t f_slots = (size_t)fb * per_bucket;
-    SGC_CUDA_TRY(cudaMalloc(&lib->d_front, (size_t)fb * 32));
-    if (lib->wide) {
-      wide_init_kernel<<<blocks_for(f_slots, T), T>>>(lib->d_front, f_slots);
-      insert_exact_kernel<1><<<blocks_for(n, T), T>>>(lib->d_front, lib->front_buckets, lib->d_keys, n, d_st.p);
-      insert_exact_kernel<2><<<blocks_for(n, T), T>>>(lib->d_front, lib->front_buckets, lib->d_keys, n, d_st.p);
-    } else {
-      SGC_CUDA_TRY(cudaMemsetAsync(lib->d_front, 0, (size_t)fb * 32, 0));
-      insert_exact_kernel<0><<<blocks_for(n, T), T>>>(lib->d_front, lib->front_buckets, lib->d_keys, n, d_st.p);
-    }
-    // Bloom filter: one 64-bit word per 4 expected keys (2 bytes per key, false positives < 1 %)
-    lib->n_bloom_words = (uint32_t)std::max<uint64_t>(entries / 4, 64);
-    SGC_CUDA_TRY(cudaMalloc(&lib->d_bloom, (size_t)lib->n_bloom_words * 8));
-    SGC_CUDA_TRY(cudaMemsetAsync(lib->d_bloom, 0, (size_t)lib->n_bloom_words * 8, 0));
-    bloom_build_kernel<<<blocks_for(n_slots, T), T>>>(lib->d_slots, n_slots, lib->wide,
-                                                      reinterpret_cast<unsigned long long*>(lib->d_bloom),
-                                                      lib->n_bloom_words);
-  } else {
-    lib->d_front = lib->d_slots;
-    lib->front_buckets = lib->n_buckets;
-  }
+  SGC_CUDA_TRY(cudaMemsetAsync(lib->d_front, 0, front_bytes, 0));
+  SGC_CUDA_TRY(cudaMemsetAsync(lib->d_front_rev, 0, front_bytes, 0));
+  pack_library_kernel<<<blocks_for(n, 256), 256>>>(d_seqs.p, n, k, lib->d_keys, d_st.p);
+  int rc = lib->wide ? build_tables<true>(lib, d_st.p) : build_tables<false>(lib, d_st.p);
+  if (rc) return rc;
   // library positional histogram for the offset detector: records 1..n-1 (offsetter.rs:57,190-191)
   SGC_CUDA_TRY(cudaMemsetAsync(lib->d_lib_hist, 0, (size_t)k * 4 * sizeof(uint32_t), 0));
   if (n > 1) {
-    int rc = position_counts_device(d_seqs.p + k, nullptr, k, k, n - 1, k, lib->d_lib_hist, 0);
+    rc = position_counts_device(d_seqs.p + k, nullptr, k, k, n - 1, k, lib->d_lib_hist, 0);
     if (rc) return rc;
   }
   SGC_CUDA_TRY(cudaEventRecord(e1, 0));
@@ -393,10 +549,11 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   lib->info.device = device;
   lib->info.n_variants = st.n_variants;
   lib->info.n_ambiguous = st.n_ambiguous;
-  lib->info.n_slots = n_slots;
-  lib->info.table_bytes =
-      table_bytes + (lib->with_perm ? (size_t)lib->front_buckets * 32 + (size_t)lib->n_bloom_words * 8 : 0);
+  lib->info.n_slots = ((size_t)1 << log_buckets) * (lib->wide ? 2 : 4);
+  // what the count kernels touch: directories + postings + one front table
+  lib->info.table_bytes = kSeeds * (dir_entries * 4 + post_words * 8) + front_bytes;
   lib->info.build_ms = ms;
+  lib->info.front_left_out = st.front_left_out;
   cleanup.l = nullptr;
   *out = lib;
   return SGC_OK;
