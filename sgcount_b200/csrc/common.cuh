@@ -47,11 +47,14 @@ constexpr uint32_t kNarrowMaxK = 20;
 constexpr int kSeeds = 3;
 constexpr int32_t kMiss = -1;
 
-// directory entry: [21:0] first posting, [31:22] number of postings, saturating (the exact
-// count of a saturated bucket is in LibView::dir_count)
+// directory entry: [21:0] first posting of the bucket, [23:22] number of postings, [31:24] tag
+// (the 8 hash bits below the bucket bits) shared by every posting of the bucket.  Count 3 marks
+// a GENERAL bucket: more than two postings, or postings of different tags; its exact size is
+// in LibView::dir_count and its tag is not used.
 constexpr uint32_t kDirStartMask = 0x3FFFFFu;
 constexpr int kDirCountShift = 22;
-constexpr uint32_t kDirCountSat = 1023u;
+constexpr uint32_t kDirGeneral = 3u;
+constexpr int kDirTagShift = 24;
 
 // narrow posting: [39:0] natural key, [61:40] guide index.  Wide posting: {natural key, guide index}.
 constexpr int kPostIdxShift = 40;
@@ -69,8 +72,9 @@ struct LibView {
   uint64_t keep[kSeeds];          // key bits seed i keeps (everything but part i)
   const uint32_t* __restrict__ dir[kSeeds];        // 1 << dir_bits entries each
   const uint32_t* __restrict__ dir_count[kSeeds];  // exact bucket sizes (read for saturated entries only)
-  const uint64_t* __restrict__ post[kSeeds];       // n postings sorted by bucket (2 words each when wide)
-  uint32_t dir_shift;                              // bucket = seed_hash >> dir_shift
+  const uint64_t* __restrict__ post;               // kSeeds x n postings, list i at i * n, each sorted by bucket
+                                                   // (2 words per posting when wide)
+  uint32_t dir_shift;                              // bucket = seed_hash >> dir_shift (>= 8)
   const uint64_t* __restrict__ front;      // forward orientation (keys of the guides as written)
   const uint64_t* __restrict__ front_rev;  // keys of the guides' reverse complements
   uint32_t front_shift;                    // bucket = front_hash >> front_shift
@@ -144,27 +148,46 @@ __device__ __forceinline__ bool one_base_differs(uint64_t x) {
   return y != 0 && (y & (y - 1)) == 0;
 }
 
-// Walks the postings of one directory entry.  `visit(key, idx)` returning true stops the walk.
+// One directory probe: where the postings of the token's seed i would be.
+struct SeedRun {
+  uint32_t first;  // index of the first posting in LibView::post (list offset included)
+  uint32_t count;
+};
+__device__ __forceinline__ uint32_t seed_bucket(const LibView& v, uint32_t h) { return h >> v.dir_shift; }
+__device__ __forceinline__ SeedRun seed_run(const LibView& v, int seed, uint32_t h, uint32_t entry) {
+  SeedRun r;
+  r.first = (uint32_t)seed * v.n + (entry & kDirStartMask);
+  r.count = (entry >> kDirCountShift) & 3u;
+  if (r.count == kDirGeneral)
+    r.count = v.dir_count[seed][h >> v.dir_shift];
+  else if ((entry >> kDirTagShift) != ((h >> (v.dir_shift - 8)) & 0xFFu))
+    r.count = 0;  // the bucket belongs to another seed
+  return r;
+}
+template <bool WIDE>
+__device__ __forceinline__ void load_posting(const LibView& v, uint32_t at, uint64_t policy, uint64_t& key, uint32_t& idx) {
+  if (WIDE) {
+    key = ldg_u64(v.post + 2 * (size_t)at, policy);
+    idx = (uint32_t)ldg_u64(v.post + 2 * (size_t)at + 1, policy);
+  } else {
+    const uint64_t w = ldg_u64(v.post + at, policy);
+    key = w & kPostKeyMask;
+    idx = (uint32_t)(w >> kPostIdxShift);
+  }
+}
+
+// Every posting of list `seed` that may share the seed of `key` (build-side checks; the count
+// kernels use window_lookup_t).  `visit(key, idx)` returning true stops the walk.
 template <bool WIDE, typename F>
-__device__ __forceinline__ void walk_postings(const LibView& v, int seed, uint32_t bucket, uint32_t entry,
-                                              uint64_t policy, F&& visit) {
-  const uint32_t start = entry & kDirStartMask;
-  uint32_t cnt = entry >> kDirCountShift;
-  if (cnt == kDirCountSat) cnt = v.dir_count[seed][bucket];
-  const uint64_t* __restrict__ post = v.post[seed];
+__device__ __forceinline__ void for_each_posting(const LibView& v, int seed, uint64_t key, uint64_t policy, F&& visit) {
+  const uint32_t h = seed_hash(key & v.keep[seed]);
+  const SeedRun r = seed_run(v, seed, h, ldg_u32(v.dir[seed] + seed_bucket(v, h), policy));
 #pragma unroll 1
-  for (uint32_t c = 0; c < cnt; ++c) {
-    uint64_t key;
+  for (uint32_t c = 0; c < r.count; ++c) {
+    uint64_t mk;
     uint32_t idx;
-    if (WIDE) {
-      key = ldg_u64(post + 2 * (size_t)(start + c), policy);
-      idx = (uint32_t)ldg_u64(post + 2 * (size_t)(start + c) + 1, policy);
-    } else {
-      const uint64_t w = ldg_u64(post + start + c, policy);
-      key = w & kPostKeyMask;
-      idx = (uint32_t)(w >> kPostIdxShift);
-    }
-    if (visit(key, idx)) break;
+    load_posting<WIDE>(v, r.first + c, policy, mk, idx);
+    if (visit(mk, idx)) break;
   }
 }
 
@@ -176,37 +199,46 @@ template <bool WIDE>
 __device__ __forceinline__ int32_t window_lookup_t(const LibView& v, bool with_perm, uint64_t key, int nbad,
                                                    int bad_pos, bool bad_is_wild, int* kind, uint64_t policy) {
   if (nbad == 0) {
-    // the three directory entries are fetched together; without a Permuter only the first is
-    // needed (a member sits in every list)
-    uint32_t bucket[kSeeds], entry[kSeeds];
+    // The three directory entries are fetched together (without a Permuter only the first is
+    // needed: a member sits in every list) and their runs are walked as ONE sequence, so a
+    // warp iterates max-over-lanes of the candidates per window, not per list.
+    uint32_t h[kSeeds], entry[kSeeds];
 #pragma unroll
     for (int i = 0; i < kSeeds; ++i) {
-      bucket[i] = seed_hash(key & v.keep[i]) >> v.dir_shift;
-      entry[i] = (i == 0 || with_perm) ? ldg_u32(v.dir[i] + bucket[i], policy) : 0u;
+      h[i] = seed_hash(key & v.keep[i]);
+      entry[i] = (i == 0 || with_perm) ? ldg_u32(v.dir[i] + seed_bucket(v, h[i]), policy) : 0u;
     }
+    SeedRun r[kSeeds];
+#pragma unroll
+    for (int i = 0; i < kSeeds; ++i) {
+      r[i] = seed_run(v, i, h[i], entry[i]);
+      if (i > 0 && !with_perm) r[i].count = 0;
+    }
+    static_assert(kSeeds == 3, "the merged walk below is written for three lists");
+    const uint32_t end0 = r[0].count, end1 = end0 + r[1].count, total = end1 + r[2].count;
+    const uint32_t base0 = r[0].first, base1 = r[1].first - end0, base2 = r[2].first - end1;
     int32_t found = kMiss;
     int parents = 0;
     bool member = false;
 #pragma unroll 1
-    for (int i = 0; i < kSeeds; ++i) {
-      const uint32_t e = i == 0 ? entry[0] : (i == 1 ? entry[1] : entry[2]);
-      const uint32_t b = i == 0 ? bucket[0] : (i == 1 ? bucket[1] : bucket[2]);
-      const uint64_t keep = v.keep[i];
-      walk_postings<WIDE>(v, i, b, e, policy, [&](uint64_t mk, uint32_t idx) {
-        const uint64_t x = mk ^ key;
-        if ((x & keep) != 0) return false;  // another seed hashed to this bucket
-        if (x == 0) {                       // Library::contains (counter.rs:111-112)
-          member = true;
-          found = (int32_t)idx;
-          return true;
-        }
-        if (one_base_differs(x)) {  // the difference lies inside part i
-          ++parents;
-          found = (int32_t)idx;
-        }
-        return false;
-      });
-      if (member || !with_perm) break;
+    for (uint32_t j = 0; j < total; ++j) {
+      const bool in0 = j < end0, in1 = j < end1;
+      const uint32_t at = (in0 ? base0 : (in1 ? base1 : base2)) + j;
+      const uint64_t keep = in0 ? v.keep[0] : (in1 ? v.keep[1] : v.keep[2]);
+      uint64_t mk;
+      uint32_t idx;
+      load_posting<WIDE>(v, at, policy, mk, idx);
+      const uint64_t x = mk ^ key;
+      if ((x & keep) != 0) continue;  // a posting of another seed that hashed to this bucket
+      if (x == 0) {                   // Library::contains (counter.rs:111-112)
+        member = true;
+        found = (int32_t)idx;
+        break;
+      }
+      if (one_base_differs(x)) {  // the difference lies inside the part this list leaves out
+        ++parents;
+        found = (int32_t)idx;
+      }
     }
     if (member) {
       if (kind) *kind = 1;
@@ -224,11 +256,9 @@ __device__ __forceinline__ int32_t window_lookup_t(const LibView& v, bool with_p
     int i = 0;
     while (i < kSeeds - 1 && (uint32_t)bad_pos >= v.part_end[i]) ++i;
     const uint64_t hole = ~(3ull << (2 * bad_pos));
-    const uint32_t b = seed_hash(key & v.keep[i]) >> v.dir_shift;
-    const uint32_t e = ldg_u32(v.dir[i] + b, policy);
     int32_t found = kMiss;
     int parents = 0;
-    walk_postings<WIDE>(v, i, b, e, policy, [&](uint64_t mk, uint32_t idx) {
+    for_each_posting<WIDE>(v, i, key, policy, [&](uint64_t mk, uint32_t idx) {
       if (((mk ^ key) & hole) == 0) {
         ++parents;
         found = (int32_t)idx;

@@ -53,7 +53,7 @@ struct sgc_library {
   uint64_t keep[sgc::kSeeds] = {};
   uint32_t* d_dir[sgc::kSeeds] = {};
   uint32_t* d_dir_count[sgc::kSeeds] = {};
-  uint64_t* d_post[sgc::kSeeds] = {};
+  uint64_t* d_post = nullptr;  // kSeeds lists of n postings
   uint32_t dir_shift = 0;
   // front tables of the streaming kernel, one per read orientation
   uint64_t* d_front = nullptr;
@@ -74,8 +74,8 @@ struct sgc_library {
       v.keep[i] = keep[i];
       v.dir[i] = d_dir[i];
       v.dir_count[i] = d_dir_count[i];
-      v.post[i] = d_post[i];
     }
+    v.post = d_post;
     v.dir_shift = dir_shift;
     v.front = d_front;
     v.front_rev = d_front_rev;

@@ -71,17 +71,23 @@ __device__ __forceinline__ uint32_t bucket_of_seed(uint64_t key, const SeedGeom&
 struct SeedArrays {
   uint32_t* a[kSeeds];
 };
-struct PostArrays {
-  uint64_t* a[kSeeds];
-};
 
-// pass 1: members per bucket
-__global__ void seed_count_kernel(const uint64_t* __restrict__ keys, uint32_t n, SeedGeom g, SeedArrays cnt) {
+// pass 1: members per bucket, and the bucket's tag: the first member's, with bit 8 raised when a
+// member with another tag joins
+constexpr uint32_t kNoTag = 0xFFFFFFFFu, kTagConflict = 0x100u;
+__global__ void seed_count_kernel(const uint64_t* __restrict__ keys, uint32_t n, SeedGeom g, SeedArrays cnt,
+                                  SeedArrays tags) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t key = keys[i];
 #pragma unroll
-  for (int s = 0; s < kSeeds; ++s) atomicAdd(cnt.a[s] + bucket_of_seed(key, g, s), 1u);
+  for (int s = 0; s < kSeeds; ++s) {
+    const uint32_t h = seed_hash(key & g.keep[s]);
+    const uint32_t b = h >> g.dir_shift, tag = (h >> (g.dir_shift - 8)) & 0xFFu;
+    atomicAdd(cnt.a[s] + b, 1u);
+    const uint32_t old = atomicCAS(tags.a[s] + b, kNoTag, tag);
+    if (old != kNoTag && (old & 0xFFu) != tag) atomicOr(tags.a[s] + b, kTagConflict);
+  }
 }
 
 // pass 2: exclusive prefix sum of the counts (three small kernels: tile sums, scan of the
@@ -168,29 +174,30 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const uint32_t
 // whatever the atomics give, which no lookup depends on.
 template <bool WIDE>
 __global__ void seed_fill_kernel(const uint64_t* __restrict__ keys, uint32_t n, SeedGeom g, SeedArrays cursor,
-                                 PostArrays post) {
+                                 uint64_t* __restrict__ post) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t key = keys[i];
 #pragma unroll
   for (int s = 0; s < kSeeds; ++s) {
-    const uint32_t a = atomicAdd(cursor.a[s] + bucket_of_seed(key, g, s), 1u);
+    const size_t a = (size_t)s * n + atomicAdd(cursor.a[s] + bucket_of_seed(key, g, s), 1u);
     if (WIDE) {
-      post.a[s][2 * (size_t)a] = key;
-      post.a[s][2 * (size_t)a + 1] = i;
+      post[2 * a] = key;
+      post[2 * a + 1] = i;
     } else {
-      post.a[s][a] = key | ((uint64_t)i << kPostIdxShift);
+      post[a] = key | ((uint64_t)i << kPostIdxShift);
     }
   }
 }
 
-// pass 4: directory entry = start | min(count, saturation) << 22
+// pass 4: directory entry = start | count << 22 | tag << 24 (count 3 = general bucket)
 __global__ void seed_dir_kernel(const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt,
-                                uint32_t* __restrict__ dir, uint32_t n_entries) {
+                                const uint32_t* __restrict__ tags, uint32_t* __restrict__ dir, uint32_t n_entries) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_entries) return;
-  const uint32_t c = cnt[i];
-  dir[i] = start[i] | ((c < kDirCountSat ? c : kDirCountSat) << kDirCountShift);
+  const uint32_t c = cnt[i], t = tags[i];
+  const bool general = c >= kDirGeneral || (t != kNoTag && (t & kTagConflict));
+  dir[i] = start[i] | ((general ? kDirGeneral : c) << kDirCountShift) | ((t & 0xFFu) << kDirTagShift);
 }
 
 // ---- checks and statistics through the finished index ---------------------------------------
@@ -201,9 +208,8 @@ __global__ void duplicate_check_kernel(LibView v, const uint64_t* __restrict__ k
   if (i >= v.n) return;
   const uint64_t key = keys[i];
   const uint64_t pol = l2_evict_last_policy();
-  const uint32_t b = seed_hash(key & v.keep[0]) >> v.dir_shift;
   bool dup = false;
-  walk_postings<WIDE>(v, 0, b, v.dir[0][b], pol, [&](uint64_t mk, uint32_t idx) {
+  for_each_posting<WIDE>(v, 0, key, pol, [&](uint64_t mk, uint32_t idx) {
     if (mk == key && idx < i) dup = true;
     return dup;
   });
@@ -229,8 +235,7 @@ __global__ void variant_stats_kernel(LibView v, const uint64_t* __restrict__ key
       uint32_t parents = 0, smallest = 0xFFFFFFFFu;
       for (int s = 0; s < kSeeds && !member; ++s) {
         const uint64_t keep = v.keep[s];
-        const uint32_t b = seed_hash(q & keep) >> v.dir_shift;
-        walk_postings<WIDE>(v, s, b, v.dir[s][b], pol, [&](uint64_t mk, uint32_t idx) {
+        for_each_posting<WIDE>(v, s, q, pol, [&](uint64_t mk, uint32_t idx) {
           const uint64_t x = mk ^ q;
           if ((x & keep) != 0) return false;
           if (x == 0) member = true;
@@ -376,8 +381,8 @@ void sgc_library_destroy(sgc_library* lib) {
   for (int i = 0; i < kSeeds; ++i) {
     cudaFree(lib->d_dir[i]);
     cudaFree(lib->d_dir_count[i]);
-    cudaFree(lib->d_post[i]);
   }
+  cudaFree(lib->d_post);
   cudaFree(lib->d_front);
   cudaFree(lib->d_front_rev);
   cudaFree(lib->d_keys);
@@ -405,29 +410,30 @@ int build_tables(sgc_library* lib, BuildStatus* d_st) {
   const unsigned T = 256;
   const uint32_t entries = 1u << (32 - lib->dir_shift);
   SeedGeom g;
-  SeedArrays cnt, cursor;
-  PostArrays post;
-  DeviceBuffer<uint32_t> start[kSeeds], cur[kSeeds], sums;
+  SeedArrays cnt, cursor, tags;
+  DeviceBuffer<uint32_t> start[kSeeds], cur[kSeeds], tag[kSeeds], sums;
   SGC_CUDA_TRY(sums.alloc((entries + kScanTile - 1) / kScanTile + 1));
   g.dir_shift = lib->dir_shift;
   for (int i = 0; i < kSeeds; ++i) {
     g.keep[i] = lib->keep[i];
     SGC_CUDA_TRY(start[i].alloc(entries));
     SGC_CUDA_TRY(cur[i].alloc(entries));
+    SGC_CUDA_TRY(tag[i].alloc(entries));
     SGC_CUDA_TRY(cudaMemsetAsync(lib->d_dir_count[i], 0, (size_t)entries * 4, 0));
+    SGC_CUDA_TRY(cudaMemsetAsync(tag[i].p, 0xFF, (size_t)entries * 4, 0));
     cnt.a[i] = lib->d_dir_count[i];
     cursor.a[i] = cur[i].p;
-    post.a[i] = lib->d_post[i];
+    tags.a[i] = tag[i].p;
   }
-  seed_count_kernel<<<blocks_for(n, T), T>>>(lib->d_keys, n, g, cnt);
+  seed_count_kernel<<<blocks_for(n, T), T>>>(lib->d_keys, n, g, cnt, tags);
   for (int i = 0; i < kSeeds; ++i) {
     int rc = exclusive_scan(lib->d_dir_count[i], entries, start[i].p, sums.p);
     if (rc) return rc;
     SGC_CUDA_TRY(cudaMemcpyAsync(cur[i].p, start[i].p, (size_t)entries * 4, cudaMemcpyDeviceToDevice, 0));
   }
-  seed_fill_kernel<WIDE><<<blocks_for(n, T), T>>>(lib->d_keys, n, g, cursor, post);
+  seed_fill_kernel<WIDE><<<blocks_for(n, T), T>>>(lib->d_keys, n, g, cursor, lib->d_post);
   for (int i = 0; i < kSeeds; ++i)
-    seed_dir_kernel<<<blocks_for(entries, T), T>>>(start[i].p, lib->d_dir_count[i], lib->d_dir[i], entries);
+    seed_dir_kernel<<<blocks_for(entries, T), T>>>(start[i].p, lib->d_dir_count[i], tag[i].p, lib->d_dir[i], entries);
   const LibView v = lib->view();
   duplicate_check_kernel<WIDE><<<blocks_for(n, T), T>>>(v, lib->d_keys, d_st);
   if (lib->with_perm)
@@ -481,7 +487,7 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
     prev = lib->part_end[i];
   }
   uint32_t dir_bits = 6;
-  while (((uint64_t)1 << dir_bits) < 4ull * n) ++dir_bits;
+  while (((uint64_t)1 << dir_bits) < 4ull * n) ++dir_bits;  // <= 24: the tag bits fit below
   lib->dir_shift = 32 - dir_bits;
   const size_t dir_entries = (size_t)1 << dir_bits;
   const size_t post_words = (size_t)n * (lib->wide ? 2 : 1);
@@ -500,8 +506,8 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   for (int i = 0; i < kSeeds; ++i) {
     SGC_CUDA_TRY(cudaMalloc(&lib->d_dir[i], dir_entries * 4));
     SGC_CUDA_TRY(cudaMalloc(&lib->d_dir_count[i], dir_entries * 4));
-    SGC_CUDA_TRY(cudaMalloc(&lib->d_post[i], post_words * 8));
   }
+  SGC_CUDA_TRY(cudaMalloc(&lib->d_post, kSeeds * post_words * 8));
   SGC_CUDA_TRY(cudaMalloc(&lib->d_front, front_bytes));
   SGC_CUDA_TRY(cudaMalloc(&lib->d_front_rev, front_bytes));
   SGC_CUDA_TRY(cudaMalloc(&lib->d_lib_hist, (size_t)k * 4 * sizeof(uint32_t)));
