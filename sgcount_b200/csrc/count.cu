@@ -508,13 +508,14 @@ struct StreamConfig {
 size_t stream_smem_bytes(const StreamConfig& c, uint32_t stage_bytes, size_t queue_bytes) {
   return (size_t)c.warps * ((size_t)c.stages * stage_bytes + kMaxStages * sizeof(uint64_t) + queue_bytes);
 }
-// Largest ring that fits: prefer 2 resident CTAs of 12 warps with >= 3 buffers per warp.
+// Largest ring that fits: prefer 2 resident CTAs of 12 warps with 2 buffers per warp (measured: the shared
+// memory a third buffer takes is worth more as L1 for the table loads).
 // SGC_WARPS / SGC_STAGES / SGC_CTAS override the choice (tuning only).
 StreamConfig pick_stream_config(uint32_t stage_bytes, size_t queue_bytes) {
   const size_t sm_budget = 227 * 1024;
   StreamConfig best{};
   const int want_warps = env_int("SGC_WARPS", 12), want_ctas = env_int("SGC_CTAS", 2);
-  const int want_stages = env_int("SGC_STAGES", 3);
+  const int want_stages = env_int("SGC_STAGES", 2);
   for (int ctas = want_ctas; ctas >= 1 && !best.stages; --ctas) {
     for (int stages = std::min(want_stages, kMaxStages); stages >= 2; --stages) {
       StreamConfig c{want_warps, stages, ctas};
