@@ -204,7 +204,7 @@ def run_gpu(args):
     import torch.distributed as dist
 
     import sgcount_b200 as sg
-    from sgcount_b200 import _cabi, synth
+    from sgcount_b200 import _cabi, shard, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -262,7 +262,7 @@ def run_gpu(args):
         counter.reset()
         counter.submit_device(d_lines.data_ptr(), n_bytes, n_reads, stride, READ_LEN)
         if world > 1:
-            dist.all_reduce(state, op=dist.ReduceOp.SUM)  # the only state that crosses GPUs
+            shard.reduce_counts(state)  # NCCL all-reduce: the only state that crosses GPUs
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -282,7 +282,7 @@ def run_gpu(args):
             counter.submit_device(d_lines.data_ptr(), n_bytes, n_reads, stride, READ_LEN)
             k_events[i][1].record()
             if world > 1:
-                dist.all_reduce(state, op=dist.ReduceOp.SUM)
+                shard.reduce_counts(state)
         end.record()
         barrier()
         sampler.active.clear()
@@ -316,7 +316,7 @@ def run_gpu(args):
         e2e_counter.reset()
         e2e_counter.submit(batch)
         if world > 1:
-            dist.all_reduce(state, op=dist.ReduceOp.SUM)
+            shard.reduce_counts(state)
         return e2e_counter.finish()
 
     for _ in range(min(args.warmup, 3)):
@@ -350,7 +350,7 @@ def run_gpu(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("count_staged_kernel_dram_bytes_per_launch")
+                traffic = json.load(open(tpath)).get("count_stream_kernel_dram_bytes_per_launch")
             except Exception:
                 traffic = None
         out = {
@@ -385,7 +385,8 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": algo_bytes,
-                         "note": "duration covers the count launches of one step (staged kernel + <256-read remainder)"},
+                         "note": "kernel = count_stream_kernel (the only count launch of a step: 50 M reads are whole 32-read tiles); "
+                                 "duration = CUDA events around sgc_counter_submit_device on the launching stream, mean over the timed steps"},
             "clocks": {"sm_mhz": clocks_kernel["sm_mhz"], "sm_max_mhz": clocks_kernel["sm_max_mhz"],
                        "reasons": clocks_kernel["reasons"], "samples": clocks_kernel["samples"],
                        "e2e_sm_mhz": clocks_e2e["sm_mhz"]},
