@@ -1,0 +1,438 @@
+// sgcount (B200 host) — the reference's command line (main.rs:54-203) and run driver
+// (count.rs:15-148) over libsgcount_cuda.so.  Everything that touches a read runs on the GPU
+// through the C ABI of include/sgcount_cuda.h; this program parses FASTA/FASTQ(.gz), keeps the
+// alias strings and writes the count table (results.rs:32-99, genemap.rs:53-86).
+//
+//   sgcount -l <library> -i <sample>... [-n names...] [-o out] [-g gene map] [-a N [-r]] [-p]
+//           [-x] [-s N] [-t N] [-q] [-z]   [--gpus N] [--device D] [--rc-keep-n]
+//
+// Differences from the reference, all documented in DESIGN.md: rows are written in library-file
+// order (the reference iterates a randomly seeded HashMap); a library byte outside A,C,G,T is an
+// error; `-t` sets the number of samples processed concurrently (one host pipeline + one CUDA
+// stream each), `--gpus` spreads them over devices.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/sgcount_cuda.h"
+#include "fastx.h"
+
+namespace {
+
+struct Fatal : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+[[noreturn]] void fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Fatal(buf);
+}
+
+void check(int rc) {
+  if (rc != SGC_OK) fail("%s", sgc_last_error());
+}
+
+struct Args {
+  std::string library_path;
+  std::vector<std::string> input_paths, sample_names;
+  bool have_names = false;
+  std::string output_path, genemap;
+  bool have_offset = false;
+  unsigned long offset = 0;
+  bool no_position_recursion = false, reverse = false, exact = false, quiet = false, include_zero = false;
+  unsigned long subsample = 5000;
+  unsigned threads = 1;
+  int gpus = 1, device = 0;
+  int rc_mode = SGC_RC_BITTRICK;
+};
+
+const char* kUsage =
+    "Usage: sgcount [OPTIONS] --library-path <LIBRARY_PATH> --input-paths <INPUT_PATHS>...\n\n"
+    "Options:\n"
+    "  -l, --library-path <LIBRARY_PATH>      Filepath of the library\n"
+    "  -i, --input-paths <INPUT_PATHS>...     Filepath(s) of fastx (fastq, fasta, *.gz) sequences to map\n"
+    "  -n, --sample-names <SAMPLE_NAMES>...   Sample Names\n"
+    "  -o, --output-path <OUTPUT_PATH>        Output filepath [default: stdout]\n"
+    "  -g, --genemap <GENEMAP>                Gene to sgRNA mapping\n"
+    "  -a, --offset <OFFSET>                  Adapter Offset\n"
+    "  -p, --no-position-recursion            Remove Position Recursion (i.e. offseting sequences by +/- 1 on mismatch condition)\n"
+    "  -r, --reverse                          Read Direction (reverse complement reads)\n"
+    "  -x, --exact                            Disallow One Off Mismatch\n"
+    "  -s, --subsample <SUBSAMPLE>            Number of Reads to Subsample in Determining Offset [default: 5000]\n"
+    "  -t, --threads <THREADS>                Number of Threads to Use for Parallel Jobs [default: 1]\n"
+    "  -q, --quiet                            Does not show progress\n"
+    "  -z, --include-zero                     Include zero count sgRNAs in output table\n"
+    "      --gpus <N>                         Spread the samples over N devices [default: 1]\n"
+    "      --device <D>                       First device to use [default: 0]\n"
+    "      --rc-keep-n                        Reverse complement keeps N (default: the fxread bit trick, N -> J)\n"
+    "  -h, --help                             Print help\n";
+
+unsigned long parse_uint(const std::string& flag, const char* v) {
+  char* end = nullptr;
+  if (!v || !*v || *v == '-') fail("invalid value for '%s'", flag.c_str());
+  unsigned long x = strtoul(v, &end, 10);
+  if (*end) fail("invalid value '%s' for '%s'", v, flag.c_str());
+  return x;
+}
+
+Args parse_args(int argc, char** argv) {
+  Args a;
+  auto is_flag = [](const char* s) { return s[0] == '-' && s[1] != '\0'; };
+  for (int i = 1; i < argc; ++i) {
+    std::string f = argv[i];
+    auto value = [&]() -> const char* {
+      if (i + 1 >= argc) fail("a value is required for '%s' but none was supplied", f.c_str());
+      return argv[++i];
+    };
+    auto values = [&](std::vector<std::string>& out) {  // clap num_args = 1..
+      while (i + 1 < argc && !is_flag(argv[i + 1])) out.push_back(argv[++i]);
+      if (out.empty()) fail("a value is required for '%s' but none was supplied", f.c_str());
+    };
+    if (f == "-l" || f == "--library-path") a.library_path = value();
+    else if (f == "-i" || f == "--input-paths") values(a.input_paths);
+    else if (f == "-n" || f == "--sample-names") { values(a.sample_names); a.have_names = true; }
+    else if (f == "-o" || f == "--output-path") a.output_path = value();
+    else if (f == "-g" || f == "--genemap") a.genemap = value();
+    else if (f == "-a" || f == "--offset") { a.offset = parse_uint(f, value()); a.have_offset = true; }
+    else if (f == "-p" || f == "--no-position-recursion") a.no_position_recursion = true;
+    else if (f == "-r" || f == "--reverse") a.reverse = true;
+    else if (f == "-x" || f == "--exact") a.exact = true;
+    else if (f == "-s" || f == "--subsample") a.subsample = parse_uint(f, value());
+    else if (f == "-t" || f == "--threads") a.threads = (unsigned)parse_uint(f, value());
+    else if (f == "-q" || f == "--quiet") a.quiet = true;
+    else if (f == "-z" || f == "--include-zero") a.include_zero = true;
+    else if (f == "--gpus") a.gpus = (int)parse_uint(f, value());
+    else if (f == "--device") a.device = (int)parse_uint(f, value());
+    else if (f == "--rc-keep-n") a.rc_mode = SGC_RC_KEEP_N;
+    else if (f == "-h" || f == "--help") { fputs(kUsage, stdout); exit(0); }
+    else fail("unexpected argument '%s' found", f.c_str());
+  }
+  if (a.library_path.empty()) fail("the following required arguments were not provided:\n  --library-path <LIBRARY_PATH>");
+  if (a.input_paths.empty()) fail("the following required arguments were not provided:\n  --input-paths <INPUT_PATHS>...");
+  if (a.threads == 0) a.threads = 1;
+  if (a.gpus < 1) a.gpus = 1;
+  return a;
+}
+
+bool exists(const std::string& p) {
+  FILE* f = fopen(p.c_str(), "rb");
+  if (f) fclose(f);
+  return f != nullptr;
+}
+
+// utils.rs:18-49
+std::vector<std::string> generate_sample_names(const std::vector<std::string>& paths) {
+  auto trim = [](std::string& s, const char* suffix) {
+    const size_t n = strlen(suffix);
+    while (s.size() >= n && s.compare(s.size() - n, n, suffix) == 0) s.erase(s.size() - n);  // trim_end_matches repeats
+  };
+  std::vector<std::string> base, simple;
+  std::unordered_set<std::string> seen;
+  for (size_t i = 0; i < paths.size(); ++i) {
+    std::string b = paths[i].substr(paths[i].find_last_of('/') == std::string::npos ? 0 : paths[i].find_last_of('/') + 1);
+    for (const char* suf : {".gz", ".fasta", ".fastq", ".fa", ".fq"}) trim(b, suf);
+    base.push_back(b);
+    seen.insert(b);
+    simple.push_back("Sample." + std::to_string(i));
+  }
+  if (seen.size() == base.size()) return base;
+  fprintf(stderr, "WARNING: Duplicate Basenames Detected, Using incrementing sample names\n");
+  return simple;
+}
+
+// library.rs:17-99: sequences and aliases in file order
+struct HostLibrary {
+  std::vector<std::string> aliases;
+  std::string seqs;  // n * k bytes
+  uint32_t n = 0, k = 0;
+};
+
+HostLibrary load_library(const std::string& path) {
+  HostLibrary lib;
+  sgh::FastxReader reader(path);
+  const char *id, *seq;
+  size_t id_len, seq_len;
+  bool inconsistent = false;
+  while (reader.next(id, id_len, seq, seq_len)) {
+    if (lib.n == 0) lib.k = (uint32_t)seq_len;
+    if (seq_len != lib.k) inconsistent = true;
+    lib.aliases.emplace_back(id, id_len);
+    if (!inconsistent) lib.seqs.append(seq, seq_len);
+    ++lib.n;
+  }
+  if (lib.n == 0) fail("empty library: %s", path.c_str());  // library.rs:74 unwraps
+  if (inconsistent) fail("Library sequence sizes are inconsistent");  // library.rs:83
+  return lib;
+}
+
+// genemap.rs:53-86
+std::unordered_map<std::string, std::string> load_genemap(const std::string& path) {
+  if (!exists(path)) fail("Provided gene mapping path doesn't exist: %s", path.c_str());
+  std::ifstream in(path, std::ios::binary);
+  std::unordered_map<std::string, std::string> map;
+  std::string line;
+  while (std::getline(in, line)) {
+    const size_t tab = line.find('\t');
+    if (tab == std::string::npos) fail("Missing '\\t' in gene map");
+    std::string sgrna = line.substr(tab + 1);
+    if (!map.emplace(sgrna, line.substr(0, tab)).second) fail("Duplicate sgRNA key found in gene map: %s", sgrna.c_str());
+  }
+  return map;
+}
+
+// Sequence lines of a run of records, as the kernels take them.
+struct Batch {
+  uint8_t* lines = nullptr;  // pinned
+  size_t cap = 0, used = 0;
+  std::vector<uint32_t> off;  // n + 1 line starts
+  bool uniform = true;        // every read as long as the first
+  size_t first_len = 0;
+  uint64_t n = 0;
+
+  void reset() {
+    used = 0;
+    n = 0;
+    uniform = true;
+    off.assign(1, 0u);
+  }
+  bool push(const char* seq, size_t len) {
+    if (used + len + 1 > cap || used + len + 1 >= (1ull << 32)) return false;
+    if (n == 0) first_len = len;
+    uniform &= len == first_len;
+    memcpy(lines + used, seq, len);
+    lines[used + len] = '\n';
+    used += len + 1;
+    off.push_back((uint32_t)used);
+    ++n;
+    return true;
+  }
+};
+
+void submit(sgc_counter* c, const Batch& b) {
+  if (b.n == 0) return;
+  if (b.uniform)  // fixed stride selects the streaming kernel
+    check(sgc_counter_submit(c, b.lines, b.used, nullptr, (uint32_t)b.first_len + 1, (uint32_t)b.first_len, b.n));
+  else
+    check(sgc_counter_submit(c, b.lines, b.used, b.off.data(), 0, 0, b.n));
+}
+
+struct OffsetValue {
+  bool reverse;
+  uint32_t index;
+};
+std::string to_string(const OffsetValue& o) {
+  return std::string(o.reverse ? "Reverse(" : "Forward(") + std::to_string(o.index) + ")";
+}
+
+// entropy_offset for one sample (offsetter.rs:192-200): the first `subsample` records
+OffsetValue detect_offset(const sgc_library* lib, const std::string& path, unsigned long subsample) {
+  sgh::FastxReader reader(path);
+  std::vector<uint8_t> lines;
+  std::vector<uint32_t> off{0};
+  const char *id, *seq;
+  size_t id_len, seq_len;
+  for (unsigned long i = 0; i < subsample && reader.next(id, id_len, seq, seq_len); ++i) {
+    lines.insert(lines.end(), seq, seq + seq_len);
+    lines.push_back('\n');
+    off.push_back((uint32_t)lines.size());
+  }
+  int rev = 0;
+  uint32_t idx = 0;
+  check(sgc_offset_detect(lib, lines.data(), lines.size(), off.data(), 0, 0, off.size() - 1, &rev, &idx));
+  return OffsetValue{rev != 0, idx};
+}
+
+struct SampleResult {
+  std::vector<uint64_t> counts;
+  uint64_t total = 0, matched = 0;
+};
+
+// count_sample (count.rs:15-45): parse on this thread into two pinned buffers; the copy and
+// the kernel of one batch overlap the parsing of the next.
+SampleResult count_sample(const sgc_library* lib, uint32_t n_guides, const std::string& path, OffsetValue offset,
+                          bool recursion, int rc_mode) {
+  sgc_counter* c = nullptr;
+  check(sgc_counter_create(lib, offset.reverse, offset.index, recursion, rc_mode, nullptr, nullptr, &c));
+  struct Guard {
+    sgc_counter* c;
+    Batch b[2];
+    ~Guard() {
+      sgc_counter_destroy(c);
+      for (auto& x : b)
+        if (x.lines) sgc_host_free(x.lines);
+    }
+  } g{c, {}};
+  const size_t cap = 64u << 20;
+  for (auto& b : g.b) {
+    void* p = nullptr;
+    check(sgc_host_alloc(&p, cap));
+    b.lines = static_cast<uint8_t*>(p);
+    b.cap = cap;
+    b.reset();
+  }
+  sgh::FastxReader reader(path);
+  const char *id, *seq;
+  size_t id_len, seq_len;
+  int cur = 0;
+  bool other_in_flight = false;
+  while (reader.next(id, id_len, seq, seq_len)) {
+    if (seq_len + 1 > cap) fail("a sequence line longer than %zu bytes", cap);
+    if (!g.b[cur].push(seq, seq_len)) {
+      submit(c, g.b[cur]);
+      cur ^= 1;
+      if (other_in_flight) check(sgc_counter_sync(c));  // the buffer we are about to refill has been consumed
+      other_in_flight = true;
+      g.b[cur].reset();
+      g.b[cur].push(seq, seq_len);
+    }
+  }
+  submit(c, g.b[cur]);
+  SampleResult r;
+  r.counts.resize(n_guides);
+  check(sgc_counter_finish(c, r.counts.data(), &r.total, &r.matched));
+  return r;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  try {
+    Args args = parse_args(argc, argv);
+    for (const auto& p : args.input_paths)
+      if (!exists(p)) fail("Provided filepath does not exist: %s", p.c_str());  // main.rs:130-140
+    std::vector<std::string> names;
+    if (args.have_names) {
+      if (args.sample_names.size() != args.input_paths.size())
+        fail("Must provide as many sample names as there are input files");  // main.rs:156
+      names = args.sample_names;
+    } else {
+      names = generate_sample_names(args.input_paths);
+    }
+    const size_t n_samples = args.input_paths.size();
+
+    HostLibrary hlib = load_library(args.library_path);
+    std::unordered_map<std::string, std::string> genemap;
+    const bool have_genemap = !args.genemap.empty();
+    if (have_genemap) {
+      genemap = load_genemap(args.genemap);
+      for (const auto& alias : hlib.aliases)  // count.rs:90-95
+        if (!genemap.count(alias)) fail("Missing sgRNA aliases in gene map: \"%s\"", alias.c_str());
+    }
+    // validate_library_size (count.rs:62-71)
+    for (const auto& p : args.input_paths) {
+      sgh::FastxReader r(p);
+      const char *id, *seq;
+      size_t id_len, seq_len;
+      if (!r.next(id, id_len, seq, seq_len)) fail("empty reader: %s", p.c_str());
+      if (hlib.k > seq_len)
+        fail("Sequences in reference library are larger than the sequences in input.\n\nConsider reducing the length of "
+             "your reference sequences (i.e. extracting the variable region of the sgRNA or reducing the length of the "
+             "adapters.)");
+    }
+
+    int ndev = 0;
+    check(sgc_device_count(&ndev));
+    if (ndev == 0) fail("no CUDA device: this build has no CPU fallback");
+    if (args.device >= ndev) fail("no such device: %d", args.device);
+    const int gpus = std::min(args.gpus, ndev - args.device);
+    // one table per device; -x builds no Permuter (count.rs:103-107)
+    std::vector<sgc_library*> libs(gpus, nullptr);
+    struct LibGuard {
+      std::vector<sgc_library*>& l;
+      ~LibGuard() {
+        for (auto* x : l) sgc_library_destroy(x);
+      }
+    } lib_guard{libs};
+    for (int d = 0; d < gpus; ++d)
+      check(sgc_library_create(args.device + d, reinterpret_cast<const uint8_t*>(hlib.seqs.data()), hlib.n, hlib.k,
+                               args.exact ? 0 : 1, &libs[d]));
+
+    std::vector<OffsetValue> offsets(n_samples);
+    if (args.have_offset) {
+      for (auto& o : offsets) o = OffsetValue{args.reverse, (uint32_t)args.offset};  // main.rs:163-170
+    } else {
+      for (size_t s = 0; s < n_samples; ++s) offsets[s] = detect_offset(libs[0], args.input_paths[s], args.subsample);
+      if (!args.quiet) {
+        std::string msg = "Calculated Offsets: [";
+        for (size_t s = 0; s < n_samples; ++s) msg += (s ? ", " : "") + to_string(offsets[s]);
+        fprintf(stderr, "%s]\n", msg.c_str());  // main.rs:125
+      }
+    }
+
+    // the reference's only fan-out: samples in parallel (count.rs:117-136)
+    std::vector<SampleResult> results(n_samples);
+    std::atomic<size_t> next{0};
+    std::mutex err_mu;
+    std::string first_error;
+    const unsigned workers = (unsigned)std::min<size_t>(std::max(args.threads, (unsigned)gpus), n_samples);
+    auto work = [&]() {
+      for (;;) {
+        const size_t s = next.fetch_add(1);
+        if (s >= n_samples) return;
+        try {
+          results[s] = count_sample(libs[s % gpus], hlib.n, args.input_paths[s], offsets[s], !args.no_position_recursion,
+                                    args.rc_mode);
+          if (!args.quiet) {
+            const SampleResult& r = results[s];
+            fprintf(stderr, "Finished: %s; Fraction mapped: %.3f [%llu / %llu]\n", names[s].c_str(),
+                    r.total ? (double)r.matched / (double)r.total : 0.0 / 0.0, (unsigned long long)r.matched,
+                    (unsigned long long)r.total);  // count.rs:36-42
+          }
+        } catch (const std::exception& e) {
+          std::lock_guard<std::mutex> lk(err_mu);
+          if (first_error.empty()) first_error = e.what();
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < workers; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (!first_error.empty()) fail("%s", first_error.c_str());
+
+    // write_results (results.rs:71-99).  Counts are keyed by alias (counter.rs:232-235):
+    // sequences that share a header print the combined count on each of their rows.
+    std::unordered_map<std::string, std::vector<uint32_t>> by_alias;
+    for (uint32_t i = 0; i < hlib.n; ++i) by_alias[hlib.aliases[i]].push_back(i);
+    FILE* out = args.output_path.empty() ? stdout : fopen(args.output_path.c_str(), "wb");
+    if (!out) fail("cannot create %s", args.output_path.c_str());
+    std::string text = "Guide";
+    for (size_t s = 0; s < n_samples; ++s) {
+      if (s == 0 && have_genemap) text += "\tGene";
+      text += "\t" + names[s];
+    }
+    text += "\n";
+    for (uint32_t i = 0; i < hlib.n; ++i) {
+      const std::string& alias = hlib.aliases[i];
+      std::string row = alias;
+      unsigned long long row_total = 0;
+      for (size_t s = 0; s < n_samples; ++s) {
+        if (s == 0 && have_genemap) row += "\t" + genemap.at(alias);
+        unsigned long long v = 0;
+        for (uint32_t j : by_alias[alias]) v += results[s].counts[j];
+        row += "\t" + std::to_string(v);
+        row_total += v;
+      }
+      if (args.include_zero || row_total > 0) text += row + "\n";
+    }
+    fwrite(text.data(), 1, text.size(), out);
+    if (out != stdout) fclose(out);
+    return 0;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "Error: %s\n", e.what());
+    return 1;
+  }
+}

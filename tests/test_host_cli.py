@@ -1,0 +1,142 @@
+"""The C++ host `sgcount` (sgcount_b200/host): the reference's command line over the C ABI.
+
+CPU part: flag surface and the validations the reference performs before it touches a read
+(main.rs:130-160, count.rs:62-100, library.rs:83, genemap.rs:53-68).  GPU part: whole runs
+on the example fixtures compared with the oracle's table (results.rs:71-99 restated in
+oracle.render_results) and the golden counts."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "sgcount_b200", "lib", "sgcount")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not os.path.exists(BIN):
+        import __graft_entry__ as g
+
+        g.build()
+    assert os.path.exists(BIN)
+
+
+def run(*args, check=False):
+    p = subprocess.run([BIN, *args], capture_output=True, text=True, timeout=300)
+    if check:
+        assert p.returncode == 0, p.stderr
+    return p
+
+
+def test_help_lists_the_reference_flags():
+    p = run("--help", check=True)
+    for flag in ["-l, --library-path", "-i, --input-paths", "-n, --sample-names", "-o, --output-path", "-g, --genemap",
+                 "-a, --offset", "-p, --no-position-recursion", "-r, --reverse", "-x, --exact", "-s, --subsample",
+                 "-t, --threads", "-q, --quiet", "-z, --include-zero"]:
+        assert flag in p.stdout
+
+
+def test_required_arguments_and_unknown_flags():
+    assert run().returncode == 1
+    assert "--library-path" in run("-i", "x").stderr
+    assert "--input-paths" in run("-l", "x").stderr
+    assert "unexpected argument" in run("-l", "x", "-i", "y", "--frobnicate").stderr
+
+
+def test_validations_before_any_read_is_counted(example_dir, tmp_path):
+    lib = os.path.join(example_dir, "library.fasta.gz")
+    seq = os.path.join(example_dir, "sequence.fastq.gz")
+    p = run("-l", lib, "-i", str(tmp_path / "missing.fq"))
+    assert p.returncode == 1 and "Provided filepath does not exist" in p.stderr  # main.rs:133
+    p = run("-l", lib, "-i", seq, seq, "-n", "only_one")
+    assert "Must provide as many sample names as there are input files" in p.stderr  # main.rs:156
+    bad = tmp_path / "ragged.fa"
+    bad.write_text(">a\nACGT\n>b\nACG\n")
+    p = run("-l", str(bad), "-i", seq)
+    assert "Library sequence sizes are inconsistent" in p.stderr  # library.rs:83
+    g = tmp_path / "g2s.txt"
+    g.write_text("gene.0\tlib.0\n")
+    p = run("-l", lib, "-i", seq, "-g", str(g))
+    assert "Missing sgRNA aliases in gene map" in p.stderr  # count.rs:90-95
+    g.write_text("gene.0 lib.0\n")
+    assert "Missing '\\t' in gene map" in run("-l", lib, "-i", seq, "-g", str(g)).stderr  # genemap.rs:58
+    g.write_text("gene.0\tlib.0\ngene.1\tlib.0\n")
+    assert "Duplicate sgRNA key" in run("-l", lib, "-i", seq, "-g", str(g)).stderr  # genemap.rs:60
+    short = tmp_path / "short.fq"
+    short.write_text("@r\nACGTACGT\n+\nIIIIIIII\n")
+    p = run("-l", lib, "-i", str(short))
+    assert "Sequences in reference library are larger than the sequences in input" in p.stderr  # count.rs:98-100
+
+
+# ---- whole runs (GPU) ------------------------------------------------------------------------
+
+def table(text):
+    lines = text.rstrip("\n").split("\n")
+    return lines[0], sorted(lines[1:])
+
+
+@pytest.mark.gpu
+def test_example_run_matches_the_oracle_table(example_dir, expected, tmp_path):
+    lib = os.path.join(example_dir, "library.fasta.gz")
+    names = ["sequence", "zero.sequence", "diff.sequence", "offset", "offset_clipped"]
+    paths = [os.path.join(example_dir, n + ".fastq.gz") for n in names]
+    out = tmp_path / "counts.tsv"
+    p = run("-l", lib, "-i", *paths, "-g", os.path.join(example_dir, "g2s.txt"), "-o", str(out), "-t", "3", check=True)
+    assert "Calculated Offsets: [Forward(5), Forward(5), Forward(5), Forward(5), Forward(5)]" in p.stderr
+    for n in names:
+        fx = expected["fixtures"][n]
+        frac = fx["matched_reads"] / fx["total_reads"]
+        assert f"Finished: {n}; Fraction mapped: {frac:.3f} [{fx['matched_reads']} / {fx['total_reads']}]" in p.stderr
+
+    olib_recs = orc.Records.from_path(lib)
+    olib = orc.Library.from_reader(olib_recs)
+    operm = orc.Permuter.new(olib)
+    counters = [orc.Counter.new(orc.Records.from_path(x), olib, operm, orc.Offset.Forward(5)) for x in paths]
+    g2s = open(os.path.join(example_dir, "g2s.txt"), "rb").read()
+    want = orc.render_results(counters, names, olib, g2s, include_zero=False)
+    assert table(out.read_text()) == table(want)
+    first = out.read_text().split("\n")[1].split("\t")
+    assert first[:2] == ["lib.0", "gene.0"] and int(first[2]) == expected["fixtures"]["sequence"]["counts"][0]
+
+
+@pytest.mark.gpu
+def test_flags_exact_offset_zero_rows_names_and_stdout(example_dir, expected, tmp_path):
+    lib = os.path.join(example_dir, "library.fasta.gz")
+    zero = os.path.join(example_dir, "zero.sequence.fastq.gz")
+    p = run("-l", lib, "-i", zero, "-x", "-a", "5", "-q", "-n", "Z", check=True)
+    assert p.stderr == ""
+    head, rows = table(p.stdout)
+    assert head == "Guide\tZ" and len(rows) == 90  # zero rows dropped (results.rs:90-94)
+    p = run("-l", lib, "-i", zero, "-x", "-a", "5", "-q", "-z", check=True)
+    head, rows = table(p.stdout)
+    assert head == "Guide\tzero.sequence" and len(rows) == 100
+    counts = {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows}
+    assert [counts[f"lib.{i}"] for i in range(100)] == expected["fixtures"]["zero.sequence"]["counts"]
+    # a wrong manual offset without recursion finds nothing; with recursion offset 4 finds all (Plus)
+    p = run("-l", lib, "-i", zero, "-x", "-a", "4", "-p", "-q", "-z", check=True)
+    assert all(r.endswith("\t0") for r in table(p.stdout)[1])
+    p = run("-l", lib, "-i", zero, "-x", "-a", "4", "-q", check=True)
+    assert len(table(p.stdout)[1]) == 90
+
+
+@pytest.mark.gpu
+def test_reverse_reads_plain_fasta_and_multi_member_gzip(example_dir, tmp_path):
+    """reverse-complemented copies of the fixture, written as a two-member gzip FASTA"""
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    seqs = [l for l in gzip.open(os.path.join(example_dir, "sequence.fastq.gz"), "rb").read().split(b"\n")[1::4]]
+    rc = [s.translate(comp)[::-1] for s in seqs]
+    path = tmp_path / "rev.fa.gz"
+    half = len(rc) // 2
+    with open(path, "wb") as f:
+        for part in (rc[:half], rc[half:]):
+            f.write(gzip.compress(b"".join(b">r\n" + s + b"\n" for s in part)))
+    lib = os.path.join(example_dir, "library.fasta.gz")
+    p = run("-l", lib, "-i", os.path.join(example_dir, "sequence.fastq.gz"), str(path), check=True)
+    assert "Calculated Offsets: [Forward(5), Reverse(5)]" in p.stderr
+    head, rows = table(p.stdout)
+    assert head == "Guide\tsequence\trev"  # utils.rs:24-28 strips .gz then .fa
+    assert all(r.split("\t")[1] == r.split("\t")[2] for r in rows) and len(rows) == 100
