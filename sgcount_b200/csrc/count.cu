@@ -12,9 +12,11 @@
 //                                       ONE 32-byte front-table bucket -> RED.64 on the guide;
 //                            slow path  reads the fast path cannot settle (a mismatch, an N,
 //                                       a shifted guide, junk; 10-20 %) are parked in a
-//                                       warp-private shared-memory queue and, 32 at a time,
-//                                       walk Counter::assign over the seed index with every
-//                                       lane busy.
+//                                       warp-private shared-memory queue as (span words, read,
+//                                       position).  32 at a time, with every lane busy, each
+//                                       parked read tries ONE position of Counter::assign
+//                                       against the seed index and, if that misses, goes back
+//                                       on the queue for the next position.
 //   count_generic_kernel : any layout (variable-length lines via u32 offsets, unaligned
 //                          buffers, tile remainders); one thread per read, byte loads.
 // Per-guide counts are 64-bit atomics in the L2-resident state vector; matched reads are
@@ -36,7 +38,7 @@ struct CountParams {
   uint64_t first_read;       // index of the first read this launch handles
   uint32_t stride, read_len;
   int offset;
-  uint8_t with_perm, reverse, recursion, wild_byte;
+  uint8_t with_perm, reverse, recursion, rc_mode;
   unsigned long long* state;  // counts[n_guides], total, matched
   uint32_t n_guides;
   int32_t* assign_out;
@@ -61,37 +63,26 @@ __device__ __forceinline__ void flush_matched(const CountParams& p, uint32_t mat
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.state + p.n_guides, (unsigned long long)p.n_reads);
 }
 
-// Oriented span geometry of a read of length n: the bases a Centered/Plus/Minus window can
-// touch are oriented positions [max(offset,1)-1, min(offset+k+1, n)).
-struct SpanGeom {
-  int base;  // oriented position of span base 0
-  int m;     // number of bases
-  int src;   // position in the read (as stored) of the first span byte
-};
-__host__ __device__ __forceinline__ SpanGeom span_geom(int n, int offset, int k, bool reverse) {
-  SpanGeom g;
-  g.base = offset > 0 ? offset - 1 : 0;
-  int end = offset + k + 1 < n ? offset + k + 1 : n;
-  g.m = end > g.base ? end - g.base : 0;
-  g.src = reverse ? n - end : g.base;  // revcomp(r)[a:b] == comp(reverse(r[n-b : n-a]))
-  return g;
-}
-
-__device__ __forceinline__ void orient(Span& sp, int m, bool reverse) {
-  if (reverse && m > 0) {
-    sp.codes = revcomp_codes(sp.codes, m);
-    sp.bad = reverse_bits(sp.bad, m);
-    sp.wild = reverse_bits(sp.wild, m);
+// Record::seq_rev_comp of the fxread crate on one byte
+__device__ __forceinline__ uint8_t complement_byte(uint8_t c, int rc_mode) {
+  if (rc_mode == SGC_RC_BITTRICK) return (c & 2) ? (c ^ 4) : (c ^ 21);
+  switch (c) {
+    case 'A': return 'T';
+    case 'C': return 'G';
+    case 'G': return 'C';
+    case 'T': return 'A';
+    default: return c;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// generic kernel
+// generic kernel: Counter::assign (counter.rs:96-140) spelled out on the oriented bytes
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
   uint32_t matched = 0;
   const uint64_t policy = l2_evict_last_policy();
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  const int k = (int)p.lib.k;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_reads; i += nthreads) {
     const uint64_t r = p.first_read + i;
     uint64_t start;
@@ -103,19 +94,38 @@ __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
       start = r * p.stride;
       n = (int)p.read_len;
     }
-    const SpanGeom g = span_geom(n, p.offset, (int)p.lib.k, p.reverse);
-    Span sp{0, 0, 0};
-    const uint8_t* s = p.lines + start + g.src;
-    for (int j = 0; j < g.m; ++j) {
-      uint8_t c = s[j];
-      sp.codes |= (uint64_t)code_of(c) << (2 * j);
-      if (!is_acgt(c)) {
-        sp.bad |= 1u << j;
-        if (c == p.wild_byte) sp.wild |= 1u << j;
+    const uint8_t* s = p.lines + start;
+    int32_t hit = kMiss;
+    const int npos = p.recursion ? 3 : 1;
+    for (int pos = 0; pos < npos && hit == kMiss; ++pos) {
+      // Centered/Null: offset; Plus: offset+1; Minus: offset-1 (counter.rs:164-174)
+      int lo;
+      if (pos == 0) {
+        lo = p.offset;
+      } else if (pos == 1) {
+        lo = p.offset + 1;
+      } else {
+        if (p.offset == 0) break;  // checked_sub(1) -> None
+        lo = p.offset - 1;
       }
+      if (lo + k > n) break;  // a failed trim RETURNS (counter.rs:105-108,175-176)
+      Key key{0, 0};
+      int nbad = 0;
+      uint32_t bad_pos = 0;
+      bool wild = false;
+      for (int j = 0; j < k; ++j) {
+        // forward: the read itself; reverse: byte lo+j of the reverse complement (counter.rs:196-204)
+        const uint8_t c = p.reverse ? complement_byte(s[n - 1 - (lo + j)], p.rc_mode) : s[lo + j];
+        key_set_base(key, (uint32_t)j, p.lib.wide, code_of(c));
+        if (!is_acgt(c)) {
+          ++nbad;
+          bad_pos = (uint32_t)j;
+          wild = c == 'N';
+        }
+      }
+      hit = p.lib.wide ? window_lookup_t<true>(p.lib, p.lib.fwd, p.with_perm, key, nbad, bad_pos, wild, nullptr, policy)
+                       : window_lookup_t<false>(p.lib, p.lib.fwd, p.with_perm, key, nbad, bad_pos, wild, nullptr, policy);
     }
-    orient(sp, g.m, p.reverse);
-    int32_t hit = assign_span(p.lib, p.with_perm, sp, g.base, n, p.offset, p.recursion, nullptr, policy);
     record_hit(p, hit, r, matched);
   }
   flush_matched(p, matched);
@@ -132,6 +142,7 @@ __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
 constexpr int kWarpReads = 32;
 constexpr int kMaxStages = 4;
 constexpr int kQueueCap = 64;  // <= 31 parked + 32 new
+constexpr uint32_t kReadIdxBits = 30;  // queue word: position << 30 | read index
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -163,10 +174,9 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
       : "memory");
 }
 
-// 4-bit mask of the non-zero bytes of x
-__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) {
-  const uint32_t nz = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
-  return ((nz >> 7) * 0x10204080u) >> 28;
+// bit 7 of every non-zero byte of x
+__device__ __forceinline__ uint32_t nonzero_byte_flags(uint32_t x) {
+  return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
 }
 
 // XOR of a word of four sequence bytes against the ASCII its 2-bit codes stand for
@@ -176,25 +186,53 @@ __device__ __forceinline__ uint32_t ascii_residue(uint32_t w) {
   return ((w & 0xF9F9F9F9u) ^ (is_t * 0x11u)) ^ 0x41414141u;
 }
 
-// Parked reads keep the raw span words; everything else is re-derived when a full warp of
-// them is drained, so parking costs a handful of shared-memory stores.
-// Layout per warp (words): w[NW + 2][kQueueCap] | read[kQueueCap]
+// The k window bytes, given as NW window-aligned words, as interleaved key + residues.
+// Returns the OR of the residues (zero iff every window byte is A/C/G/T).
+template <int NW, bool WIDE>
+__device__ __forceinline__ uint32_t pack_window(const uint32_t (&w)[NW], int n_words, uint32_t last_mask, Key& key,
+                                                uint32_t (&x)[NW]) {
+  uint32_t lo = 0, hi = 0, any = 0;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    x[i] = ascii_residue(w[i]);
+    uint32_t c = (w[i] >> 1) & 0x03030303u;
+    if (NW != 5 || i == NW - 1) {  // bytes past the window (NW = 5: only the last word can have any)
+      const uint32_t mk = i < n_words - 1 ? ~0u : (i == n_words - 1 ? last_mask : 0u);
+      x[i] &= mk;
+      c &= mk;
+    }
+    any |= x[i];
+    if (i < 4)
+      lo += c << (2 * i);
+    else
+      hi += c << (2 * (i - 4));
+  }
+  if (!WIDE) hi = (hi * 0x01041040u) >> 24;
+  key = Key{lo, hi};
+  return any;
+}
+
+// Parked reads: NW + 1 span words (the bytes from one before the Centered window on, so the
+// entry does not depend on the lane that parked it) and position << 30 | read index.
 template <int NW>
 struct WarpQueueT {
-  uint32_t w[NW + 2][kQueueCap];
-  uint32_t read[kQueueCap];  // read index relative to the launch's first read
+  uint32_t w[NW + 1][kQueueCap];
+  uint32_t tag[kQueueCap];
 };
 
 // Geometry of the streaming kernel: every read has the same length, so it is warp uniform.
+// Positions are in STORED coordinates: for a reverse read the oriented window [o, o+k) is the
+// stored window [n-o-k, n-o), Plus (o+1) is one byte EARLIER and Minus one byte later.
 struct StreamGeom {
   int k, n, o;
-  bool reverse, recursion, with_perm;
-  int lead;       // stored bytes kept before the window (1 if the neighbouring position can be tried)
-  int m;          // span bytes: lead + k + trail
-  int span_base;  // oriented position of the first oriented span base
-  int n_words;    // words holding the k window bytes
+  bool with_perm;
+  int win_src;             // stored position of the Centered window
+  int lead;                // 1 if the span starts one byte before the Centered window
+  uint32_t shift_bits[3];  // where the Centered / Plus / Minus window starts in the span, in bits
+  bool try_plus, try_minus;  // the position exists (its trim succeeds) and recursion is on
+  int n_words;             // words holding the k window bytes
   uint32_t last_mask;
-  uint32_t wild_byte;
+  uint32_t wild_byte;      // the stored byte the lookup sees as 'N'
 };
 
 __device__ __forceinline__ StreamGeom make_geom(const CountParams& p) {
@@ -202,51 +240,55 @@ __device__ __forceinline__ StreamGeom make_geom(const CountParams& p) {
   g.k = (int)p.lib.k;
   g.n = (int)p.read_len;
   g.o = p.offset;
-  g.reverse = p.reverse;
-  g.recursion = p.recursion;
   g.with_perm = p.with_perm;
-  const bool before = g.o > 0, after = g.o + g.k < g.n;  // oriented neighbours (Minus / Plus)
-  g.lead = (g.reverse ? after : before) ? 1 : 0;
-  g.m = g.k + (before ? 1 : 0) + (after ? 1 : 0);
-  g.span_base = g.o - (before ? 1 : 0);
+  // Plus is tried after a Centered miss if its trim succeeds; Minus after a Plus miss if
+  // offset >= 1 (a failed trim returns, counter.rs:105-108: no Plus means no Minus either)
+  g.try_plus = p.recursion && g.o + 1 + g.k <= g.n;
+  g.try_minus = g.try_plus && g.o >= 1;
+  g.win_src = p.reverse ? g.n - g.o - g.k : g.o;
+  const int d_plus = p.reverse ? -1 : 1;  // stored displacement of the Plus window
+  const bool before = (g.try_plus && d_plus < 0) || (g.try_minus && d_plus > 0);
+  g.lead = before ? 1 : 0;
+  g.shift_bits[0] = 8u * (uint32_t)g.lead;
+  g.shift_bits[1] = 8u * (uint32_t)(g.lead + d_plus);
+  g.shift_bits[2] = 8u * (uint32_t)(g.lead - d_plus);
   g.n_words = (g.k + 3) >> 2;
   g.last_mask = (g.k & 3) ? ((1u << (8 * (g.k & 3))) - 1) : ~0u;
-  g.wild_byte = p.wild_byte;
+  // under the fxread bit trick a reverse-complemented 'J' reads as 'N' (and 'N' as 'J')
+  g.wild_byte = (p.reverse && p.rc_mode == SGC_RC_BITTRICK) ? (uint32_t)'J' : (uint32_t)'N';
   return g;
 }
 
-// Full Counter::assign (counter.rs:96-140) for one parked read.  W holds the span words as
-// they sat in the tile; the span starts `off` bytes into W[0].
+// One position of Counter::assign (counter.rs:111-117) for one parked read: the window that
+// starts `shift` bits into the span S.
 template <int NW, bool WIDE>
-__device__ __forceinline__ int32_t walk_parked(const LibView& v, const StreamGeom& g, const uint32_t (&W)[NW + 2],
-                                               uint32_t off_bits, uint64_t policy) {
-  constexpr int kSpanWords = NW + 1 < 8 ? NW + 1 : 8;  // m <= 32 bases
-  Span sp{0, 0, 0};
-  const uint32_t wild4 = 0x01010101u * g.wild_byte;
-  uint32_t any = 0;
-  uint32_t xs[kSpanWords], aw[kSpanWords];
+__device__ __forceinline__ int32_t try_position(const LibView& v, const IndexView& ix, const StreamGeom& g,
+                                                const uint32_t (&S)[NW + 1], uint32_t shift, uint64_t policy) {
+  uint32_t w[NW], x[NW];
 #pragma unroll
-  for (int i = 0; i < kSpanWords; ++i) {
-    aw[i] = __funnelshift_r(W[i], W[i + 1], off_bits);
-    const uint32_t c = (aw[i] >> 1) & 0x03030303u;
-    const uint32_t packed = (c * 0x01041040u) >> 24;  // gather 4 x 2 bits, base order
-    sp.codes |= (uint64_t)packed << (8 * i);
-    xs[i] = ascii_residue(aw[i]);
-    any |= xs[i];
-  }
-  const uint32_t mmask = g.m >= 32 ? ~0u : ((1u << g.m) - 1);
-  // `any` may come from bytes past the span; the masks below are exact
-  if (any) {
+  for (int i = 0; i < NW; ++i) w[i] = __funnelshift_r(S[i], S[i + 1], shift);  // shift <= 16
+  Key key;
+  const uint32_t any = pack_window<NW, WIDE>(w, g.n_words, g.last_mask, key, x);
+  if (any == 0) return lookup_clean<WIDE>(v, ix, g.with_perm, key, nullptr, policy);
+  if (!g.with_perm) return kMiss;
+  // bytes outside A,C,G,T: exactly one, and it is the wildcard -> its parents
+  int nbad = 0;
+  uint32_t bad_word = 0, bad_flags = 0, bad_w = 0;
 #pragma unroll
-    for (int i = 0; i < kSpanWords; ++i) {
-      sp.bad |= nonzero_bytes(xs[i]) << (4 * i);
-      sp.wild |= (nonzero_bytes(aw[i] ^ wild4) ^ 0xFu) << (4 * i);
+  for (int i = 0; i < NW; ++i) {
+    const uint32_t f = nonzero_byte_flags(x[i]);
+    nbad += __popc(f);
+    if (f) {
+      bad_word = (uint32_t)i;
+      bad_flags = f;
+      bad_w = w[i];
     }
-    sp.bad &= mmask;
-    sp.wild &= sp.bad;
   }
-  orient(sp, g.m, g.reverse);
-  return assign_span_t<WIDE>(v, g.with_perm, sp, g.span_base, g.n, g.o, g.recursion, nullptr, policy);
+  if (nbad != 1) return kMiss;
+  const uint32_t byte = (uint32_t)(__ffs((int)bad_flags) - 8) >> 3;  // flags sit at bit 7 of their byte
+  if (((bad_w >> (8 * byte)) & 0xFFu) != g.wild_byte) return kMiss;
+  // stored base position; the keys of the reverse index are in stored order too
+  return lookup_wild<WIDE>(v, ix, key, 4 * bad_word + byte, nullptr, policy);
 }
 
 // NW = words that hold the k window bytes: 5 (k = 17..20, the common guide lengths) or 8.
@@ -290,16 +332,18 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   // every read has the same length n, so the geometry is uniform; the host sends reads whose
   // Centered window does not fit (every one of them fails its first trim) to the generic kernel
   const StreamGeom g = make_geom(p);
-  const int win_src = g.reverse ? g.n - g.o - g.k : g.o;  // stored position of the Centered window
-  const uint32_t sbyte = (uint32_t)lane * p.stride + (uint32_t)(win_src - g.lead);  // first span byte
+  const uint32_t sbyte = (uint32_t)lane * p.stride + (uint32_t)(g.win_src - g.lead);  // first span byte
   const uint32_t word0 = sbyte >> 2;
   const uint32_t off_bits = (sbyte & 3u) * 8;
-  const uint32_t win_bits = off_bits + 8u * (uint32_t)g.lead;  // 0..32: where the window starts in W
-  const uint64_t* __restrict__ front = g.reverse ? p.lib.front_rev : p.lib.front;
+  const uint32_t win_bits = off_bits + g.shift_bits[0];  // 0..32: where the Centered window starts in W
+  const IndexView& ix = p.reverse ? p.lib.rev : p.lib.fwd;
+  const uint64_t* __restrict__ front = ix.front;
   const uint32_t front_shift = p.lib.front_shift;
   const uint64_t table_policy = l2_evict_last_policy();
-  const bool settle_miss = !g.with_perm && !g.recursion;  // a definite Centered miss is final
   const uint32_t debug = MODE == 2 ? p.debug : 0u;
+  // what a read needs after its Centered window is not a library member
+  const bool centered_again = g.with_perm;  // the one-mismatch lookup of the same window
+  const bool any_next = centered_again || g.try_plus;
 
   uint32_t matched = 0;
   uint32_t qn = 0;  // parked reads (warp-uniform)
@@ -345,90 +389,97 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
         parity ^= 1u;
       }
 
-      // window-aligned words -> interleaved key + validity of the k window bytes
-      uint32_t lo = 0, hi = 0, any = 0;
+      // Centered window -> interleaved key + validity of its k bytes
+      uint32_t w[NW], x[NW];
 #pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        uint32_t w = __funnelshift_rc(W[i], W[i + 1], win_bits);
-        uint32_t x = ascii_residue(w);
-        uint32_t c = (w >> 1) & 0x03030303u;
-        if (NW != 5 || i == NW - 1) {  // bytes past the window (NW = 5: only the last word can have any)
-          const uint32_t mk = i < g.n_words - 1 ? ~0u : (i == g.n_words - 1 ? g.last_mask : 0u);
-          x &= mk;
-          c &= mk;
-        }
-        any |= x;
-        if (i < 4)
-          lo += c << (2 * i);
-        else
-          hi += c << (2 * (i - 4));
-      }
-      if (!WIDE) hi = (hi * 0x01041040u) >> 24;
+      for (int i = 0; i < NW; ++i) w[i] = __funnelshift_rc(W[i], W[i + 1], win_bits);
+      Key key;
+      const uint32_t any = pack_window<NW, WIDE>(w, g.n_words, g.last_mask, key, x);
 
-      bool park = true;
+      // park = position to resume at (0 Centered, 1 Plus), or -1 when the read is settled
+      int park = 0;
       if (any == 0) {
         bool found, flagged;
         int32_t hit;
         if (MODE == 2 && (debug & 2u)) {
           found = true;
           flagged = false;
-          hit = (int32_t)((lo ^ hi) % p.n_guides);
+          hit = (int32_t)((key.lo ^ key.hi) % p.n_guides);
         } else {
-          uint64_t w[4];
-          load_bucket(front + (size_t)(front_hash(lo, hi) >> front_shift) * 4, w, table_policy);
+          uint64_t b[4];
+          load_bucket(front + (size_t)(front_hash(key.lo, key.hi) >> front_shift) * 4, b, table_policy);
           if (!WIDE) {
             // the slot whose lo word matches (the build keeps them distinct within a bucket)
             uint32_t sel = 0;
 #pragma unroll
             for (int j = 3; j >= 0; --j)
-              if ((uint32_t)w[j] == lo) sel = (uint32_t)(w[j] >> 32);
-            const uint32_t want = hi | (uint32_t)(kFrontOccupied >> 32);
+              if ((uint32_t)b[j] == key.lo) sel = (uint32_t)(b[j] >> 32);
+            const uint32_t want = key.hi | (uint32_t)(kFrontOccupied >> 32);
             found = ((sel ^ want) & (0xFFu | (uint32_t)(kFrontOccupied >> 32))) == 0;
             hit = (int32_t)(sel >> (kFrontIdxShift - 32));
-            flagged = (w[0] & kFrontFlag) != 0;
+            flagged = (b[0] & kFrontFlag) != 0;
           } else {
-            const uint64_t probe = ((uint64_t)hi << 32) | lo;
-            const bool m0 = w[0] == probe && (w[1] & kFrontOccupied), m1 = w[2] == probe && (w[3] & kFrontOccupied);
+            const uint64_t probe = ((uint64_t)key.hi << 32) | key.lo;
+            const bool m0 = b[0] == probe && (b[1] & kFrontOccupied), m1 = b[2] == probe && (b[3] & kFrontOccupied);
             found = m0 || m1;
-            hit = (int32_t)((m0 ? w[1] : w[3]) >> kFrontIdxShift);
-            flagged = (w[1] & kFrontFlag) != 0;
+            hit = (int32_t)((m0 ? b[1] : b[3]) >> kFrontIdxShift);
+            flagged = (b[1] & kFrontFlag) != 0;
           }
         }
         if (found) {
-          park = false;
+          park = -1;
           record_hit<MODE>(p, hit, (uint64_t)read_idx, matched);
-        } else if (!flagged && settle_miss) {
-          park = false;
-          record_hit<MODE>(p, kMiss, (uint64_t)read_idx, matched);
+        } else if (!flagged && !centered_again) {
+          // not a member and no Permuter: Centered is decided, go on with Plus if there is one
+          park = g.try_plus ? 1 : -1;
+          if (park < 0) record_hit<MODE>(p, kMiss, (uint64_t)read_idx, matched);
         }
+      } else if (!any_next) {
+        park = -1;  // a bad byte, no Permuter, no recursion
+        record_hit<MODE>(p, kMiss, (uint64_t)read_idx, matched);
       }
-      if (MODE == 2 && (debug & 4u)) park = false;
-      const uint32_t pm = __ballot_sync(0xffffffffu, park);
+      if (MODE == 2 && (debug & 4u)) park = -1;
+      const uint32_t pm = __ballot_sync(0xffffffffu, park >= 0);
       if (pm) {
-        if (park) {
+        if (park >= 0) {
           const uint32_t e = qn + __popc(pm & ((1u << lane) - 1));
 #pragma unroll
-          for (int i = 0; i < NW + 2; ++i) q->w[i][e] = W[i];
-          q->read[e] = read_idx;
+          for (int i = 0; i < NW + 1; ++i) q->w[i][e] = __funnelshift_r(W[i], W[i + 1], off_bits);
+          q->tag[e] = ((uint32_t)park << kReadIdxBits) | read_idx;
         }
         qn += __popc(pm);
         __syncwarp();
       }
     }
-    // drain the queue a full warp at a time (and whatever is left once the tiles are done)
-    if (qn >= 32 || (!have_tile && qn > 0)) {
+    // Drain: 32 parked reads try one position each; a miss goes back on the queue for its next
+    // position.  Between tiles the queue is brought below 32 so a whole tile can park; once
+    // the tiles are done it is emptied.
+    while (qn >= 32 || (!have_tile && qn > 0)) {
       const uint32_t cnt = qn < 32 ? qn : 32;
       qn -= cnt;
+      int next = -1;  // position to retry at, or -1
+      uint32_t S[NW + 1], tag = 0;
       if ((uint32_t)lane < cnt) {
         const uint32_t e = qn + lane;
-        uint32_t W[NW + 2];
 #pragma unroll
-        for (int i = 0; i < NW + 2; ++i) W[i] = q->w[i][e];
-        const uint32_t ridx = q->read[e];
-        // the span's byte offset inside W[0] is that of the lane that parked the read
-        const uint32_t poff = (((ridx & 31u) * p.stride + (uint32_t)(win_src - g.lead)) & 3u) * 8;
-        const int32_t hit = walk_parked<NW, WIDE>(p.lib, g, W, poff, table_policy);
-        record_hit<MODE>(p, hit, (uint64_t)ridx, matched);
+        for (int i = 0; i < NW + 1; ++i) S[i] = q->w[i][e];
+        tag = q->tag[e];
+        const uint32_t pos = tag >> kReadIdxBits, ridx = tag & ((1u << kReadIdxBits) - 1);
+        const uint32_t shift = pos == 0 ? g.shift_bits[0] : (pos == 1 ? g.shift_bits[1] : g.shift_bits[2]);
+        const int32_t hit = try_position<NW, WIDE>(p.lib, ix, g, S, shift, table_policy);
+        if (hit == kMiss) next = pos == 0 ? (g.try_plus ? 1 : -1) : (pos == 1 && g.try_minus ? 2 : -1);
+        if (next < 0) record_hit<MODE>(p, hit, (uint64_t)ridx, matched);
+      }
+      __syncwarp();  // every lane has read its entry before any slot is overwritten
+      const uint32_t pm = __ballot_sync(0xffffffffu, next >= 0);
+      if (pm) {
+        if (next >= 0) {
+          const uint32_t e = qn + __popc(pm & ((1u << lane) - 1));
+#pragma unroll
+          for (int i = 0; i < NW + 1; ++i) q->w[i][e] = S[i];
+          q->tag[e] = ((uint32_t)next << kReadIdxBits) | (tag & ((1u << kReadIdxBits) - 1));
+        }
+        qn += __popc(pm);
       }
       __syncwarp();
     }
@@ -476,12 +527,6 @@ int env_int(const char* name, int fallback) {
   return v && *v ? atoi(v) : fallback;
 }
 
-uint8_t wild_byte_for(const sgc_counter* c) {
-  // the byte that reads as 'N' to the lookup: under the fxread bit trick a reverse-complemented
-  // 'J' becomes 'N' and 'N' becomes 'J' 
-  return (c->is_reverse && c->rc_mode == SGC_RC_BITTRICK) ? (uint8_t)'J' : (uint8_t)'N';
-}
-
 CountParams make_params(const sgc_counter* c, const uint8_t* d_lines, const uint32_t* d_off, uint32_t stride,
                         uint32_t read_len, int32_t* d_assign) {
   CountParams p{};
@@ -494,7 +539,7 @@ CountParams make_params(const sgc_counter* c, const uint8_t* d_lines, const uint
   p.with_perm = c->lib->with_perm;
   p.reverse = c->is_reverse != 0;
   p.recursion = c->recursion != 0;
-  p.wild_byte = wild_byte_for(c);
+  p.rc_mode = (uint8_t)c->rc_mode;
   p.state = c->d_state;
   p.n_guides = c->lib->n;
   p.assign_out = d_assign;
@@ -548,10 +593,12 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
   const bool nw5 = !c->lib->wide && c->lib->k > 16;
   const size_t queue_bytes = nw5 ? sizeof(WarpQueueT<5>) : sizeof(WarpQueueT<8>);
   StreamConfig cfg = stageable ? pick_stream_config(stage_bytes, queue_bytes) : StreamConfig{};
-  // whole tiles only, and never a bulk copy that would run past n_bytes
-  uint64_t n_wtiles = stageable && cfg.stages ? std::min(n_reads / kWarpReads, n_bytes / tile_bytes) : 0;
-  n_wtiles = std::min<uint64_t>(n_wtiles, 0xFFFFFFFFull / kWarpReads - 65536);  // 32-bit tile and read counters
-  if (n_wtiles > 0) {
+  // whole tiles only, and never a bulk copy that would run past n_bytes; one launch handles at
+  // most 2^30 reads (the queue words keep a 30-bit read index)
+  uint64_t tiles_left = stageable && cfg.stages ? std::min(n_reads / kWarpReads, n_bytes / tile_bytes) : 0;
+  const uint64_t max_tiles = (1ull << kReadIdxBits) / kWarpReads - 65536;
+  while (tiles_left > 0) {
+    const uint64_t n_wtiles = std::min(tiles_left, max_tiles);
     const int mode = p.debug ? 2 : (d_assign ? 1 : 0);
     using Kernel = void (*)(const CountParams, uint32_t, int, uint32_t);
     static const Kernel kernels[3][3] = {
@@ -564,11 +611,15 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
     uint64_t grid = (uint64_t)c->lib->sm_count * cfg.ctas_per_sm;  // persistent: every CTA resident
     const uint64_t ctas_needed = (n_wtiles + cfg.warps - 1) / cfg.warps;
     if (grid > ctas_needed) grid = ctas_needed;
-    p.n_reads = n_wtiles * kWarpReads;
-    p.first_read = 0;
-    kernel<<<(unsigned)grid, cfg.warps * 32, smem, stream>>>(p, (uint32_t)n_wtiles, cfg.stages, stage_bytes);
+    CountParams q = p;  // this launch's slice: read indices are relative to it
+    q.lines = d_lines + done * stride;
+    q.assign_out = d_assign ? d_assign + done : nullptr;
+    q.n_reads = n_wtiles * kWarpReads;
+    q.first_read = 0;
+    kernel<<<(unsigned)grid, cfg.warps * 32, smem, stream>>>(q, (uint32_t)n_wtiles, cfg.stages, stage_bytes);
     SGC_CUDA_TRY(cudaGetLastError());
-    done = n_wtiles * kWarpReads;
+    done += n_wtiles * kWarpReads;
+    tiles_left -= n_wtiles;
     c->last.grid = (uint32_t)grid;
     c->last.block = cfg.warps * 32;
     c->last.smem_bytes = (uint32_t)smem;

@@ -48,18 +48,16 @@ struct sgc_library {
   uint32_t n = 0, k = 0;
   bool with_perm = false;
   bool wide = false;
-  // seed index (common.cuh)
-  uint32_t part_end[sgc::kSeeds] = {};
-  uint64_t keep[sgc::kSeeds] = {};
-  uint32_t* d_dir[sgc::kSeeds] = {};
-  uint32_t* d_dir_count[sgc::kSeeds] = {};
-  uint64_t* d_post = nullptr;  // kSeeds lists of n postings
-  uint32_t dir_shift = 0;
-  // front tables of the streaming kernel, one per read orientation
-  uint64_t* d_front = nullptr;
-  uint64_t* d_front_rev = nullptr;
-  uint32_t front_shift = 0;
-  uint64_t* d_keys = nullptr;      // n natural keys, library order
+  // seed index + front table per read orientation (common.cuh): [0] forward, [1] reverse
+  struct Index {
+    uint64_t* d_keys = nullptr;  // n interleaved keys (hi << 32 | lo), library order
+    uint32_t* d_dir[sgc::kSeeds] = {};
+    uint32_t* d_dir_count[sgc::kSeeds] = {};
+    uint64_t* d_post = nullptr;  // kSeeds lists of n postings
+    uint64_t* d_front = nullptr;
+  } ix[2];
+  uint32_t dir_shift = 0, front_shift = 0;
+  size_t front_bytes = 0;
   uint32_t* d_lib_hist = nullptr;  // k*4 positional counts over guides 1..n-1 (offsetter.rs:190-191)
   int sm_count = 0;
   sgc_library_info info{};
@@ -69,17 +67,17 @@ struct sgc_library {
     v.k = k;
     v.n = n;
     v.wide = wide ? 1u : 0u;
-    for (int i = 0; i < sgc::kSeeds; ++i) {
-      v.part_end[i] = part_end[i];
-      v.keep[i] = keep[i];
-      v.dir[i] = d_dir[i];
-      v.dir_count[i] = d_dir_count[i];
-    }
-    v.post = d_post;
     v.dir_shift = dir_shift;
-    v.front = d_front;
-    v.front_rev = d_front_rev;
     v.front_shift = front_shift;
+    sgc::IndexView* views[2] = {&v.fwd, &v.rev};
+    for (int o = 0; o < 2; ++o) {
+      for (int i = 0; i < sgc::kSeeds; ++i) {
+        views[o]->dir[i] = ix[o].d_dir[i];
+        views[o]->dir_count[i] = ix[o].d_dir_count[i];
+      }
+      views[o]->post = ix[o].d_post;
+      views[o]->front = ix[o].d_front;
+    }
     return v;
   }
 };

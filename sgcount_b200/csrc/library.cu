@@ -43,31 +43,28 @@ struct BuildStatus {
   unsigned int front_left_out;  // members that did not fit their front-table bucket
 };
 
-// K2a: one thread per guide.
-__global__ void pack_library_kernel(const uint8_t* __restrict__ seqs, uint32_t n, uint32_t k,
-                                    uint64_t* __restrict__ keys, BuildStatus* st) {
+// K2a: one thread per guide: the interleaved key of the guide as written and of its reverse
+// complement (hi << 32 | lo each).
+__global__ void pack_library_kernel(const uint8_t* __restrict__ seqs, uint32_t n, uint32_t k, bool wide,
+                                    uint64_t* __restrict__ keys_fwd, uint64_t* __restrict__ keys_rev, BuildStatus* st) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint8_t* s = seqs + (size_t)i * k;
-  uint64_t key = 0;
+  Key f{0, 0}, r{0, 0};
   bool bad = false;
   for (uint32_t j = 0; j < k; ++j) {
-    uint8_t c = s[j];
+    const uint8_t c = s[j];
     bad |= !is_acgt(c);
-    key |= (uint64_t)code_of(c) << (2 * j);
+    key_set_base(f, j, wide, code_of(c));
+    key_set_base(r, k - 1 - j, wide, code_of(c) ^ 2u);
   }
-  keys[i] = key;
+  keys_fwd[i] = ((uint64_t)f.hi << 32) | f.lo;
+  keys_rev[i] = ((uint64_t)r.hi << 32) | r.lo;
   if (bad) atomicMin(&st->bad_guide, i);
 }
+__device__ __forceinline__ Key as_key(uint64_t w) { return Key{(uint32_t)w, (uint32_t)(w >> 32)}; }
 
 // ---- seed index ---------------------------------------------------------------------------
-struct SeedGeom {
-  uint64_t keep[kSeeds];
-  uint32_t dir_shift;
-};
-__device__ __forceinline__ uint32_t bucket_of_seed(uint64_t key, const SeedGeom& g, int i) {
-  return seed_hash(key & g.keep[i]) >> g.dir_shift;
-}
 struct SeedArrays {
   uint32_t* a[kSeeds];
 };
@@ -75,15 +72,15 @@ struct SeedArrays {
 // pass 1: members per bucket, and the bucket's tag: the first member's, with bit 8 raised when a
 // member with another tag joins
 constexpr uint32_t kNoTag = 0xFFFFFFFFu, kTagConflict = 0x100u;
-__global__ void seed_count_kernel(const uint64_t* __restrict__ keys, uint32_t n, SeedGeom g, SeedArrays cnt,
+__global__ void seed_count_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t dir_shift, SeedArrays cnt,
                                   SeedArrays tags) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t key = keys[i];
+  const Key key = as_key(keys[i]);
 #pragma unroll
   for (int s = 0; s < kSeeds; ++s) {
-    const uint32_t h = seed_hash(key & g.keep[s]);
-    const uint32_t b = h >> g.dir_shift, tag = (h >> (g.dir_shift - 8)) & 0xFFu;
+    const uint32_t h = seed_hash(seed_of(key, s));
+    const uint32_t b = h >> dir_shift, tag = (h >> (dir_shift - 8)) & 0xFFu;
     atomicAdd(cnt.a[s] + b, 1u);
     const uint32_t old = atomicCAS(tags.a[s] + b, kNoTag, tag);
     if (old != kNoTag && (old & 0xFFu) != tag) atomicOr(tags.a[s] + b, kTagConflict);
@@ -173,19 +170,20 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const uint32_t
 // pass 3: postings.  `cursor` starts as a copy of `start`; the order inside one bucket is
 // whatever the atomics give, which no lookup depends on.
 template <bool WIDE>
-__global__ void seed_fill_kernel(const uint64_t* __restrict__ keys, uint32_t n, SeedGeom g, SeedArrays cursor,
+__global__ void seed_fill_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t dir_shift, SeedArrays cursor,
                                  uint64_t* __restrict__ post) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t key = keys[i];
+  const uint64_t w = keys[i];
+  const Key key = as_key(w);
 #pragma unroll
   for (int s = 0; s < kSeeds; ++s) {
-    const size_t a = (size_t)s * n + atomicAdd(cursor.a[s] + bucket_of_seed(key, g, s), 1u);
+    const size_t a = (size_t)s * n + atomicAdd(cursor.a[s] + (seed_hash(seed_of(key, s)) >> dir_shift), 1u);
     if (WIDE) {
-      post[2 * a] = key;
+      post[2 * a] = w;
       post[2 * a + 1] = i;
     } else {
-      post[a] = key | ((uint64_t)i << kPostIdxShift);
+      post[a] = w | ((uint64_t)i << kPostIdxShift);  // hi has 8 bits
     }
   }
 }
@@ -200,17 +198,17 @@ __global__ void seed_dir_kernel(const uint32_t* __restrict__ start, const uint32
   dir[i] = start[i] | ((general ? kDirGeneral : c) << kDirCountShift) | ((t & 0xFFu) << kDirTagShift);
 }
 
-// ---- checks and statistics through the finished index ---------------------------------------
+// ---- checks and statistics through the finished (forward) index -----------------------------
 // duplicate sequences (library.rs:91-95): the later of two equal records reports itself
 template <bool WIDE>
 __global__ void duplicate_check_kernel(LibView v, const uint64_t* __restrict__ keys, BuildStatus* st) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= v.n) return;
-  const uint64_t key = keys[i];
+  const Key key = as_key(keys[i]);
   const uint64_t pol = l2_evict_last_policy();
   bool dup = false;
-  for_each_posting<WIDE>(v, 0, key, pol, [&](uint64_t mk, uint32_t idx) {
-    if (mk == key && idx < i) dup = true;
+  for_each_posting<WIDE>(v, v.fwd, 0, key, pol, [&](Key mk, uint32_t idx) {
+    if (mk.lo == key.lo && mk.hi == key.hi && idx < i) dup = true;
     return dup;
   });
   if (dup) atomicMin(&st->dup_guide, i);
@@ -228,18 +226,21 @@ __global__ void variant_stats_kernel(LibView v, const uint64_t* __restrict__ key
   const uint64_t pol = l2_evict_last_policy();
   if (t < (uint64_t)v.n * v.k) {
     const uint32_t i = (uint32_t)(t / v.k), pos = (uint32_t)(t % v.k);
-    const uint64_t key = keys[i];
-    for (uint64_t d = 1; d < 4; ++d) {
-      const uint64_t q = key ^ (d << (2 * pos));
+    const Key key = as_key(keys[i]);
+    const uint32_t own = key_get_base(key, pos, WIDE);
+    for (uint32_t d = 1; d < 4; ++d) {
+      Key q = key;
+      key_set_base(q, pos, WIDE, own ^ d);
       bool member = false;
       uint32_t parents = 0, smallest = 0xFFFFFFFFu;
       for (int s = 0; s < kSeeds && !member; ++s) {
-        const uint64_t keep = v.keep[s];
-        for_each_posting<WIDE>(v, s, q, pol, [&](uint64_t mk, uint32_t idx) {
-          const uint64_t x = mk ^ q;
-          if ((x & keep) != 0) return false;
-          if (x == 0) member = true;
-          if (one_base_differs(x)) {
+        const Key qs = seed_of(q, s);
+        for_each_posting<WIDE>(v, v.fwd, s, q, pol, [&](Key mk, uint32_t idx) {
+          const Key ms = seed_of(mk, s);
+          if (ms.lo != qs.lo || ms.hi != qs.hi) return false;  // another seed in this bucket
+          const Key x{mk.lo ^ q.lo, mk.hi ^ q.hi};
+          if ((x.lo | x.hi) == 0) member = true;
+          if (bases_differing(x) == 1) {
             ++parents;
             smallest = min(smallest, idx);
           }
@@ -260,46 +261,35 @@ __global__ void variant_stats_kernel(LibView v, const uint64_t* __restrict__ key
 }
 
 // ---- front table ------------------------------------------------------------------------------
-// One thread per guide and orientation.  A member goes into the first free slot of its home
-// bucket; if the bucket is full, or already holds a member with the same `lo` word (the
-// streaming kernel selects a slot by `lo` alone), it is left out and the bucket is flagged.
-__device__ __forceinline__ uint64_t revcomp_key(uint64_t x, uint32_t k) {
-  uint64_t r = __brevll(x);
-  r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
-  r >>= (64 - 2 * k);
-  return r ^ (0xAAAAAAAAAAAAAAAAull >> (64 - 2 * k));
-}
-
+// One thread per guide.  A member goes into the first free slot of its home bucket; if the
+// bucket is full, or already holds a member with the same `lo` word (the streaming kernel
+// selects a slot by `lo` alone), it is left out and the bucket is flagged.
 template <bool WIDE>
-__global__ void front_insert_kernel(uint64_t* fwd, uint64_t* rev, uint32_t front_shift,
-                                    const uint64_t* __restrict__ keys, uint32_t n, uint32_t k, BuildStatus* st) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 2 * n) return;
-  const uint32_t i = t >> 1;
-  const bool reverse = t & 1u;
-  unsigned long long* table = reinterpret_cast<unsigned long long*>(reverse ? rev : fwd);
-  const uint64_t key = reverse ? revcomp_key(keys[i], k) : keys[i];
-  uint32_t lo, hi;
-  interleave_key(key, k, WIDE, lo, hi);
-  const uint32_t b = front_hash(lo, hi) >> front_shift;
+__global__ void front_insert_kernel(uint64_t* table_, uint32_t front_shift, const uint64_t* __restrict__ keys,
+                                    uint32_t n, BuildStatus* st) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long* table = reinterpret_cast<unsigned long long*>(table_);
+  const Key key = as_key(keys[i]);
+  const uint32_t b = front_hash(key.lo, key.hi) >> front_shift;
   unsigned long long* bucket = table + (size_t)b * 4;
   const uint64_t meta = kFrontOccupied | ((uint64_t)i << kFrontIdxShift);
   bool placed = false;
   if (!WIDE) {
-    const uint64_t val = meta | ((uint64_t)hi << 32) | lo;
+    const uint64_t val = meta | ((uint64_t)key.hi << 32) | key.lo;
     for (int s = 0; s < 4 && !placed; ++s) {
       unsigned long long cur = atomicCAS(bucket + s, 0ull, (unsigned long long)val);
       if (cur == 0) {
         placed = true;
-      } else if ((uint32_t)cur == lo) {
+      } else if ((uint32_t)cur == key.lo) {
         break;  // same lo word as an earlier member: leave this one out
       }
     }
   } else {
-    const uint64_t w0 = ((uint64_t)hi << 32) | lo;
+    const uint64_t w0 = ((uint64_t)key.hi << 32) | key.lo;
     for (int s = 0; s < 2 && !placed; ++s) {
       // the meta word claims the slot; the key word is written by the claimer and read by
-      // nobody until the build has finished, except for the `lo` comparison below
+      // nobody until the build has finished
       unsigned long long cur = atomicCAS(bucket + 2 * s + 1, 0ull, (unsigned long long)meta);
       if (cur == 0) {
         bucket[2 * s] = w0;
@@ -319,21 +309,23 @@ __global__ void lookup_tokens_kernel(LibView v, bool with_perm, const uint8_t* _
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_tokens) return;
   const uint8_t* s = tokens + i * v.k;
-  uint64_t key = 0;
-  int nbad = 0, bad_pos = 0;
+  Key key{0, 0};
+  int nbad = 0;
+  uint32_t bad_pos = 0;
   bool wild = false;
   for (uint32_t j = 0; j < v.k; ++j) {
     uint8_t c = s[j];
-    key |= (uint64_t)code_of(c) << (2 * j);
+    key_set_base(key, j, v.wide, code_of(c));
     if (!is_acgt(c)) {
       ++nbad;
-      bad_pos = (int)j;
+      bad_pos = j;
       wild = (c == 'N');
     }
   }
   int kind = 0;
-  if (nbad == 1) key &= ~(3ull << (2 * bad_pos));
-  int32_t hit = window_lookup(v, with_perm, key, nbad, bad_pos, wild, &kind, l2_evict_last_policy());
+  const uint64_t pol = l2_evict_last_policy();
+  int32_t hit = v.wide ? window_lookup_t<true>(v, v.fwd, with_perm, key, nbad, bad_pos, wild, &kind, pol)
+                       : window_lookup_t<false>(v, v.fwd, with_perm, key, nbad, bad_pos, wild, &kind, pol);
   idx_out[i] = hit;
   if (kind_out) kind_out[i] = hit == kMiss ? 0 : (uint8_t)kind;
 }
@@ -378,14 +370,15 @@ int sgc_host_free(void* ptr) {
 void sgc_library_destroy(sgc_library* lib) {
   if (!lib) return;
   DeviceGuard g(lib->device);
-  for (int i = 0; i < kSeeds; ++i) {
-    cudaFree(lib->d_dir[i]);
-    cudaFree(lib->d_dir_count[i]);
+  for (int o = 0; o < 2; ++o) {
+    for (int i = 0; i < kSeeds; ++i) {
+      cudaFree(lib->ix[o].d_dir[i]);
+      cudaFree(lib->ix[o].d_dir_count[i]);
+    }
+    cudaFree(lib->ix[o].d_post);
+    cudaFree(lib->ix[o].d_front);
+    cudaFree(lib->ix[o].d_keys);
   }
-  cudaFree(lib->d_post);
-  cudaFree(lib->d_front);
-  cudaFree(lib->d_front_rev);
-  cudaFree(lib->d_keys);
   cudaFree(lib->d_lib_hist);
   delete lib;
 }
@@ -404,44 +397,62 @@ int exclusive_scan(const uint32_t* d_cnt, uint32_t n, uint32_t* d_start, uint32_
   return SGC_OK;
 }
 
+// temporaries of one build, allocated before the timed region
+struct BuildScratch {
+  DeviceBuffer<uint32_t> start[kSeeds], cur[kSeeds], tag[kSeeds], sums;
+  int alloc(uint32_t entries) {
+    SGC_CUDA_TRY(sums.alloc((entries + kScanTile - 1) / kScanTile + 1));
+    for (int i = 0; i < kSeeds; ++i) {
+      SGC_CUDA_TRY(start[i].alloc(entries));
+      SGC_CUDA_TRY(cur[i].alloc(entries));
+      SGC_CUDA_TRY(tag[i].alloc(entries));
+    }
+    return SGC_OK;
+  }
+};
+
+// seed index + front table of one orientation
 template <bool WIDE>
-int build_tables(sgc_library* lib, BuildStatus* d_st) {
-  const uint32_t n = lib->n, k = lib->k;
+int build_index(sgc_library* lib, int o, BuildScratch& sc, BuildStatus* d_st) {
+  const uint32_t n = lib->n;
   const unsigned T = 256;
   const uint32_t entries = 1u << (32 - lib->dir_shift);
-  SeedGeom g;
+  sgc_library::Index& ix = lib->ix[o];
   SeedArrays cnt, cursor, tags;
-  DeviceBuffer<uint32_t> start[kSeeds], cur[kSeeds], tag[kSeeds], sums;
-  SGC_CUDA_TRY(sums.alloc((entries + kScanTile - 1) / kScanTile + 1));
-  g.dir_shift = lib->dir_shift;
   for (int i = 0; i < kSeeds; ++i) {
-    g.keep[i] = lib->keep[i];
-    SGC_CUDA_TRY(start[i].alloc(entries));
-    SGC_CUDA_TRY(cur[i].alloc(entries));
-    SGC_CUDA_TRY(tag[i].alloc(entries));
-    SGC_CUDA_TRY(cudaMemsetAsync(lib->d_dir_count[i], 0, (size_t)entries * 4, 0));
-    SGC_CUDA_TRY(cudaMemsetAsync(tag[i].p, 0xFF, (size_t)entries * 4, 0));
-    cnt.a[i] = lib->d_dir_count[i];
-    cursor.a[i] = cur[i].p;
-    tags.a[i] = tag[i].p;
+    SGC_CUDA_TRY(cudaMemsetAsync(ix.d_dir_count[i], 0, (size_t)entries * 4, 0));
+    SGC_CUDA_TRY(cudaMemsetAsync(sc.tag[i].p, 0xFF, (size_t)entries * 4, 0));
+    cnt.a[i] = ix.d_dir_count[i];
+    cursor.a[i] = sc.cur[i].p;
+    tags.a[i] = sc.tag[i].p;
   }
-  seed_count_kernel<<<blocks_for(n, T), T>>>(lib->d_keys, n, g, cnt, tags);
+  seed_count_kernel<<<blocks_for(n, T), T>>>(ix.d_keys, n, lib->dir_shift, cnt, tags);
   for (int i = 0; i < kSeeds; ++i) {
-    int rc = exclusive_scan(lib->d_dir_count[i], entries, start[i].p, sums.p);
+    int rc = exclusive_scan(ix.d_dir_count[i], entries, sc.start[i].p, sc.sums.p);
     if (rc) return rc;
-    SGC_CUDA_TRY(cudaMemcpyAsync(cur[i].p, start[i].p, (size_t)entries * 4, cudaMemcpyDeviceToDevice, 0));
+    SGC_CUDA_TRY(cudaMemcpyAsync(sc.cur[i].p, sc.start[i].p, (size_t)entries * 4, cudaMemcpyDeviceToDevice, 0));
   }
-  seed_fill_kernel<WIDE><<<blocks_for(n, T), T>>>(lib->d_keys, n, g, cursor, lib->d_post);
+  seed_fill_kernel<WIDE><<<blocks_for(n, T), T>>>(ix.d_keys, n, lib->dir_shift, cursor, ix.d_post);
   for (int i = 0; i < kSeeds; ++i)
-    seed_dir_kernel<<<blocks_for(entries, T), T>>>(start[i].p, lib->d_dir_count[i], tag[i].p, lib->d_dir[i], entries);
-  const LibView v = lib->view();
-  duplicate_check_kernel<WIDE><<<blocks_for(n, T), T>>>(v, lib->d_keys, d_st);
-  if (lib->with_perm)
-    variant_stats_kernel<WIDE><<<blocks_for((uint64_t)n * k, T), T>>>(v, lib->d_keys, d_st);
-  front_insert_kernel<WIDE><<<blocks_for(2ull * n, T), T>>>(lib->d_front, lib->d_front_rev, lib->front_shift,
-                                                            lib->d_keys, n, k, d_st);
+    seed_dir_kernel<<<blocks_for(entries, T), T>>>(sc.start[i].p, ix.d_dir_count[i], sc.tag[i].p, ix.d_dir[i], entries);
+  SGC_CUDA_TRY(cudaMemsetAsync(ix.d_front, 0, lib->front_bytes, 0));
+  front_insert_kernel<WIDE><<<blocks_for(n, T), T>>>(ix.d_front, lib->front_shift, ix.d_keys, n, d_st);
   SGC_CUDA_TRY(cudaGetLastError());
-  SGC_CUDA_TRY(cudaDeviceSynchronize());  // the temporaries above are freed on return
+  return SGC_OK;
+}
+
+template <bool WIDE>
+int build_tables(sgc_library* lib, BuildScratch& sc, BuildStatus* d_st) {
+  const unsigned T = 256;
+  for (int o = 0; o < 2; ++o) {
+    int rc = build_index<WIDE>(lib, o, sc, d_st);
+    if (rc) return rc;
+  }
+  const LibView v = lib->view();
+  duplicate_check_kernel<WIDE><<<blocks_for(lib->n, T), T>>>(v, lib->ix[0].d_keys, d_st);
+  if (lib->with_perm)
+    variant_stats_kernel<WIDE><<<blocks_for((uint64_t)lib->n * lib->k, T), T>>>(v, lib->ix[0].d_keys, d_st);
+  SGC_CUDA_TRY(cudaGetLastError());
   return SGC_OK;
 }
 
@@ -475,19 +486,10 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   } cleanup{lib};
   SGC_CUDA_TRY(cudaDeviceGetAttribute(&lib->sm_count, cudaDevAttrMultiProcessorCount, device));
 
-  // seed geometry: three contiguous parts; seed i keeps every base outside part i.  Each
-  // directory has a power of two of buckets, at least four per member.
-  const uint64_t kmask = (1ull << (2 * k)) - 1;
-  uint32_t prev = 0;
-  for (int i = 0; i < kSeeds; ++i) {
-    lib->part_end[i] = i == kSeeds - 1 ? k : (uint32_t)((uint64_t)k * (i + 1) / kSeeds);
-    const uint32_t len = lib->part_end[i] - prev;
-    const uint64_t part = len ? (((1ull << (2 * len)) - 1) << (2 * prev)) : 0ull;
-    lib->keep[i] = kmask & ~part;
-    prev = lib->part_end[i];
-  }
-  uint32_t dir_bits = 6;
-  while (((uint64_t)1 << dir_bits) < 4ull * n) ++dir_bits;  // <= 24: the tag bits fit below
+  // each directory has a power of two of buckets, at least four per member (<= 2^24, so the 8
+  // tag bits fit below the bucket bits of the 32-bit hash)
+  uint32_t dir_bits = 8;
+  while (((uint64_t)1 << dir_bits) < 4ull * n) ++dir_bits;
   lib->dir_shift = 32 - dir_bits;
   const size_t dir_entries = (size_t)1 << dir_bits;
   const size_t post_words = (size_t)n * (lib->wide ? 2 : 1);
@@ -496,20 +498,25 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   uint32_t log_buckets = 6;
   while (((uint64_t)1 << log_buckets) < (uint64_t)n * (lib->wide ? 2 : 1)) ++log_buckets;
   lib->front_shift = 32 - log_buckets;
-  const size_t front_bytes = ((size_t)1 << log_buckets) * 32;
+  lib->front_bytes = ((size_t)1 << log_buckets) * 32;
 
   DeviceBuffer<uint8_t> d_seqs;
   DeviceBuffer<BuildStatus> d_st;
+  BuildScratch scratch;
   SGC_CUDA_TRY(d_seqs.alloc((size_t)n * k));
   SGC_CUDA_TRY(d_st.alloc(1));
-  SGC_CUDA_TRY(cudaMalloc(&lib->d_keys, (size_t)n * sizeof(uint64_t)));
-  for (int i = 0; i < kSeeds; ++i) {
-    SGC_CUDA_TRY(cudaMalloc(&lib->d_dir[i], dir_entries * 4));
-    SGC_CUDA_TRY(cudaMalloc(&lib->d_dir_count[i], dir_entries * 4));
+  int rc = scratch.alloc((uint32_t)dir_entries);
+  if (rc) return rc;
+  for (int o = 0; o < 2; ++o) {
+    sgc_library::Index& ix = lib->ix[o];
+    SGC_CUDA_TRY(cudaMalloc(&ix.d_keys, (size_t)n * sizeof(uint64_t)));
+    for (int i = 0; i < kSeeds; ++i) {
+      SGC_CUDA_TRY(cudaMalloc(&ix.d_dir[i], dir_entries * 4));
+      SGC_CUDA_TRY(cudaMalloc(&ix.d_dir_count[i], dir_entries * 4));
+    }
+    SGC_CUDA_TRY(cudaMalloc(&ix.d_post, kSeeds * post_words * 8));
+    SGC_CUDA_TRY(cudaMalloc(&ix.d_front, lib->front_bytes));
   }
-  SGC_CUDA_TRY(cudaMalloc(&lib->d_post, kSeeds * post_words * 8));
-  SGC_CUDA_TRY(cudaMalloc(&lib->d_front, front_bytes));
-  SGC_CUDA_TRY(cudaMalloc(&lib->d_front_rev, front_bytes));
   SGC_CUDA_TRY(cudaMalloc(&lib->d_lib_hist, (size_t)k * 4 * sizeof(uint32_t)));
   SGC_CUDA_TRY(cudaMemcpy(d_seqs.p, seqs, (size_t)n * k, cudaMemcpyHostToDevice));
   BuildStatus st0{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
@@ -519,10 +526,9 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   SGC_CUDA_TRY(cudaEventCreate(&e0));
   SGC_CUDA_TRY(cudaEventCreate(&e1));
   SGC_CUDA_TRY(cudaEventRecord(e0, 0));
-  SGC_CUDA_TRY(cudaMemsetAsync(lib->d_front, 0, front_bytes, 0));
-  SGC_CUDA_TRY(cudaMemsetAsync(lib->d_front_rev, 0, front_bytes, 0));
-  pack_library_kernel<<<blocks_for(n, 256), 256>>>(d_seqs.p, n, k, lib->d_keys, d_st.p);
-  int rc = lib->wide ? build_tables<true>(lib, d_st.p) : build_tables<false>(lib, d_st.p);
+  pack_library_kernel<<<blocks_for(n, 256), 256>>>(d_seqs.p, n, k, lib->wide, lib->ix[0].d_keys, lib->ix[1].d_keys,
+                                                   d_st.p);
+  rc = lib->wide ? build_tables<true>(lib, scratch, d_st.p) : build_tables<false>(lib, scratch, d_st.p);
   if (rc) return rc;
   // library positional histogram for the offset detector: records 1..n-1 (offsetter.rs:57,190-191)
   SGC_CUDA_TRY(cudaMemsetAsync(lib->d_lib_hist, 0, (size_t)k * 4 * sizeof(uint32_t), 0));
@@ -556,8 +562,8 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   lib->info.n_variants = st.n_variants;
   lib->info.n_ambiguous = st.n_ambiguous;
   lib->info.n_slots = ((size_t)1 << log_buckets) * (lib->wide ? 2 : 4);
-  // what the count kernels touch: directories + postings + one front table
-  lib->info.table_bytes = kSeeds * (dir_entries * 4 + post_words * 8) + front_bytes;
+  // what one counter touches: the directories, postings and front table of its orientation
+  lib->info.table_bytes = kSeeds * (dir_entries * 4 + post_words * 8) + lib->front_bytes;
   lib->info.build_ms = ms;
   lib->info.front_left_out = st.front_left_out;
   cleanup.l = nullptr;
