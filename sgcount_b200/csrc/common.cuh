@@ -137,19 +137,23 @@ struct LibView {
 
 #ifdef __CUDACC__
 
+// L1 policy of the table loads (tuning knob): the tables have no L1 locality worth keeping
+#ifndef SGC_L1_HINT
+#define SGC_L1_HINT ""
+#endif
 __device__ __forceinline__ uint64_t ldg_u64(const uint64_t* p, uint64_t policy) {
   uint64_t v;
-  asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+  asm volatile("ld.global.nc" SGC_L1_HINT ".L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
   return v;
 }
 __device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p, uint64_t policy) {
   uint32_t v;
-  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+  asm volatile("ld.global.nc" SGC_L1_HINT ".L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
   return v;
 }
 // one 32-byte bucket = one sector, fetched with a single 256-bit read-only load (LDG.256)
 __device__ __forceinline__ void load_bucket(const uint64_t* p, uint64_t (&w)[4], uint64_t policy) {
-  asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+  asm volatile("ld.global.nc" SGC_L1_HINT ".L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
                : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
                : "l"(p), "l"(policy));
 }

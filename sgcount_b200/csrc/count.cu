@@ -349,112 +349,120 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   uint32_t qn = 0;  // parked reads (warp-uniform)
   int s = 0;
   uint32_t parity = 0;
-  uint32_t read_idx = gwarp * kWarpReads + lane;
-  const uint32_t read_step = gwarps * kWarpReads;
-  uint32_t t = gwarp;
-  for (;;) {
-    const bool have_tile = t < n_wtiles;
-    if (have_tile) {
-      // wait for the tile, lift this lane's span out of shared memory, hand the buffer back
-      mbar_wait(&my_bar[s], parity);
-      uint8_t* stage = my_tiles + (size_t)s * stage_bytes;
-      const uint32_t* tile = reinterpret_cast<const uint32_t*>(stage);
-      uint32_t W[NW + 2];
-#pragma unroll
-      for (int i = 0; i < NW + 2; ++i) W[i] = tile[word0 + i];
-      {
-        // The buffer may be refilled once every lane's loads have RETURNED.  A warp vote on a
-        // value computed from all of them is that point: it cannot issue before the data is
-        // in registers, which orders the generic-proxy reads before the async-proxy write
-        // without a CTA-wide membar per tile.
-        uint32_t allw = W[0];
-#pragma unroll
-        for (int i = 1; i < NW + 2; ++i) allw &= W[i];
-        uint32_t vote;
-        asm volatile(
-            "{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\nvote.sync.ballot.b32 %0, p, 0xffffffff;\n}\n"
-            : "=r"(vote)
-            : "r"(allw)
-            : "memory");
-        (void)vote;
-      }
-      if (lane == 0 && requested < n_wtiles) {
-        mbar_expect_tx(&my_bar[s], tile_bytes);
-        bulk_load(stage, next_src, tile_bytes, &my_bar[s], policy);
-        requested += gwarps;
-        next_src += src_step;
-      }
-      if (++s == n_stages) {
-        s = 0;
-        parity ^= 1u;
-      }
 
-      // Centered window -> interleaved key + validity of its k bytes
-      uint32_t w[NW], x[NW];
+  // A tile is handled in two steps one loop iteration apart, so that the front-table sector of
+  // tile j+1 travels L2 -> L1 while tile j is being finished (and its parked reads drained):
+  //   step A  wait for the tile, lift the span, hand the buffer back, pack the Centered window,
+  //           PREFETCH the front bucket into L1; carried to step B: span words, key, validity
+  //   step B  load the bucket (an L1 hit), compare, count or park
+  struct Pending {
+    uint32_t S[NW + 1];  // span words from one byte before the Centered window (lane independent)
+    Key key;
+    uint32_t any;  // non-zero: some window byte is not A/C/G/T
+    uint64_t b[4];  // the front bucket, in flight between the two steps
+  };
+  auto step_a = [&](Pending& pd) {
+    mbar_wait(&my_bar[s], parity);
+    uint8_t* stage = my_tiles + (size_t)s * stage_bytes;
+    const uint32_t* tile = reinterpret_cast<const uint32_t*>(stage);
+    uint32_t W[NW + 2];
 #pragma unroll
-      for (int i = 0; i < NW; ++i) w[i] = __funnelshift_rc(W[i], W[i + 1], win_bits);
-      Key key;
-      const uint32_t any = pack_window<NW, WIDE>(w, g.n_words, g.last_mask, key, x);
-
-      // park = position to resume at (0 Centered, 1 Plus), or -1 when the read is settled
-      int park = 0;
-      if (any == 0) {
-        bool found, flagged;
-        int32_t hit;
-        if (MODE == 2 && (debug & 2u)) {
-          found = true;
-          flagged = false;
-          hit = (int32_t)((key.lo ^ key.hi) % p.n_guides);
-        } else {
-          uint64_t b[4];
-          load_bucket(front + (size_t)(front_hash(key.lo, key.hi) >> front_shift) * 4, b, table_policy);
-          if (!WIDE) {
-            // the slot whose lo word matches (the build keeps them distinct within a bucket)
-            uint32_t sel = 0;
+    for (int i = 0; i < NW + 2; ++i) W[i] = tile[word0 + i];
+    {
+      // The buffer may be refilled once every lane's loads have RETURNED.  A warp vote on a
+      // value computed from all of them is that point: it cannot issue before the data is in
+      // registers, which orders the generic-proxy reads before the async-proxy write without
+      // a CTA-wide membar per tile.
+      uint32_t allw = W[0];
 #pragma unroll
-            for (int j = 3; j >= 0; --j)
-              if ((uint32_t)b[j] == key.lo) sel = (uint32_t)(b[j] >> 32);
-            const uint32_t want = key.hi | (uint32_t)(kFrontOccupied >> 32);
-            found = ((sel ^ want) & (0xFFu | (uint32_t)(kFrontOccupied >> 32))) == 0;
-            hit = (int32_t)(sel >> (kFrontIdxShift - 32));
-            flagged = (b[0] & kFrontFlag) != 0;
-          } else {
-            const uint64_t probe = ((uint64_t)key.hi << 32) | key.lo;
-            const bool m0 = b[0] == probe && (b[1] & kFrontOccupied), m1 = b[2] == probe && (b[3] & kFrontOccupied);
-            found = m0 || m1;
-            hit = (int32_t)((m0 ? b[1] : b[3]) >> kFrontIdxShift);
-            flagged = (b[1] & kFrontFlag) != 0;
-          }
-        }
-        if (found) {
-          park = -1;
-          record_hit<MODE>(p, hit, (uint64_t)read_idx, matched);
-        } else if (!flagged && !centered_again) {
-          // not a member and no Permuter: Centered is decided, go on with Plus if there is one
-          park = g.try_plus ? 1 : -1;
-          if (park < 0) record_hit<MODE>(p, kMiss, (uint64_t)read_idx, matched);
-        }
-      } else if (!any_next) {
-        park = -1;  // a bad byte, no Permuter, no recursion
-        record_hit<MODE>(p, kMiss, (uint64_t)read_idx, matched);
-      }
-      if (MODE == 2 && (debug & 4u)) park = -1;
-      const uint32_t pm = __ballot_sync(0xffffffffu, park >= 0);
-      if (pm) {
-        if (park >= 0) {
-          const uint32_t e = qn + __popc(pm & ((1u << lane) - 1));
-#pragma unroll
-          for (int i = 0; i < NW + 1; ++i) q->w[i][e] = __funnelshift_r(W[i], W[i + 1], off_bits);
-          q->tag[e] = ((uint32_t)park << kReadIdxBits) | read_idx;
-        }
-        qn += __popc(pm);
-        __syncwarp();
-      }
+      for (int i = 1; i < NW + 2; ++i) allw &= W[i];
+      uint32_t vote;
+      asm volatile(
+          "{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\nvote.sync.ballot.b32 %0, p, 0xffffffff;\n}\n"
+          : "=r"(vote)
+          : "r"(allw)
+          : "memory");
+      (void)vote;
     }
-    // Drain: 32 parked reads try one position each; a miss goes back on the queue for its next
-    // position.  Between tiles the queue is brought below 32 so a whole tile can park; once
-    // the tiles are done it is emptied.
-    while (qn >= 32 || (!have_tile && qn > 0)) {
+    if (lane == 0 && requested < n_wtiles) {
+      mbar_expect_tx(&my_bar[s], tile_bytes);
+      bulk_load(stage, next_src, tile_bytes, &my_bar[s], policy);
+      requested += gwarps;
+      next_src += src_step;
+    }
+    if (++s == n_stages) {
+      s = 0;
+      parity ^= 1u;
+    }
+#pragma unroll
+    for (int i = 0; i < NW + 1; ++i) pd.S[i] = __funnelshift_r(W[i], W[i + 1], off_bits);
+    uint32_t w[NW], x[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) w[i] = __funnelshift_r(pd.S[i], pd.S[i + 1], g.shift_bits[0]);
+    pd.any = pack_window<NW, WIDE>(w, g.n_words, g.last_mask, pd.key, x);
+    if (pd.any == 0 && !(MODE == 2 && (debug & 2u)))
+      load_bucket(front + (size_t)(front_hash(pd.key.lo, pd.key.hi) >> front_shift) * 4, pd.b, table_policy);
+  };
+  auto step_b = [&](const Pending& pd, uint32_t read_idx) {
+    // park = position to resume at (0 Centered, 1 Plus), or -1 when the read is settled
+    int park = 0;
+    if (pd.any == 0) {
+      bool found, flagged;
+      int32_t hit;
+      if (MODE == 2 && (debug & 2u)) {
+        found = true;
+        flagged = false;
+        hit = (int32_t)((pd.key.lo ^ pd.key.hi) % p.n_guides);
+      } else {
+        const uint64_t(&b)[4] = pd.b;
+        if (!WIDE) {
+          // the slot whose lo word matches (the build keeps them distinct within a bucket)
+          uint32_t sel = 0;
+#pragma unroll
+          for (int j = 3; j >= 0; --j)
+            if ((uint32_t)b[j] == pd.key.lo) sel = (uint32_t)(b[j] >> 32);
+          const uint32_t want = pd.key.hi | (uint32_t)(kFrontOccupied >> 32);
+          found = ((sel ^ want) & (0xFFu | (uint32_t)(kFrontOccupied >> 32))) == 0;
+          hit = (int32_t)(sel >> (kFrontIdxShift - 32));
+          flagged = (b[0] & kFrontFlag) != 0;
+        } else {
+          const uint64_t probe = ((uint64_t)pd.key.hi << 32) | pd.key.lo;
+          const bool m0 = b[0] == probe && (b[1] & kFrontOccupied), m1 = b[2] == probe && (b[3] & kFrontOccupied);
+          found = m0 || m1;
+          hit = (int32_t)((m0 ? b[1] : b[3]) >> kFrontIdxShift);
+          flagged = (b[1] & kFrontFlag) != 0;
+        }
+      }
+      if (found) {
+        park = -1;
+        record_hit<MODE>(p, hit, (uint64_t)read_idx, matched);
+      } else if (!flagged && !centered_again) {
+        // not a member and no Permuter: Centered is decided, go on with Plus if there is one
+        park = g.try_plus ? 1 : -1;
+        if (park < 0) record_hit<MODE>(p, kMiss, (uint64_t)read_idx, matched);
+      }
+    } else if (!any_next) {
+      park = -1;  // a bad byte, no Permuter, no recursion
+      record_hit<MODE>(p, kMiss, (uint64_t)read_idx, matched);
+    }
+    if (MODE == 2 && (debug & 4u)) park = -1;
+    const uint32_t pm = __ballot_sync(0xffffffffu, park >= 0);
+    if (pm) {
+      if (park >= 0) {
+        const uint32_t e = qn + __popc(pm & ((1u << lane) - 1));
+#pragma unroll
+        for (int i = 0; i < NW + 1; ++i) q->w[i][e] = pd.S[i];
+        q->tag[e] = ((uint32_t)park << kReadIdxBits) | read_idx;
+      }
+      qn += __popc(pm);
+      __syncwarp();
+    }
+  };
+  // Drain: 32 parked reads try one position each; a miss goes back on the queue for its next
+  // position.  Between tiles the queue is brought below 32 so a whole tile can park; once the
+  // tiles are done it is emptied.
+  auto drain = [&](bool all) {
+    while (qn >= 32 || (all && qn > 0)) {
       const uint32_t cnt = qn < 32 ? qn : 32;
       qn -= cnt;
       int next = -1;  // position to retry at, or -1
@@ -483,10 +491,26 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
       }
       __syncwarp();
     }
-    if (!have_tile) break;
+  };
+
+  uint32_t read_idx = gwarp * kWarpReads + lane;
+  const uint32_t read_step = gwarps * kWarpReads;
+  uint32_t t = gwarp;
+  Pending cur;
+  bool have_cur = t < n_wtiles;
+  if (have_cur) step_a(cur);
+  while (have_cur) {
+    Pending nxt;
+    const bool have_nxt = t + gwarps < n_wtiles;
+    if (have_nxt) step_a(nxt);
+    step_b(cur, read_idx);
+    drain(false);
+    cur = nxt;
+    have_cur = have_nxt;
     t += gwarps;
     read_idx += read_step;
   }
+  drain(true);
   flush_matched(p, matched);
 }
 
