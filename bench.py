@@ -98,6 +98,73 @@ class OracleLeg:
                 f"{self.threads} threads; one-off Permuter::new took {self.permuter_s:.1f} s on 1 thread (not timed)")
 
 
+# ---------------------------------------------------------------------------------------------
+# end to end from a gzip FASTQ through the C++ host (ingest + count + table), with the oracle's
+# gunzip + parse + match on the same file beside it
+# ---------------------------------------------------------------------------------------------
+def fastq_leg(lib_arr, n_reads: int, with_oracle: bool):
+    import shutil
+    import subprocess
+    import tempfile
+
+    from sgcount_b200 import synth
+
+    exe = os.path.join(ROOT, "sgcount_b200", "lib", "sgcount")
+    if not os.path.exists(exe):
+        return {"unavailable": "sgcount host binary not built"}
+    tmp = tempfile.mkdtemp(prefix="sgc_bench_")
+    try:
+        lib_path = os.path.join(tmp, "library.fa")
+        with open(lib_path, "wb") as f:
+            f.write(b"".join(b">lib.%d\n%s\n" % (i, lib_arr[i].tobytes()) for i in range(len(lib_arr))))
+        fq = os.path.join(tmp, "sample0.fastq.gz")
+        sample = synth.Sample(SEED, 0, lib_arr, READ_LEN, OFFSET, False)
+        sample.write_fastq(fq, 0, n_reads, reads_per_member=1 << 20, gz_level=1)
+        gz_bytes = os.path.getsize(fq)
+        out_path = os.path.join(tmp, "counts.tsv")
+        best = None
+        for _ in range(2):  # the first run pages the file in
+            t0 = time.perf_counter()
+            p = subprocess.run([exe, "-l", lib_path, "-i", fq, "-a", str(OFFSET), "-q", "-o", out_path, "--timing"],
+                               capture_output=True, text=True, timeout=900)
+            wall = time.perf_counter() - t0
+            if p.returncode != 0:
+                return {"unavailable": "sgcount failed: " + p.stderr.strip()[-200:]}
+            timing = json.loads([l for l in p.stderr.splitlines() if l.startswith("{")][-1])
+            if best is None or timing["count_s"] < best[0]["count_s"]:
+                best = (timing, wall)
+        timing, wall = best
+        rows = open(out_path).read().rstrip("\n").split("\n")
+        table = {r.split("\t")[0]: int(r.split("\t")[1]) for r in rows[1:]}
+        res = {"value": timing["reads"] / timing["count_s"], "unit": "reads/s", "reads": timing["reads"],
+               "count_s": timing["count_s"], "process_wall_s": wall, "gz_bytes": gz_bytes,
+               "ingest_threads": timing["ingest_threads"],
+               "what": "sgcount CLI on a multi-member gzip FASTQ (1 Mi reads per member): parallel inflate, parse, "
+                       "H2D, count kernel, D2H; table build and process start-up are outside count_s"}
+        if with_oracle:
+            from oracle import oracle as orc
+
+            t0 = time.perf_counter()
+            recs = orc.Records.from_path(fq)
+            t_parse = time.perf_counter() - t0
+            lib_recs = orc.Records.from_path(lib_path)
+            olib = orc.Library.from_reader(lib_recs)
+            operm = orc.Permuter.new(olib)
+            t0 = time.perf_counter()
+            oc = orc.Counter.new(recs, olib, operm, orc.Offset.Forward(OFFSET), None, True, n_threads=1)
+            t_match = time.perf_counter() - t0
+            res["cpu_port"] = {"value": n_reads / (t_parse + t_match), "unit": "reads/s", "cores": 1,
+                               "gunzip_parse_s": t_parse, "match_s": t_match,
+                               "note": "oracle port, one thread per sample like the reference (count.rs:117-136)"}
+            counts = oc.counts_by_index()
+            want = {"lib.%d" % i: int(c) for i, c in enumerate(counts) if c}
+            res["parity"] = "ok" if want == table else "MISMATCH"
+            assert want == table, "CLI count table differs from the oracle's"
+        return res
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -406,6 +473,8 @@ def run_gpu(args):
                   and g_matched == oc.matched_reads())
             out["parity"] = "ok" if ok else "MISMATCH"
             assert ok, "GPU counts differ from the oracle on the cpu_baseline sample"
+        if world == 1 and args.fastq_reads > 0:
+            out["e2e_fastq"] = fastq_leg(lib_arr, args.fastq_reads, with_oracle=not args.no_cpu_baseline)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -422,6 +491,8 @@ def main():
     ap.add_argument("--reads-per-gpu", type=int, default=READS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fastq-reads", type=int, default=4_000_000,
+                    help="reads of the gzip-FASTQ end-to-end leg through the C++ host (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -11,6 +11,7 @@
 // error; `-t` sets the number of samples processed concurrently (one host pipeline + one CUDA
 // stream each), `--gpus` spreads them over devices.
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -56,6 +57,8 @@ struct Args {
   unsigned long subsample = 5000;
   unsigned threads = 1;
   int gpus = 1, device = 0;
+  unsigned ingest_threads = 0;  // inflate threads per sample; 0 = hardware threads / concurrent samples
+  bool timing = false;
   int rc_mode = SGC_RC_BITTRICK;
 };
 
@@ -77,7 +80,9 @@ const char* kUsage =
     "  -z, --include-zero                     Include zero count sgRNAs in output table\n"
     "      --gpus <N>                         Spread the samples over N devices [default: 1]\n"
     "      --device <D>                       First device to use [default: 0]\n"
+    "      --ingest-threads <N>               Threads inflating the gzip members of one sample [default: cores / samples in flight]\n"
     "      --rc-keep-n                        Reverse complement keeps N (default: the fxread bit trick, N -> J)\n"
+    "      --timing                           Print a JSON line with the phase times to stderr\n"
     "  -h, --help                             Print help\n";
 
 unsigned long parse_uint(const std::string& flag, const char* v) {
@@ -116,7 +121,9 @@ Args parse_args(int argc, char** argv) {
     else if (f == "-z" || f == "--include-zero") a.include_zero = true;
     else if (f == "--gpus") a.gpus = (int)parse_uint(f, value());
     else if (f == "--device") a.device = (int)parse_uint(f, value());
+    else if (f == "--ingest-threads") a.ingest_threads = (unsigned)parse_uint(f, value());
     else if (f == "--rc-keep-n") a.rc_mode = SGC_RC_KEEP_N;
+    else if (f == "--timing") a.timing = true;
     else if (f == "-h" || f == "--help") { fputs(kUsage, stdout); exit(0); }
     else fail("unexpected argument '%s' found", f.c_str());
   }
@@ -263,7 +270,7 @@ struct SampleResult {
 // count_sample (count.rs:15-45): parse on this thread into two pinned buffers; the copy and
 // the kernel of one batch overlap the parsing of the next.
 SampleResult count_sample(const sgc_library* lib, uint32_t n_guides, const std::string& path, OffsetValue offset,
-                          bool recursion, int rc_mode) {
+                          bool recursion, int rc_mode, unsigned ingest_threads) {
   sgc_counter* c = nullptr;
   check(sgc_counter_create(lib, offset.reverse, offset.index, recursion, rc_mode, nullptr, nullptr, &c));
   struct Guard {
@@ -283,12 +290,12 @@ SampleResult count_sample(const sgc_library* lib, uint32_t n_guides, const std::
     b.cap = cap;
     b.reset();
   }
-  sgh::FastxReader reader(path);
-  const char *id, *seq;
-  size_t id_len, seq_len;
+  sgh::FastxReader reader(path, ingest_threads);
+  const char* seq;
+  size_t seq_len;
   int cur = 0;
   bool other_in_flight = false;
-  while (reader.next(id, id_len, seq, seq_len)) {
+  while (reader.next_seq(seq, seq_len)) {
     if (seq_len + 1 > cap) fail("a sequence line longer than %zu bytes", cap);
     if (!g.b[cur].push(seq, seq_len)) {
       submit(c, g.b[cur]);
@@ -378,13 +385,15 @@ int main(int argc, char** argv) {
     std::mutex err_mu;
     std::string first_error;
     const unsigned workers = (unsigned)std::min<size_t>(std::max(args.threads, (unsigned)gpus), n_samples);
+    const unsigned ingest_threads =
+        args.ingest_threads ? args.ingest_threads : std::max(1u, std::thread::hardware_concurrency() / workers);
     auto work = [&]() {
       for (;;) {
         const size_t s = next.fetch_add(1);
         if (s >= n_samples) return;
         try {
           results[s] = count_sample(libs[s % gpus], hlib.n, args.input_paths[s], offsets[s], !args.no_position_recursion,
-                                    args.rc_mode);
+                                    args.rc_mode, ingest_threads);
           if (!args.quiet) {
             const SampleResult& r = results[s];
             fprintf(stderr, "Finished: %s; Fraction mapped: %.3f [%llu / %llu]\n", names[s].c_str(),
@@ -397,11 +406,19 @@ int main(int argc, char** argv) {
         }
       }
     };
+    const auto t_count0 = std::chrono::steady_clock::now();
     std::vector<std::thread> pool;
     for (unsigned t = 1; t < workers; ++t) pool.emplace_back(work);
     work();
     for (auto& t : pool) t.join();
     if (!first_error.empty()) fail("%s", first_error.c_str());
+    if (args.timing) {
+      const double count_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_count0).count();
+      unsigned long long reads = 0;
+      for (const auto& r : results) reads += r.total;
+      fprintf(stderr, "{\"count_s\": %.6f, \"reads\": %llu, \"samples\": %zu, \"sample_workers\": %u, "
+              "\"ingest_threads\": %u, \"gpus\": %d}\n", count_s, reads, n_samples, workers, ingest_threads, gpus);
+    }
 
     // write_results (results.rs:71-99).  Counts are keyed by alias (counter.rs:232-235):
     // sequences that share a header print the combined count on each of their rows.

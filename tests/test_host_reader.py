@@ -1,0 +1,94 @@
+"""The host's FASTA/FASTQ reader (sgcount_b200/host/fastx.cpp), the stand-in for the `fxread`
+crate: plain, gzip and multi-member gzip inflated by a thread pool must yield the same records
+as Python's own parsing; malformed input must be reported, not mis-parsed."""
+import gzip
+import os
+import random
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DUMP = os.path.join(ROOT, "sgcount_b200", "lib", "fastx_dump")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not os.path.exists(DUMP):
+        import __graft_entry__ as g
+
+        g.build()
+    assert os.path.exists(DUMP)
+
+
+def fnv(records, with_ids=True):
+    h = 1469598103934665603
+    for rid, seq in records:
+        for c in seq:
+            h = ((h ^ c) * 1099511628211) & (2**64 - 1)
+        h = ((h ^ 0xFF) * 1099511628211) & (2**64 - 1)
+        if with_ids:
+            for c in rid:
+                h = ((h ^ c) * 1099511628211) & (2**64 - 1)
+    return f"{len(records)} {h:x}"
+
+
+def dump(path, threads, *extra):
+    p = subprocess.run([DUMP, str(path), str(threads), *extra], capture_output=True, text=True, timeout=120)
+    return p.returncode, p.stdout.strip(), p.stderr
+
+
+def make_records(n, seed, fastq=True):
+    rng = random.Random(seed)
+    recs = []
+    for i in range(n):
+        length = rng.choice([75, 75, 75, 80, 12, 0])
+        recs.append((b"r%d extra" % i, bytes(rng.choice(b"ACGTNacgt") for _ in range(length))))
+    recs[3] = (b"\x1f\x8b\x08\x00 looks like a gzip header", b"ACGT")
+    if fastq:
+        text = b"".join(b"@" + i + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n" for i, s in recs)
+    else:
+        text = b"".join(b">" + i + b"\n" + s + b"\n" for i, s in recs)
+    return recs, text
+
+
+@pytest.mark.parametrize("fastq", [True, False])
+def test_plain_gzip_and_multi_member_agree(tmp_path, fastq):
+    recs, text = make_records(30000, 7 + fastq, fastq)
+    want = fnv(recs)
+    rng = random.Random(1)
+    cuts = sorted(rng.sample(range(1, len(text)), 9))  # member boundaries fall inside records
+    members = [text[a:b] for a, b in zip([0] + cuts, cuts + [len(text)])]
+    files = {"plain.fx": text, "single.fx.gz": gzip.compress(text, 1),
+             "multi.fx.gz": b"".join(gzip.compress(m, 1) for m in members),
+             "with_empty_member.fx.gz": gzip.compress(text[:100], 1) + gzip.compress(b"", 1) + gzip.compress(text[100:], 1)}
+    for name, blob in files.items():
+        (tmp_path / name).write_bytes(blob)
+        for threads in (1, 3, 16):
+            rc, out, err = dump(tmp_path / name, threads)
+            assert (rc, out) == (0, want), (name, threads, err)
+    rc, out, _ = dump(tmp_path / "multi.fx.gz", 4, "seq")
+    assert (rc, out) == (0, fnv(recs, with_ids=False))
+
+
+def test_last_line_without_newline_and_empty_file(tmp_path):
+    (tmp_path / "a.fa").write_bytes(b">x\nACGT\n>y\nGG")
+    assert dump(tmp_path / "a.fa", 1)[1] == fnv([(b"x", b"ACGT"), (b"y", b"GG")])
+    (tmp_path / "empty.fq").write_bytes(b"")
+    assert dump(tmp_path / "empty.fq", 1)[:2] == (0, fnv([]))
+
+
+def test_malformed_inputs_are_errors(tmp_path):
+    (tmp_path / "bad.fq").write_bytes(b"ACGT\nACGT\n")
+    assert dump(tmp_path / "bad.fq", 1)[0] == 1
+    (tmp_path / "trunc.fq").write_bytes(b"@r\nACGT\n+\n")
+    assert "truncated" in dump(tmp_path / "trunc.fq", 1)[2]
+    (tmp_path / "trunc.fa").write_bytes(b">r\n")
+    assert "truncated" in dump(tmp_path / "trunc.fa", 1)[2]
+    blob = gzip.compress(b"@r\nACGT\n+\nIIII\n" * 5000, 1)
+    (tmp_path / "cut.fq.gz").write_bytes(blob[:len(blob) // 2])
+    assert dump(tmp_path / "cut.fq.gz", 1)[0] == 1
+    (tmp_path / "cut2.fq.gz").write_bytes(gzip.compress(b"@a\nAC\n+\nII\n", 1) * 3 + blob[:len(blob) // 2])
+    assert dump(tmp_path / "cut2.fq.gz", 4)[0] == 1
+    (tmp_path / "notgz.fq.gz").write_bytes(b"@r\nACGT\n+\nIIII\n")
+    assert dump(tmp_path / "notgz.fq.gz", 2)[0] == 1
