@@ -147,6 +147,12 @@ int sgc_counter_submit_device(sgc_counter*, const uint8_t* d_lines, uint64_t n_b
                               const uint32_t* d_line_off, uint32_t stride, uint32_t read_len,
                               uint64_t n_reads, int32_t* d_assign_out);
 
+/* Skewed screens: count into `replicas` copies of the count vector (rounded down to a power of
+ * two, at most 64 copies / 64 MB; 1 = off, the default), folded into the state vector after
+ * every count launch.  Spreads the atomics of a guide that carries a large share of the reads
+ * over several L2 addresses; see count.cu count_hit for the measurements. */
+int sgc_counter_set_replicas(sgc_counter*, uint32_t replicas);
+
 int sgc_counter_sync(sgc_counter*);
 int sgc_counter_reset(sgc_counter*); /* zero the state vector */
 

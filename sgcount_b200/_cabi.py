@@ -78,6 +78,7 @@ SIGNATURES = {
     "sgc_counter_destroy": (None, [_vp]),
     "sgc_counter_submit": (_int, [_vp, _vp, _u64, _vp, _u32, _u32, _u64]),
     "sgc_counter_submit_device": (_int, [_vp, _vp, _u64, _vp, _u32, _u32, _u64, _vp]),
+    "sgc_counter_set_replicas": (_int, [_vp, _u32]),
     "sgc_counter_sync": (_int, [_vp]),
     "sgc_counter_reset": (_int, [_vp]),
     "sgc_counter_finish": (_int, [_vp, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
@@ -98,6 +99,8 @@ def load() -> C.CDLL:
                 "(there is no CPU fallback for the sgcount CUDA path)")
         lib = C.CDLL(SO_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if os.environ.get("SGC_CUDA_LIB") and not hasattr(lib, name):
+                continue  # A/B timing against an older build (tuning only)
             fn = getattr(lib, name)  # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args

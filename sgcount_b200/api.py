@@ -276,6 +276,10 @@ class Counter:
                                                      n_reads, d_assign_out))
         self._result = None
 
+    def set_replicas(self, replicas: int) -> None:
+        """spread the count atomics over `replicas` copies of the count vector (skewed screens)"""
+        check(_cabi.load().sgc_counter_set_replicas(self._ptr, int(replicas)))
+
     def sync(self) -> None:
         check(_cabi.load().sgc_counter_sync(self._ptr))
 

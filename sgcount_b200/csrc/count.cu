@@ -40,27 +40,60 @@ struct CountParams {
   int offset;
   uint8_t with_perm, reverse, recursion, rc_mode;
   unsigned long long* state;  // counts[n_guides], total, matched
+  unsigned long long* rep;    // n_rep replicas of counts[n_guides] (see count_hit)
+  uint32_t n_rep;             // power of two
   uint32_t n_guides;
   int32_t* assign_out;
   uint32_t debug;  // SGC_DEBUG bit mask (tuning only): 1 no count atomics, 2 no table probe, 4 no slow path
 };
 
 // MODE 0: production (no per-read output, no tuning switches); 1: also writes the per-read
-// assignment; 2: tuning build that honours SGC_DEBUG as well.
-template <int MODE = 2>
-__device__ __forceinline__ void record_hit(const CountParams& p, int32_t hit, uint64_t read_idx, uint32_t& matched) {
-  if (MODE >= 1 && p.assign_out) p.assign_out[read_idx] = hit;
-  if (hit >= 0) {
-    ++matched;
-    if (MODE < 2 || !(p.debug & 1u)) atomicAdd(p.state + hit, 1ull);  // counter.rs:232-235
-  }
-}
-
+// assignment; 2: tuning build that honours SGC_DEBUG as well; 3: production with count replicas.
 __device__ __forceinline__ void flush_matched(const CountParams& p, uint32_t matched) {
   matched = __reduce_add_sync(0xffffffffu, matched);
   if ((threadIdx.x & 31) == 0 && matched) atomicAdd(p.state + p.n_guides + 1, (unsigned long long)matched);
   // total_reads counts every record this launch walked (counter.rs:223-226)
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.state + p.n_guides, (unsigned long long)p.n_reads);
+}
+
+// Count update (counter.rs:232-235): one RED.64 per matched read, fire and forget, resolved in L2.
+//
+// Skewed screens.  When one guide carries a large share of the reads, its atomics serialise on
+// ONE L2 address (about 1.4 G same-address REDs per second): measured on 50 M device-resident
+// reads, 1 % of the reads on one guide cost +29 %, 10 % made the kernel 5.7x slower, 90 % 35x.
+// Warp-level remedies were measured and rejected for the per-read path: grouping lanes with
+// MATCH.ANY costs 20 % of the kernel on ordinary data, and even a one-entry register cache of
+// the warp's hot guide (vote + popcount per step) costs 9 %, because any warp-collective
+// forces the lanes to reconverge between the table probe and the RED.  What is free on the
+// per-read path is to spread the atomics: sgc_counter_set_replicas(c, R) makes warp w count
+// into copy (w mod R) of the count vector, and fold_replicas_kernel adds the copies into the
+// state vector after the count kernel (measured with R = 16: -6 % on ordinary data, 4-6x
+// faster at 10-90 % skew).  It is off by default: through sgc_counter_submit the kernel hides
+// behind the host-to-device copy whatever the skew.
+template <int MODE>
+__device__ __forceinline__ void count_hit(const CountParams& p, unsigned long long* my_counts, int32_t hit,
+                                          uint32_t& matched) {
+  if (hit >= 0) {
+    ++matched;
+    // without replicas the base is the kernel parameter itself (a uniform register)
+    if (MODE != 2 || !(p.debug & 1u)) atomicAdd((MODE == 3 ? my_counts : p.state) + hit, 1ull);
+  }
+}
+
+// state[i] += sum over the replicas, which are left zero for the next launch
+__global__ void fold_replicas_kernel(unsigned long long* __restrict__ state, unsigned long long* __restrict__ rep,
+                                     uint32_t n, uint32_t n_rep) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long sum = 0;
+  for (uint32_t r = 0; r < n_rep; ++r) {
+    const unsigned long long v = rep[(size_t)r * n + i];
+    if (v) {
+      sum += v;
+      rep[(size_t)r * n + i] = 0;
+    }
+  }
+  if (sum) state[i] += sum;
 }
 
 // Record::seq_rev_comp of the fxread crate on one byte
@@ -83,50 +116,56 @@ __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
   const uint64_t policy = l2_evict_last_policy();
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
   const int k = (int)p.lib.k;
+  unsigned long long* my_counts =
+      p.rep + (size_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (p.n_rep - 1)) * p.n_guides;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_reads; i += nthreads) {
-    const uint64_t r = p.first_read + i;
-    uint64_t start;
-    int n;
-    if (p.line_off) {
-      start = p.line_off[r];
-      n = (int)(p.line_off[r + 1] - p.line_off[r]) - 1;
-    } else {
-      start = r * p.stride;
-      n = (int)p.read_len;
-    }
-    const uint8_t* s = p.lines + start;
     int32_t hit = kMiss;
-    const int npos = p.recursion ? 3 : 1;
-    for (int pos = 0; pos < npos && hit == kMiss; ++pos) {
-      // Centered/Null: offset; Plus: offset+1; Minus: offset-1 (counter.rs:164-174)
-      int lo;
-      if (pos == 0) {
-        lo = p.offset;
-      } else if (pos == 1) {
-        lo = p.offset + 1;
+    {
+      const uint64_t r = p.first_read + i;
+      uint64_t start;
+      int n;
+      if (p.line_off) {
+        start = p.line_off[r];
+        n = (int)(p.line_off[r + 1] - p.line_off[r]) - 1;
       } else {
-        if (p.offset == 0) break;  // checked_sub(1) -> None
-        lo = p.offset - 1;
+        start = r * p.stride;
+        n = (int)p.read_len;
       }
-      if (lo + k > n) break;  // a failed trim RETURNS (counter.rs:105-108,175-176)
-      Key key{0, 0};
-      int nbad = 0;
-      uint32_t bad_pos = 0;
-      bool wild = false;
-      for (int j = 0; j < k; ++j) {
-        // forward: the read itself; reverse: byte lo+j of the reverse complement (counter.rs:196-204)
-        const uint8_t c = p.reverse ? complement_byte(s[n - 1 - (lo + j)], p.rc_mode) : s[lo + j];
-        key_set_base(key, (uint32_t)j, p.lib.wide, code_of(c));
-        if (!is_acgt(c)) {
-          ++nbad;
-          bad_pos = (uint32_t)j;
-          wild = c == 'N';
+      const uint8_t* s = p.lines + start;
+      const int npos = p.recursion ? 3 : 1;
+      for (int pos = 0; pos < npos && hit == kMiss; ++pos) {
+        // Centered/Null: offset; Plus: offset+1; Minus: offset-1 (counter.rs:164-174)
+        int lo;
+        if (pos == 0) {
+          lo = p.offset;
+        } else if (pos == 1) {
+          lo = p.offset + 1;
+        } else {
+          if (p.offset == 0) break;  // checked_sub(1) -> None
+          lo = p.offset - 1;
         }
+        if (lo + k > n) break;  // a failed trim RETURNS (counter.rs:105-108,175-176)
+        Key key{0, 0};
+        int nbad = 0;
+        uint32_t bad_pos = 0;
+        bool wild = false;
+        for (int j = 0; j < k; ++j) {
+          // forward: the read itself; reverse: byte lo+j of the reverse complement (counter.rs:196-204)
+          const uint8_t c = p.reverse ? complement_byte(s[n - 1 - (lo + j)], p.rc_mode) : s[lo + j];
+          key_set_base(key, (uint32_t)j, p.lib.wide, code_of(c));
+          if (!is_acgt(c)) {
+            ++nbad;
+            bad_pos = (uint32_t)j;
+            wild = c == 'N';
+          }
+        }
+        hit = p.lib.wide
+                  ? window_lookup_t<true>(p.lib, p.lib.fwd, p.with_perm, key, nbad, bad_pos, wild, nullptr, policy)
+                  : window_lookup_t<false>(p.lib, p.lib.fwd, p.with_perm, key, nbad, bad_pos, wild, nullptr, policy);
       }
-      hit = p.lib.wide ? window_lookup_t<true>(p.lib, p.lib.fwd, p.with_perm, key, nbad, bad_pos, wild, nullptr, policy)
-                       : window_lookup_t<false>(p.lib, p.lib.fwd, p.with_perm, key, nbad, bad_pos, wild, nullptr, policy);
+      if (p.assign_out) p.assign_out[r] = hit;
     }
-    record_hit(p, hit, r, matched);
+    count_hit<3>(p, my_counts, hit, matched);
   }
   flush_matched(p, matched);
 }
@@ -346,6 +385,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   const bool any_next = centered_again || g.try_plus;
 
   uint32_t matched = 0;
+  unsigned long long* my_counts = p.rep + (size_t)(gwarp & (p.n_rep - 1)) * p.n_guides;
   uint32_t qn = 0;  // parked reads (warp-uniform)
   int s = 0;
   uint32_t parity = 0;
@@ -360,6 +400,11 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
     Key key;
     uint32_t any;  // non-zero: some window byte is not A/C/G/T
     uint64_t b[4];  // the front bucket, in flight between the two steps
+  };
+  // a read is settled: its assignment (tests), its guide's counter
+  auto settle = [&](int32_t hit, uint32_t ridx) {
+    if ((MODE == 1 || MODE == 2) && p.assign_out) p.assign_out[ridx] = hit;
+    count_hit<MODE>(p, my_counts, hit, matched);
   };
   auto step_a = [&](Pending& pd) {
     mbar_wait(&my_bar[s], parity);
@@ -435,15 +480,15 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
       }
       if (found) {
         park = -1;
-        record_hit<MODE>(p, hit, (uint64_t)read_idx, matched);
+        settle(hit, read_idx);
       } else if (!flagged && !centered_again) {
         // not a member and no Permuter: Centered is decided, go on with Plus if there is one
         park = g.try_plus ? 1 : -1;
-        if (park < 0) record_hit<MODE>(p, kMiss, (uint64_t)read_idx, matched);
+        if (park < 0) settle(kMiss, read_idx);
       }
     } else if (!any_next) {
       park = -1;  // a bad byte, no Permuter, no recursion
-      record_hit<MODE>(p, kMiss, (uint64_t)read_idx, matched);
+      settle(kMiss, read_idx);
     }
     if (MODE == 2 && (debug & 4u)) park = -1;
     const uint32_t pm = __ballot_sync(0xffffffffu, park >= 0);
@@ -476,7 +521,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
         const uint32_t shift = pos == 0 ? g.shift_bits[0] : (pos == 1 ? g.shift_bits[1] : g.shift_bits[2]);
         const int32_t hit = try_position<NW, WIDE>(p.lib, ix, g, S, shift, table_policy);
         if (hit == kMiss) next = pos == 0 ? (g.try_plus ? 1 : -1) : (pos == 1 && g.try_minus ? 2 : -1);
-        if (next < 0) record_hit<MODE>(p, hit, (uint64_t)ridx, matched);
+        if (next < 0) settle(hit, ridx);
       }
       __syncwarp();  // every lane has read its entry before any slot is overwritten
       const uint32_t pm = __ballot_sync(0xffffffffu, next >= 0);
@@ -529,6 +574,8 @@ struct sgc_counter {
   cudaStream_t stream = nullptr;
   unsigned long long* d_state = nullptr;
   bool own_state = false;
+  unsigned long long* d_rep = nullptr;  // n_rep x n_guides words, zero between launches
+  uint32_t n_rep = 1;
   // host-batch staging (sgc_counter_submit)
   cudaStream_t copy_stream = nullptr;
   uint8_t* d_stage[2] = {nullptr, nullptr};
@@ -565,6 +612,8 @@ CountParams make_params(const sgc_counter* c, const uint8_t* d_lines, const uint
   p.recursion = c->recursion != 0;
   p.rc_mode = (uint8_t)c->rc_mode;
   p.state = c->d_state;
+  p.rep = c->n_rep > 1 ? c->d_rep : c->d_state;
+  p.n_rep = c->n_rep;
   p.n_guides = c->lib->n;
   p.assign_out = d_assign;
   p.debug = (uint32_t)env_int("SGC_DEBUG", 0);
@@ -623,12 +672,17 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
   const uint64_t max_tiles = (1ull << kReadIdxBits) / kWarpReads - 65536;
   while (tiles_left > 0) {
     const uint64_t n_wtiles = std::min(tiles_left, max_tiles);
-    const int mode = p.debug ? 2 : (d_assign ? 1 : 0);
+    // replicas are a production feature: with a per-read output or tuning switches the counts go
+    // straight to the state vector (p.rep == p.state then, see make_params)
+    const int mode = p.debug ? 2 : (d_assign ? 1 : (c->n_rep > 1 ? 3 : 0));
     using Kernel = void (*)(const CountParams, uint32_t, int, uint32_t);
-    static const Kernel kernels[3][3] = {
-        {count_stream_kernel<5, false, 0>, count_stream_kernel<5, false, 1>, count_stream_kernel<5, false, 2>},
-        {count_stream_kernel<8, false, 0>, count_stream_kernel<8, false, 1>, count_stream_kernel<8, false, 2>},
-        {count_stream_kernel<8, true, 0>, count_stream_kernel<8, true, 1>, count_stream_kernel<8, true, 2>}};
+    static const Kernel kernels[3][4] = {
+        {count_stream_kernel<5, false, 0>, count_stream_kernel<5, false, 1>, count_stream_kernel<5, false, 2>,
+         count_stream_kernel<5, false, 3>},
+        {count_stream_kernel<8, false, 0>, count_stream_kernel<8, false, 1>, count_stream_kernel<8, false, 2>,
+         count_stream_kernel<8, false, 3>},
+        {count_stream_kernel<8, true, 0>, count_stream_kernel<8, true, 1>, count_stream_kernel<8, true, 2>,
+         count_stream_kernel<8, true, 3>}};
     Kernel kernel = kernels[c->lib->wide ? 2 : (nw5 ? 0 : 1)][mode];
     const size_t smem = stream_smem_bytes(cfg, stage_bytes, queue_bytes);
     SGC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -662,6 +716,11 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
       c->last.grid = (uint32_t)blocks;
       c->last.block = 256;
     }
+    c->last.launches_total += 1;
+  }
+  if (c->n_rep > 1) {
+    fold_replicas_kernel<<<(c->lib->n + 255) / 256, 256, 0, stream>>>(c->d_state, c->d_rep, c->lib->n, c->n_rep);
+    SGC_CUDA_TRY(cudaGetLastError());
     c->last.launches_total += 1;
   }
   return SGC_OK;
@@ -714,6 +773,11 @@ int sgc_counter_create(const sgc_library* lib, int is_reverse, uint32_t offset, 
     c->own_state = true;
   }
   SGC_CUDA_TRY(cudaMemsetAsync(c->d_state, 0, words * sizeof(uint64_t), c->stream));
+  const int want_rep = env_int("SGC_REPLICAS", 1);  // tuning override of sgc_counter_set_replicas
+  if (want_rep > 1) {
+    int rc = sgc_counter_set_replicas(c, (uint32_t)want_rep);
+    if (rc) return rc;
+  }
   cleanup.c = nullptr;
   *out = c;
   return SGC_OK;
@@ -733,6 +797,7 @@ void sgc_counter_destroy(sgc_counter* c) {
     if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
     if (c->kernel_done[i]) cudaEventDestroy(c->kernel_done[i]);
   }
+  cudaFree(c->d_rep);
   if (c->own_state) cudaFree(c->d_state);
   delete c;
 }
@@ -820,6 +885,26 @@ int sgc_counter_submit(sgc_counter* c, const uint8_t* lines, uint64_t n_bytes, c
     SGC_CUDA_TRY(cudaEventRecord(c->kernel_done[b], c->stream));
     c->chunks_submitted += 1;
     r0 = r1;
+  }
+  return SGC_OK;
+}
+
+int sgc_counter_set_replicas(sgc_counter* c, uint32_t replicas) {
+  if (!c) return set_error(SGC_ERR_INVALID_ARG, "counter is NULL");
+  DeviceGuard guard(c->lib->device);
+  // a power of two, at most 64 copies and 64 MB
+  uint32_t n_rep = 1;
+  while (n_rep * 2 <= replicas && n_rep < 64 && (size_t)n_rep * 2 * c->lib->n * sizeof(uint64_t) <= (64u << 20))
+    n_rep *= 2;
+  if (n_rep == c->n_rep) return SGC_OK;
+  SGC_CUDA_TRY(cudaStreamSynchronize(c->stream));  // the replicas are zero between launches
+  cudaFree(c->d_rep);
+  c->d_rep = nullptr;
+  c->n_rep = 1;
+  if (n_rep > 1) {
+    SGC_CUDA_TRY(cudaMalloc(&c->d_rep, (size_t)n_rep * c->lib->n * sizeof(uint64_t)));
+    SGC_CUDA_TRY(cudaMemsetAsync(c->d_rep, 0, (size_t)n_rep * c->lib->n * sizeof(uint64_t), c->stream));
+    c->n_rep = n_rep;
   }
   return SGC_OK;
 }

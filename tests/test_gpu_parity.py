@@ -212,3 +212,28 @@ def test_brunello_shaped_two_million_reads():
     want = oracle_count(guides, seqs, True, off, n_threads=os.cpu_count() or 4)
     assert np.array_equal(got[0], want[0])
     assert np.array_equal(got[1], want[1]) and got[2:4] == want[2:4]
+
+
+def test_count_replicas_give_the_same_table_on_a_skewed_sample():
+    """sgc_counter_set_replicas: a third of the reads carry one guide; 1, 16 and 64 copies of the
+    count vector must fold to the same table, batch after batch"""
+    rng = np.random.default_rng(21)
+    guides = make_library(rng, 400, 20)
+    seqs = make_reads(rng, guides, 6000, 75, 5)
+    hot = seqs[0][:5] + guides[7] + seqs[0][25:]
+    seqs = [hot if rng.random() < 0.33 else s for s in seqs]
+    library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+    permuter = sg.Permuter.new(library)
+    want = oracle_count(guides, seqs, True, sg.Offset.Forward(5))
+    for force in (False, True):
+        batch = sg.ReadBatch.from_seqs(seqs, force_offsets=force)
+        for replicas in (1, 16, 64, 3):
+            c = sg.Counter(library, permuter, sg.Offset.Forward(5))
+            c.set_replicas(replicas)
+            c.submit(batch)
+            c.submit(batch)
+            counts, total, matched = c.finish()
+            assert np.array_equal(counts, 2 * want[1]) and (total, matched) == (2 * want[2], 2 * want[3])
+            c.set_replicas(1)
+            c.submit(batch)
+            assert np.array_equal(c.finish()[0], 3 * want[1])
