@@ -188,10 +188,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+// The ring is addressed with 32-bit shared-space addresses kept in registers: generic pointers
+// would have the compiler rebuild the shared window base for every tile.
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -200,18 +202,36 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
+      "}\n" ::"r"(bar),
       "r"(parity)
       : "memory");
 }
 // 1-D bulk async copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
-          "r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
+template <int OFFSET>
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFFSET) : "memory");
+  return v;
+}
+// W[I..N) = consecutive shared-memory words from `addr`
+template <int I, int N>
+struct LoadWords {
+  static __device__ __forceinline__ void run(uint32_t addr, uint32_t* W) {
+    W[I] = lds_u32<4 * I>(addr);
+    LoadWords<I + 1, N>::run(addr, W);
+  }
+};
+template <int N>
+struct LoadWords<N, N> {
+  static __device__ __forceinline__ void run(uint32_t, uint32_t*) {}
+};
 
 // bit 7 of every non-zero byte of x
 __device__ __forceinline__ uint32_t nonzero_byte_flags(uint32_t x) {
@@ -350,6 +370,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   const uint64_t src_step = (uint64_t)gwarps * tile_bytes;
   const uint8_t* next_src = p.lines + (uint64_t)gwarp * tile_bytes;  // source of the next tile to request
 
+  const uint32_t tiles_sm = smem_u32(my_tiles), bars_sm = smem_u32(my_bar);
   uint64_t policy = 0;
   uint32_t requested = gwarp;  // tile index of the next request (n_wtiles + gwarps < 2^32)
   if (lane == 0) {
@@ -359,8 +380,8 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
     policy = l2_evict_first_policy();
     for (int s = 0; s < n_stages; ++s) {
       if (requested < n_wtiles) {
-        mbar_expect_tx(&my_bar[s], tile_bytes);
-        bulk_load(my_tiles + (size_t)s * stage_bytes, next_src, tile_bytes, &my_bar[s], policy);
+        mbar_expect_tx(bars_sm + 8u * (uint32_t)s, tile_bytes);
+        bulk_load(tiles_sm + (uint32_t)s * stage_bytes, next_src, tile_bytes, bars_sm + 8u * (uint32_t)s, policy);
         requested += gwarps;
         next_src += src_step;
       }
@@ -372,7 +393,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   // Centered window does not fit (every one of them fails its first trim) to the generic kernel
   const StreamGeom g = make_geom(p);
   const uint32_t sbyte = (uint32_t)lane * p.stride + (uint32_t)(g.win_src - g.lead);  // first span byte
-  const uint32_t word0 = sbyte >> 2;
+  const uint32_t lane_off = sbyte & ~3u;  // byte offset of this lane's first span word in a tile
   const uint32_t off_bits = (sbyte & 3u) * 8;
   const uint32_t win_bits = off_bits + g.shift_bits[0];  // 0..32: where the Centered window starts in W
   const IndexView& ix = p.reverse ? p.lib.rev : p.lib.fwd;
@@ -389,6 +410,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   uint32_t qn = 0;  // parked reads (warp-uniform)
   int s = 0;
   uint32_t parity = 0;
+  uint32_t cur_tile = tiles_sm, cur_bar = bars_sm;  // stage s of the ring
 
   // A tile is handled in two steps one loop iteration apart, so that the front-table sector of
   // tile j+1 travels L2 -> L1 while tile j is being finished (and its parked reads drained):
@@ -407,12 +429,9 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
     count_hit<MODE>(p, my_counts, hit, matched);
   };
   auto step_a = [&](Pending& pd) {
-    mbar_wait(&my_bar[s], parity);
-    uint8_t* stage = my_tiles + (size_t)s * stage_bytes;
-    const uint32_t* tile = reinterpret_cast<const uint32_t*>(stage);
+    mbar_wait(cur_bar, parity);
     uint32_t W[NW + 2];
-#pragma unroll
-    for (int i = 0; i < NW + 2; ++i) W[i] = tile[word0 + i];
+    LoadWords<0, NW + 2>::run(cur_tile + lane_off, W);
     {
       // The buffer may be refilled once every lane's loads have RETURNED.  A warp vote on a
       // value computed from all of them is that point: it cannot issue before the data is in
@@ -430,14 +449,18 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
       (void)vote;
     }
     if (lane == 0 && requested < n_wtiles) {
-      mbar_expect_tx(&my_bar[s], tile_bytes);
-      bulk_load(stage, next_src, tile_bytes, &my_bar[s], policy);
+      mbar_expect_tx(cur_bar, tile_bytes);
+      bulk_load(cur_tile, next_src, tile_bytes, cur_bar, policy);
       requested += gwarps;
       next_src += src_step;
     }
+    cur_tile += stage_bytes;
+    cur_bar += 8;
     if (++s == n_stages) {
       s = 0;
       parity ^= 1u;
+      cur_tile = tiles_sm;
+      cur_bar = bars_sm;
     }
 #pragma unroll
     for (int i = 0; i < NW + 1; ++i) pd.S[i] = __funnelshift_r(W[i], W[i + 1], off_bits);
