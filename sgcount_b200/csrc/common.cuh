@@ -56,10 +56,17 @@ constexpr uint32_t kNarrowMaxK = 20;
 constexpr int kSeeds = 3;
 constexpr int32_t kMiss = -1;
 
-// directory entry: [21:0] first posting of the bucket, [23:22] number of postings, [31:24] tag
-// (the 8 hash bits below the bucket bits) shared by every posting of the bucket.  Count 3 marks
-// a GENERAL bucket: more than two postings, or postings of different tags; its exact size is
-// in IndexView::dir_count and its tag is not used.
+// NARROW directory entry (k <= 20), 64 bit, kind in [63:62]:
+//   0  empty bucket
+//   1  the bucket's ONLY posting, inline: [31:0] lo, [39:32] hi, [61:40] guide index — the common
+//      case is decided with ONE load, and the inline key is its own (exact) tag
+//   2  a run of postings: [21:0] first posting, [53:22] count
+constexpr uint64_t kDirKindInline = 1ull << 62, kDirKindRun = 2ull << 62;
+constexpr int kDirKindShift = 62;
+// WIDE directory entry (k = 21..30), 32 bit: [21:0] first posting of the bucket, [23:22] number
+// of postings, [31:24] tag (the 8 hash bits below the bucket bits) shared by every posting of
+// the bucket.  Count 3 marks a GENERAL bucket: more than two postings, or postings of different
+// tags; its exact size is in IndexView::dir_count and its tag is not used.
 constexpr uint32_t kDirStartMask = 0x3FFFFFu;
 constexpr int kDirCountShift = 22;
 constexpr uint32_t kDirGeneral = 3u;
@@ -119,8 +126,9 @@ __host__ __device__ __forceinline__ uint32_t code_of(uint8_t c) { return (c >> 1
 
 // One orientation's structures.
 struct IndexView {
-  const uint32_t* __restrict__ dir[kSeeds];        // 1 << dir_bits entries each
-  const uint32_t* __restrict__ dir_count[kSeeds];  // exact bucket sizes (read for general buckets only)
+  const uint64_t* __restrict__ dir64[kSeeds];      // narrow: 1 << dir_bits entries each
+  const uint32_t* __restrict__ dir[kSeeds];        // wide: 1 << dir_bits entries each
+  const uint32_t* __restrict__ dir_count[kSeeds];  // wide: exact bucket sizes (read for general buckets only)
   const uint64_t* __restrict__ post;               // kSeeds x n postings, list i at i * n, each sorted by bucket
                                                    // (2 words per posting when wide)
   const uint64_t* __restrict__ front;              // front table
@@ -178,6 +186,7 @@ struct SeedRun {
   uint32_t first;  // index of the first posting in IndexView::post (list offset included)
   uint32_t count;
 };
+// wide entries
 __device__ __forceinline__ SeedRun seed_run(const LibView& v, const IndexView& ix, int seed, uint32_t h, uint32_t entry) {
   SeedRun r;
   r.first = (uint32_t)seed * v.n + (entry & kDirStartMask);
@@ -186,6 +195,13 @@ __device__ __forceinline__ SeedRun seed_run(const LibView& v, const IndexView& i
     r.count = ix.dir_count[seed][h >> v.dir_shift];
   else if ((entry >> kDirTagShift) != ((h >> (v.dir_shift - 8)) & 0xFFu))
     r.count = 0;  // the bucket belongs to another seed
+  return r;
+}
+// narrow entries of kind 2 (any other kind: an empty run)
+__device__ __forceinline__ SeedRun seed_run64(const LibView& v, int seed, uint64_t entry) {
+  SeedRun r;
+  r.first = (uint32_t)seed * v.n + ((uint32_t)entry & kDirStartMask);
+  r.count = (entry >> kDirKindShift) == 2 ? (uint32_t)(entry >> 22) : 0u;
   return r;
 }
 template <bool WIDE>
@@ -197,7 +213,7 @@ __device__ __forceinline__ void load_posting(const IndexView& ix, uint32_t at, u
   } else {
     const uint64_t w = ldg_u64(ix.post + at, policy);
     key = Key{(uint32_t)w, (uint32_t)(w >> 32) & 0xFFu};
-    idx = (uint32_t)(w >> kPostIdxShift);
+    idx = (uint32_t)(w >> kPostIdxShift) & 0x3FFFFFu;
   }
 }
 
@@ -207,7 +223,17 @@ template <bool WIDE, typename F>
 __device__ __forceinline__ void for_each_posting(const LibView& v, const IndexView& ix, int seed, Key key,
                                                  uint64_t policy, F&& visit) {
   const uint32_t h = seed_hash(seed_of(key, seed));
-  const SeedRun r = seed_run(v, ix, seed, h, ldg_u32(ix.dir[seed] + (h >> v.dir_shift), policy));
+  SeedRun r;
+  if (WIDE) {
+    r = seed_run(v, ix, seed, h, ldg_u32(ix.dir[seed] + (h >> v.dir_shift), policy));
+  } else {
+    const uint64_t e = ldg_u64(ix.dir64[seed] + (h >> v.dir_shift), policy);
+    if ((e >> kDirKindShift) == 1) {
+      visit(Key{(uint32_t)e, (uint32_t)(e >> 32) & 0xFFu}, (uint32_t)(e >> kPostIdxShift) & 0x3FFFFFu);
+      return;
+    }
+    r = seed_run64(v, seed, e);
+  }
 #pragma unroll 1
   for (uint32_t c = 0; c < r.count; ++c) {
     Key mk;
@@ -222,46 +248,71 @@ __device__ __forceinline__ void for_each_posting(const LibView& v, const IndexVi
 template <bool WIDE>
 __device__ __forceinline__ int32_t lookup_clean(const LibView& v, const IndexView& ix, bool with_perm, Key key,
                                                 int* kind, uint64_t policy) {
-  // The three directory entries are fetched together (without a Permuter only the first is
-  // needed: a member sits in every list) and their runs are walked as ONE sequence, so a warp
-  // iterates max-over-lanes of the candidates per window, not per list.
-  uint32_t h[kSeeds], entry[kSeeds];
-#pragma unroll
-  for (int i = 0; i < kSeeds; ++i) {
-    h[i] = seed_hash(seed_of(key, i));
-    entry[i] = (i == 0 || with_perm) ? ldg_u32(ix.dir[i] + (h[i] >> v.dir_shift), policy) : 0u;
-  }
-  SeedRun r[kSeeds];
-#pragma unroll
-  for (int i = 0; i < kSeeds; ++i) {
-    r[i] = seed_run(v, ix, i, h[i], entry[i]);
-    if (i > 0 && !with_perm) r[i].count = 0;
-  }
-  static_assert(kSeeds == 3, "the merged walk below is written for three lists");
-  const uint32_t end0 = r[0].count, end1 = end0 + r[1].count, total = end1 + r[2].count;
-  const uint32_t base0 = r[0].first, base1 = r[1].first - end0, base2 = r[2].first - end1;
+  static_assert(kSeeds == 3, "written for three lists");
   int32_t found = kMiss;
   int parents = 0;
+  bool member = false;
+  // one candidate of list `list`: a posting of another seed that hashed to this bucket differs
+  // on what the list keeps; the token itself is a member; a difference of one base lies inside
+  // the part this list leaves out
+  auto consider = [&](int list, Key mk, uint32_t idx) {
+    const Key x{mk.lo ^ key.lo, mk.hi ^ key.hi};
+    const uint32_t keep_lo = list == 0 ? 0xF0F0F0F0u : (list == 1 ? 0x0F0F0F0Fu : 0xFFFFFFFFu);
+    if (((x.lo & keep_lo) | (list < 2 ? x.hi : 0u)) != 0) return;
+    if ((x.lo | x.hi) == 0) {  // Library::contains (counter.rs:111-112)
+      member = true;
+      found = (int32_t)idx;
+    } else if (!member && bases_differing(x) == 1) {
+      ++parents;
+      found = (int32_t)idx;
+    }
+  };
+  // The three directory entries are fetched together (without a Permuter only the first is
+  // needed: a member sits in every list).  Narrow keys: a bucket with one posting carries it
+  // inline, so the usual window is decided by this one round trip.  What is left are runs of
+  // postings, walked as ONE sequence so that a warp iterates max-over-lanes of the candidates
+  // per window, not per list.
+  uint32_t h[kSeeds];
+  SeedRun r[kSeeds];
+#pragma unroll
+  for (int i = 0; i < kSeeds; ++i) h[i] = seed_hash(seed_of(key, i));
+  if (WIDE) {
+    uint32_t entry[kSeeds];
+#pragma unroll
+    for (int i = 0; i < kSeeds; ++i)
+      entry[i] = (i == 0 || with_perm) ? ldg_u32(ix.dir[i] + (h[i] >> v.dir_shift), policy) : 0u;
+#pragma unroll
+    for (int i = 0; i < kSeeds; ++i) {
+      r[i] = seed_run(v, ix, i, h[i], entry[i]);
+      if (i > 0 && !with_perm) r[i].count = 0;
+    }
+  } else {
+    uint64_t entry[kSeeds];
+#pragma unroll
+    for (int i = 0; i < kSeeds; ++i)
+      entry[i] = (i == 0 || with_perm) ? ldg_u64(ix.dir64[i] + (h[i] >> v.dir_shift), policy) : 0ull;
+#pragma unroll
+    for (int i = 0; i < kSeeds; ++i) {
+      if ((entry[i] >> kDirKindShift) == 1)
+        consider(i, Key{(uint32_t)entry[i], (uint32_t)(entry[i] >> 32) & 0xFFu},
+                 (uint32_t)(entry[i] >> kPostIdxShift) & 0x3FFFFFu);
+      r[i] = seed_run64(v, i, entry[i]);
+    }
+  }
+  const uint32_t end0 = r[0].count, end1 = end0 + r[1].count, total = end1 + r[2].count;
+  const uint32_t base0 = r[0].first, base1 = r[1].first - end0, base2 = r[2].first - end1;
 #pragma unroll 1
-  for (uint32_t j = 0; j < total; ++j) {
+  for (uint32_t j = 0; j < total && !member; ++j) {
     const bool in0 = j < end0, in1 = j < end1;
     const uint32_t at = (in0 ? base0 : (in1 ? base1 : base2)) + j;
     Key mk;
     uint32_t idx;
     load_posting<WIDE>(ix, at, policy, mk, idx);
-    const Key x{mk.lo ^ key.lo, mk.hi ^ key.hi};
-    // a posting of another seed that hashed to this bucket differs on what the list keeps
-    const uint32_t keep_lo = in0 ? 0xF0F0F0F0u : (in1 ? 0x0F0F0F0Fu : 0xFFFFFFFFu);
-    const uint32_t off_seed = (x.lo & keep_lo) | (in1 ? x.hi : 0u);  // in1 covers lists 0 and 1
-    if (off_seed != 0) continue;
-    if ((x.lo | x.hi) == 0) {  // Library::contains (counter.rs:111-112)
-      if (kind) *kind = 1;
-      return (int32_t)idx;
-    }
-    if (bases_differing(x) == 1) {  // the difference lies inside the part this list leaves out
-      ++parents;
-      found = (int32_t)idx;
-    }
+    consider(in0 ? 0 : (in1 ? 1 : 2), mk, idx);
+  }
+  if (member) {
+    if (kind) *kind = 1;
+    return found;
   }
   if (with_perm && parents == 1) {  // Permuter::contains -> Library::alias (counter.rs:113-116)
     if (kind) *kind = 2;

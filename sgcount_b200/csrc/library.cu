@@ -198,6 +198,20 @@ __global__ void seed_dir_kernel(const uint32_t* __restrict__ start, const uint32
   dir[i] = start[i] | ((general ? kDirGeneral : c) << kDirCountShift) | ((t & 0xFFu) << kDirTagShift);
 }
 
+// narrow keys: 64-bit entries; a bucket with one posting carries the posting itself
+__global__ void seed_dir64_kernel(const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt,
+                                  const uint64_t* __restrict__ post, uint64_t* __restrict__ dir, uint32_t n_entries) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_entries) return;
+  const uint32_t c = cnt[i];
+  uint64_t e = 0;
+  if (c == 1)
+    e = kDirKindInline | (post[start[i]] & (kDirKindInline - 1));
+  else if (c >= 2)
+    e = kDirKindRun | start[i] | ((uint64_t)c << 22);
+  dir[i] = e;
+}
+
 // ---- checks and statistics through the finished (forward) index -----------------------------
 // duplicate sequences (library.rs:91-95): the later of two equal records reports itself
 template <bool WIDE>
@@ -372,6 +386,7 @@ void sgc_library_destroy(sgc_library* lib) {
   DeviceGuard g(lib->device);
   for (int o = 0; o < 2; ++o) {
     for (int i = 0; i < kSeeds; ++i) {
+      cudaFree(lib->ix[o].d_dir64[i]);
       cudaFree(lib->ix[o].d_dir[i]);
       cudaFree(lib->ix[o].d_dir_count[i]);
     }
@@ -433,8 +448,14 @@ int build_index(sgc_library* lib, int o, BuildScratch& sc, BuildStatus* d_st) {
     SGC_CUDA_TRY(cudaMemcpyAsync(sc.cur[i].p, sc.start[i].p, (size_t)entries * 4, cudaMemcpyDeviceToDevice, 0));
   }
   seed_fill_kernel<WIDE><<<blocks_for(n, T), T>>>(ix.d_keys, n, lib->dir_shift, cursor, ix.d_post);
-  for (int i = 0; i < kSeeds; ++i)
-    seed_dir_kernel<<<blocks_for(entries, T), T>>>(sc.start[i].p, ix.d_dir_count[i], sc.tag[i].p, ix.d_dir[i], entries);
+  for (int i = 0; i < kSeeds; ++i) {
+    if (WIDE)
+      seed_dir_kernel<<<blocks_for(entries, T), T>>>(sc.start[i].p, ix.d_dir_count[i], sc.tag[i].p, ix.d_dir[i],
+                                                     entries);
+    else
+      seed_dir64_kernel<<<blocks_for(entries, T), T>>>(sc.start[i].p, ix.d_dir_count[i], ix.d_post + (size_t)i * n,
+                                                       ix.d_dir64[i], entries);
+  }
   SGC_CUDA_TRY(cudaMemsetAsync(ix.d_front, 0, lib->front_bytes, 0));
   front_insert_kernel<WIDE><<<blocks_for(n, T), T>>>(ix.d_front, lib->front_shift, ix.d_keys, n, d_st);
   SGC_CUDA_TRY(cudaGetLastError());
@@ -511,7 +532,10 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
     sgc_library::Index& ix = lib->ix[o];
     SGC_CUDA_TRY(cudaMalloc(&ix.d_keys, (size_t)n * sizeof(uint64_t)));
     for (int i = 0; i < kSeeds; ++i) {
-      SGC_CUDA_TRY(cudaMalloc(&ix.d_dir[i], dir_entries * 4));
+      if (lib->wide)
+        SGC_CUDA_TRY(cudaMalloc(&ix.d_dir[i], dir_entries * 4));
+      else
+        SGC_CUDA_TRY(cudaMalloc(&ix.d_dir64[i], dir_entries * 8));
       SGC_CUDA_TRY(cudaMalloc(&ix.d_dir_count[i], dir_entries * 4));
     }
     SGC_CUDA_TRY(cudaMalloc(&ix.d_post, kSeeds * post_words * 8));
@@ -563,7 +587,7 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   lib->info.n_ambiguous = st.n_ambiguous;
   lib->info.n_slots = ((size_t)1 << log_buckets) * (lib->wide ? 2 : 4);
   // what one counter touches: the directories, postings and front table of its orientation
-  lib->info.table_bytes = kSeeds * (dir_entries * 4 + post_words * 8) + lib->front_bytes;
+  lib->info.table_bytes = kSeeds * (dir_entries * (lib->wide ? 4 : 8) + post_words * 8) + lib->front_bytes;
   lib->info.build_ms = ms;
   lib->info.front_left_out = st.front_left_out;
   cleanup.l = nullptr;
