@@ -250,7 +250,9 @@ class ClockSampler(threading.Thread):
                     self.reason_bits |= int(bits)
                 except Exception:
                     pass
-            time.sleep(0.01)
+                time.sleep(0.0005)  # an NVML query takes a fraction of a millisecond: sample back to back
+            else:
+                time.sleep(0.002)
 
     def summary(self):
         if not self.ok or not self.samples:
@@ -389,6 +391,26 @@ def run_gpu(args):
         sampler.reason_bits = 0
         total_ms, kernel_ms, launches = timed_kernel_arm()
     clocks_kernel = sampler.summary()
+    clocks_kernel["window"] = "timed region"
+    if clocks_kernel["samples"] < 5:
+        # K steps of ~1 ms are over before NVML answers a handful of queries: sample the SAME launches,
+        # back to back for a quarter of a second, right after the timed region (not part of `value`)
+        sampler.active.set()
+        t_end = time.perf_counter() + 0.25
+        i = 0
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                kernel_step(i)
+                i += 1
+            join_reduces()
+            torch.cuda.synchronize()
+        barrier()
+        sampler.active.clear()
+        clocks_kernel = sampler.summary()
+        clocks_kernel["window"] = "timed region + 0.25 s of the same launches right after it"
+        kernel_step(args.steps - 1)  # leave the last timed step's table in its state vector
+        join_reduces()
+        torch.cuda.synchronize()
 
     last = (args.steps - 1) % n_buf
     state, counter = states[last], counters[last]
@@ -484,7 +506,7 @@ def run_gpu(args):
                                  "duration = CUDA events around sgc_counter_submit_device on the launching stream, mean over the timed steps"},
             "clocks": {"sm_mhz": clocks_kernel["sm_mhz"], "sm_max_mhz": clocks_kernel["sm_max_mhz"],
                        "reasons": clocks_kernel["reasons"], "samples": clocks_kernel["samples"],
-                       "e2e_sm_mhz": clocks_e2e["sm_mhz"]},
+                       "window": clocks_kernel["window"], "e2e_sm_mhz": clocks_e2e["sm_mhz"]},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = cpu_threads()

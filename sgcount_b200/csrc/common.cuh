@@ -243,54 +243,69 @@ __device__ __forceinline__ void for_each_posting(const LibView& v, const IndexVi
   }
 }
 
-// A token all of whose bytes are A/C/G/T (Library::contains, then Permuter::contains,
-// counter.rs:111-117).  Returns the guide index or kMiss; *kind = 1 member, 2 one-mismatch variant.
+// ONE token against the seed index, both kinds of token through the same straight-line code so
+// that the lanes of a warp stay together (counter.rs:111-117):
+//   hole_list < 0   every byte is A/C/G/T: Library::contains, then Permuter::contains.  A posting
+//                   equal to the token is the member; otherwise exactly one member at Hamming
+//                   distance 1 is the Permuter's parent, two or more its null set.
+//   hole_list >= 0  exactly one byte is the wildcard; `hole` is its 2-bit field, already cleared
+//                   in `key`, and hole_list the list of the part it lies in.  Its parents are the
+//                   members equal to it everywhere else; they all sit in that one list (the other
+//                   lists keep the hole base in their seed and are not consulted).
+//   !active         nothing is loaded, the answer is kMiss.
+// Returns the guide index or kMiss; *kind = 1 member, 2 one-mismatch variant.
 template <bool WIDE>
-__device__ __forceinline__ int32_t lookup_clean(const LibView& v, const IndexView& ix, bool with_perm, Key key,
-                                                int* kind, uint64_t policy) {
+__device__ __forceinline__ int32_t lookup_token(const LibView& v, const IndexView& ix, bool with_perm, Key key, Key hole,
+                                                int hole_list, bool active, int* kind, uint64_t policy) {
   static_assert(kSeeds == 3, "written for three lists");
+  const bool wild = hole_list >= 0;
   int32_t found = kMiss;
   int parents = 0;
   bool member = false;
   // one candidate of list `list`: a posting of another seed that hashed to this bucket differs
-  // on what the list keeps; the token itself is a member; a difference of one base lies inside
-  // the part this list leaves out
+  // on what the list keeps; a difference of one base lies inside the part this list leaves out
   auto consider = [&](int list, Key mk, uint32_t idx) {
-    const Key x{mk.lo ^ key.lo, mk.hi ^ key.hi};
+    const Key x{(mk.lo ^ key.lo) & ~hole.lo, (mk.hi ^ key.hi) & ~hole.hi};
     const uint32_t keep_lo = list == 0 ? 0xF0F0F0F0u : (list == 1 ? 0x0F0F0F0Fu : 0xFFFFFFFFu);
     if (((x.lo & keep_lo) | (list < 2 ? x.hi : 0u)) != 0) return;
-    if ((x.lo | x.hi) == 0) {  // Library::contains (counter.rs:111-112)
-      member = true;
+    if ((x.lo | x.hi) == 0) {
+      if (wild) {
+        ++parents;
+      } else {
+        member = true;  // Library::contains (counter.rs:111-112)
+      }
       found = (int32_t)idx;
-    } else if (!member && bases_differing(x) == 1) {
+    } else if (!wild && !member && bases_differing(x) == 1) {
       ++parents;
       found = (int32_t)idx;
     }
   };
-  // The three directory entries are fetched together (without a Permuter only the first is
-  // needed: a member sits in every list).  Narrow keys: a bucket with one posting carries it
-  // inline, so the usual window is decided by this one round trip.  What is left are runs of
-  // postings, walked as ONE sequence so that a warp iterates max-over-lanes of the candidates
-  // per window, not per list.
+  // The directory entries are fetched together (without a Permuter only the first is needed: a
+  // member sits in every list).  Narrow keys: a bucket with one posting carries it inline, so
+  // the usual window is decided by this one round trip.  What is left are runs of postings,
+  // walked as ONE sequence so that a warp iterates max-over-lanes of the candidates per window,
+  // not per list.
+  bool use[kSeeds];
   uint32_t h[kSeeds];
   SeedRun r[kSeeds];
 #pragma unroll
-  for (int i = 0; i < kSeeds; ++i) h[i] = seed_hash(seed_of(key, i));
+  for (int i = 0; i < kSeeds; ++i) {
+    use[i] = active && (wild ? i == hole_list : (i == 0 || with_perm));
+    h[i] = seed_hash(seed_of(key, i));
+  }
   if (WIDE) {
     uint32_t entry[kSeeds];
 #pragma unroll
-    for (int i = 0; i < kSeeds; ++i)
-      entry[i] = (i == 0 || with_perm) ? ldg_u32(ix.dir[i] + (h[i] >> v.dir_shift), policy) : 0u;
+    for (int i = 0; i < kSeeds; ++i) entry[i] = use[i] ? ldg_u32(ix.dir[i] + (h[i] >> v.dir_shift), policy) : 0u;
 #pragma unroll
     for (int i = 0; i < kSeeds; ++i) {
-      r[i] = seed_run(v, ix, i, h[i], entry[i]);
-      if (i > 0 && !with_perm) r[i].count = 0;
+      r[i].first = r[i].count = 0;
+      if (use[i]) r[i] = seed_run(v, ix, i, h[i], entry[i]);
     }
   } else {
     uint64_t entry[kSeeds];
 #pragma unroll
-    for (int i = 0; i < kSeeds; ++i)
-      entry[i] = (i == 0 || with_perm) ? ldg_u64(ix.dir64[i] + (h[i] >> v.dir_shift), policy) : 0ull;
+    for (int i = 0; i < kSeeds; ++i) entry[i] = use[i] ? ldg_u64(ix.dir64[i] + (h[i] >> v.dir_shift), policy) : 0ull;
 #pragma unroll
     for (int i = 0; i < kSeeds; ++i) {
       if ((entry[i] >> kDirKindShift) == 1)
@@ -321,28 +336,22 @@ __device__ __forceinline__ int32_t lookup_clean(const LibView& v, const IndexVie
   return kMiss;  // no parent, or the Permuter's null set (permutes.rs:149-152)
 }
 
+// A token all of whose bytes are A/C/G/T.
+template <bool WIDE>
+__device__ __forceinline__ int32_t lookup_clean(const LibView& v, const IndexView& ix, bool with_perm, Key key,
+                                                int* kind, uint64_t policy) {
+  return lookup_token<WIDE>(v, ix, with_perm, key, Key{0u, 0u}, -1, true, kind, policy);
+}
+
 // A token with exactly one wildcard byte at base `pos` (its 2-bit field in `key` is ignored):
-// the parents are the members equal to it everywhere else.
+// the parents are the members equal to it everywhere else.  Only asked with a Permuter.
 template <bool WIDE>
 __device__ __forceinline__ int32_t lookup_wild(const LibView& v, const IndexView& ix, Key key, uint32_t pos, int* kind,
                                                uint64_t policy) {
   const Key hole = base_field(pos, WIDE);
   key.lo &= ~hole.lo;
   key.hi &= ~hole.hi;
-  int32_t found = kMiss;
-  int parents = 0;
-  for_each_posting<WIDE>(v, ix, part_of_base(pos), key, policy, [&](Key mk, uint32_t idx) {
-    if ((((mk.lo ^ key.lo) & ~hole.lo) | ((mk.hi ^ key.hi) & ~hole.hi)) == 0) {
-      ++parents;
-      found = (int32_t)idx;
-    }
-    return false;
-  });
-  if (parents == 1) {
-    if (kind) *kind = 2;
-    return found;
-  }
-  return kMiss;
+  return lookup_token<WIDE>(v, ix, true, key, hole, part_of_base(pos), true, kind, policy);
 }
 
 // Decision for ONE window given its key, the number of bytes in it that

@@ -330,9 +330,9 @@ __device__ __forceinline__ int32_t try_position(const LibView& v, const IndexVie
   Key key;
   const uint32_t any = pack_window<NW, WIDE>(w, g.n_words, g.last_mask, key, x);
   if (debug & 8u) return (key.lo == 0x12345678u && any == 77u) ? 0 : kMiss;  // tuning: pack only, no lookups
-  if (any == 0) return lookup_clean<WIDE>(v, ix, g.with_perm, key, nullptr, policy);
-  if (!g.with_perm) return kMiss;
-  // bytes outside A,C,G,T: exactly one, and it is the wildcard -> its parents
+  // Bytes outside A,C,G,T: the window still matches if there is exactly one and it is the
+  // wildcard -> its parents.  Both kinds of window go through ONE lookup so
+  // that the lanes of a pass issue their directory loads together.
   int nbad = 0;
   uint32_t bad_word = 0, bad_flags = 0, bad_w = 0;
 #pragma unroll
@@ -345,11 +345,18 @@ __device__ __forceinline__ int32_t try_position(const LibView& v, const IndexVie
       bad_w = w[i];
     }
   }
-  if (nbad != 1) return kMiss;
-  const uint32_t byte = (uint32_t)(__ffs((int)bad_flags) - 8) >> 3;  // flags sit at bit 7 of their byte
-  if (((bad_w >> (8 * byte)) & 0xFFu) != g.wild_byte) return kMiss;
+  const uint32_t byte = ((uint32_t)(__ffs((int)bad_flags) - 8) >> 3) & 3u;  // flags sit at bit 7 of their byte
+  const bool wild = g.with_perm && nbad == 1 && ((bad_w >> (8 * byte)) & 0xFFu) == g.wild_byte;
   // stored base position; the keys of the reverse index are in stored order too
-  return lookup_wild<WIDE>(v, ix, key, 4 * bad_word + byte, nullptr, policy);
+  const uint32_t pos = wild ? 4 * bad_word + byte : 0u;
+  Key hole{0u, 0u};
+  if (wild) {
+    hole = base_field(pos, WIDE);
+    key.lo &= ~hole.lo;
+    key.hi &= ~hole.hi;
+  }
+  return lookup_token<WIDE>(v, ix, g.with_perm, key, hole, wild ? part_of_base(pos) : -1, any == 0 || wild, nullptr,
+                            policy);
 }
 
 // NW = words that hold the k window bytes: 5 (k = 17..20, the common guide lengths) or 8.
@@ -711,6 +718,8 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
     Kernel kernel = kernels[c->lib->wide ? 2 : (nw5 ? 0 : 1)][mode];
     const size_t smem = stream_smem_bytes(cfg, stage_bytes, queue_bytes);
     SGC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (const int carve = env_int("SGC_CARVEOUT", -1); carve >= 0)  // tuning: shared-memory share of the L1, percent
+      SGC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     uint64_t grid = (uint64_t)c->lib->sm_count * cfg.ctas_per_sm;  // persistent: every CTA resident
     const uint64_t ctas_needed = (n_wtiles + cfg.warps - 1) / cfg.warps;
     if (grid > ctas_needed) grid = ctas_needed;

@@ -21,10 +21,11 @@ sample.fill_device(0, N_READS, d.data_ptr())
 torch.cuda.synchronize()
 counter = sg.Counter(library, permuter, sg.Offset.Forward(5))
 configs = [tuple(int(x) for x in c.split(",")) for c in sys.argv[1:]] or [(12, 2, 3)]
-configs = [c if len(c) == 4 else c + (0,) for c in configs]
+configs = [c + (0, -1)[len(c) - 3:] for c in configs]  # warps,ctas,stages[,debug[,carveout %]]
 ref = None
-for warps, ctas, stages, debug in configs:
-    os.environ.update(SGC_WARPS=str(warps), SGC_CTAS=str(ctas), SGC_STAGES=str(stages), SGC_DEBUG=str(debug))
+for warps, ctas, stages, debug, carve in configs:
+    os.environ.update(SGC_WARPS=str(warps), SGC_CTAS=str(ctas), SGC_STAGES=str(stages), SGC_DEBUG=str(debug),
+                      SGC_CARVEOUT=str(carve))
     for _ in range(3):
         counter.submit_device(d.data_ptr(), N_READS * 76, N_READS, 76, 75)
     torch.cuda.synchronize()
@@ -42,6 +43,6 @@ for warps, ctas, stages, debug in configs:
     if ref is None and debug == 0:
         ref = counts.copy()
     ok = ref is not None and (counts == ref).all()
-    print(f"warps={warps} ctas={ctas} stages={stages} debug={debug} grid={li.grid} smem={li.smem_bytes} "
+    print(f"warps={warps} ctas={ctas} stages={stages} debug={debug} carve={carve} grid={li.grid} smem={li.smem_bytes} "
           f"{ms:.3f} ms  {N_READS/ms/1e6:.2f} Greads/s  {N_READS*76/ms/1e6:.0f} GB/s "
           f"frac={N_READS*76/ms/1e6/6547.2:.3f} matched={matched//iters} same={ok}", flush=True)
