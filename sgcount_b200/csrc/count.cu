@@ -422,15 +422,24 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   uint32_t cur_tile = tiles_sm, cur_bar = bars_sm;  // stage s of the ring
 
   // A tile is handled in two steps one loop iteration apart, so that the front-table sector of
-  // tile j+1 travels L2 -> L1 while tile j is being finished (and its parked reads drained):
-  //   step A  wait for the tile, lift the span, hand the buffer back, pack the Centered window,
-  //           PREFETCH the front bucket into L1; carried to step B: span words, key, validity
-  //   step B  load the bucket (an L1 hit), compare, count or park
+  // tile j+1 travels from L2 while tile j's parked reads are drained and tile j+2 is lifted:
+  //   step A  wait for the tile, lift the span, hand the buffer back, pack the Centered window;
+  //           carried to step B: span words, key, validity
+  //   fetch   the front bucket of that window (issued right after step B of the tile before)
+  //   step B  compare the bucket, count or park
   struct Pending {
     uint32_t S[NW + 1];  // span words from one byte before the Centered window (lane independent)
     Key key;
     uint32_t any;  // non-zero: some window byte is not A/C/G/T
-    uint64_t b[4];  // the front bucket, in flight between the two steps
+  };
+  // The front bucket of the tile step B handles next, in flight.  ONE register set: step B
+  // consumes it and the load for the following tile is issued right behind, so it flies through
+  // the drain and the next step A.  (Carrying it inside Pending made the `current = next` copy at
+  // the loop tail wait for a load that had just been issued.)
+  uint64_t bucket[4];
+  auto fetch_bucket = [&](const Pending& pd) {
+    if (pd.any == 0 && !(MODE == 2 && (debug & 2u)))
+      load_bucket(front + (size_t)(front_hash(pd.key.lo, pd.key.hi) >> front_shift) * 4, bucket, table_policy);
   };
   // a read is settled: its assignment (tests), its guide's counter
   auto settle = [&](int32_t hit, uint32_t ridx) {
@@ -477,8 +486,6 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
 #pragma unroll
     for (int i = 0; i < NW; ++i) w[i] = __funnelshift_r(pd.S[i], pd.S[i + 1], g.shift_bits[0]);
     pd.any = pack_window<NW, WIDE>(w, g.n_words, g.last_mask, pd.key, x);
-    if (pd.any == 0 && !(MODE == 2 && (debug & 2u)))
-      load_bucket(front + (size_t)(front_hash(pd.key.lo, pd.key.hi) >> front_shift) * 4, pd.b, table_policy);
   };
   auto step_b = [&](const Pending& pd, uint32_t read_idx) {
     // park = position to resume at (0 Centered, 1 Plus), or -1 when the read is settled
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
         flagged = false;
         hit = (int32_t)((pd.key.lo ^ pd.key.hi) % p.n_guides);
       } else {
-        const uint64_t(&b)[4] = pd.b;
+        const uint64_t(&b)[4] = bucket;
         if (!WIDE) {
           // the slot whose lo word matches (the build keeps them distinct within a bucket)
           uint32_t sel = 0;
@@ -575,12 +582,16 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   uint32_t t = gwarp;
   Pending cur;
   bool have_cur = t < n_wtiles;
-  if (have_cur) step_a(cur);
+  if (have_cur) {
+    step_a(cur);
+    fetch_bucket(cur);
+  }
   while (have_cur) {
     Pending nxt;
     const bool have_nxt = t + gwarps < n_wtiles;
     if (have_nxt) step_a(nxt);
     step_b(cur, read_idx);
+    if (have_nxt) fetch_bucket(nxt);
     drain(false);
     cur = nxt;
     have_cur = have_nxt;
