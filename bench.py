@@ -139,8 +139,10 @@ def fastq_leg(lib_arr, n_reads: int, with_oracle: bool):
         res = {"value": timing["reads"] / timing["count_s"], "unit": "reads/s", "reads": timing["reads"],
                "count_s": timing["count_s"], "process_wall_s": wall, "gz_bytes": gz_bytes,
                "ingest_threads": timing["ingest_threads"],
-               "what": "sgcount CLI on a multi-member gzip FASTQ (1 Mi reads per member): parallel inflate, parse, "
-                       "H2D, count kernel, D2H; table build and process start-up are outside count_s"}
+               "members": (n_reads + (1 << 20) - 1) >> 20,
+               "what": "sgcount CLI on a multi-member gzip FASTQ (1 Mi reads per member, so at most `members` inflate "
+                       "threads have work): member-parallel inflate + record framing, H2D, count kernel, D2H; table "
+                       "build and process start-up are outside count_s"}
         if with_oracle:
             from oracle import oracle as orc
 
@@ -541,7 +543,7 @@ def main():
     ap.add_argument("--reads-per-gpu", type=int, default=READS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fastq-reads", type=int, default=4_000_000,
+    ap.add_argument("--fastq-reads", type=int, default=16 << 20,
                     help="reads of the gzip-FASTQ end-to-end leg through the C++ host (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

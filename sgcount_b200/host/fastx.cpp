@@ -10,6 +10,31 @@
 
 namespace sgh {
 
+// ---- big buffers ----------------------------------------------------------------------------
+namespace {
+constexpr size_t kBigThreshold = 4u << 20, kHugePage = 2u << 20;
+}
+void* big_alloc_bytes(size_t bytes) {
+  if (bytes < kBigThreshold) {
+    void* p = malloc(bytes ? bytes : 1);
+    if (!p) throw std::bad_alloc();
+    return p;
+  }
+  const size_t len = (bytes + kHugePage - 1) / kHugePage * kHugePage;
+  void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) throw std::bad_alloc();
+#ifdef MADV_HUGEPAGE
+  madvise(p, len, MADV_HUGEPAGE);
+#endif
+  return p;
+}
+void big_free_bytes(void* p, size_t bytes) {
+  if (bytes < kBigThreshold)
+    free(p);
+  else
+    munmap(p, (bytes + kHugePage - 1) / kHugePage * kHugePage);
+}
+
 namespace {
 
 bool ends_with(const std::string& s, const char* suffix) {
@@ -47,7 +72,8 @@ class PlainSource : public ByteSource {
 // multi-member decoder (flate2's MultiGzDecoder in the reference) produces.
 class GzSource : public ByteSource {
  public:
-  GzSource(const std::string& path, unsigned threads) {
+  // frame_records: the workers also frame the records of their member (SeqBlockReader)
+  GzSource(const std::string& path, unsigned threads, bool frame_records = false) {
     fd_ = open(path.c_str(), O_RDONLY);
     if (fd_ < 0) throw FastxError("cannot open " + path);
     struct stat st;
@@ -62,6 +88,7 @@ class GzSource : public ByteSource {
     threads_ = std::max(1u, threads);
     if (threads_ > 1 && size_ > (1u << 16)) find_candidates();
     if (cand_.size() <= 1) threads_ = 1;  // a single member: nothing to run in parallel
+    if (threads_ > 1 && frame_records) frame_lpr_ = peek_lines_per_record();
     if (threads_ > 1) {
       jobs_.resize(cand_.size());
       window_ = 2 * threads_;
@@ -81,6 +108,40 @@ class GzSource : public ByteSource {
   }
 
   bool read_more(std::vector<char>& out) override {
+    Bytes data;
+    bool framed;
+    SeqBlock block;
+    SeqParser::State state;
+    if (!next_member(data, framed, block, state)) return false;
+    if (!data.empty()) {
+      const size_t at = out.size();
+      out.resize(at + data.size());
+      memcpy(out.data() + at, data.data(), data.size());
+    }
+    recycle(std::move(data), SeqBlock());
+    if (out.empty()) return read_more(out);  // an empty member
+    return true;
+  }
+
+  // Hands buffers back to the inflate threads (their pages stay mapped and faulted).
+  void recycle(Bytes&& raw, SeqBlock&& block) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (raw.capacity() && free_raw_.size() < window_ + 2) {
+      raw.clear();
+      free_raw_.push_back(std::move(raw));
+    }
+    if (block.lines.capacity() && free_blocks_.size() < window_ + 2) {
+      block.clear();
+      free_blocks_.push_back(std::move(block));
+    }
+  }
+
+  // The next member (member-parallel mode) or the next chunk (sequential mode) of decompressed
+  // bytes, possibly none.  `framed`: the worker framed the member's records from a clean state
+  // into `block`, ending in `end_state`.  Returns false at the end of the input.
+  bool next_member(Bytes& raw, bool& framed, SeqBlock& block, SeqParser::State& end_state) {
+    raw.clear();  // keeps its pages: the sequential path refills it, the parallel path recycles it
+    framed = false;
     if (threads_ > 1 && !sequential_) {
       if (pos_ >= size_) return false;
       // the candidate that starts exactly at pos_
@@ -93,18 +154,14 @@ class GzSource : public ByteSource {
         cv_done_.wait(lk, [&] { return jobs_[j].done; });
         Job& job = jobs_[j];
         if (job.ok) {
-          std::vector<char> data = std::move(job.out);
-          const size_t end = job.end;
-          lk.unlock();
-          if (out.empty()) {
-            out.swap(data);
-          } else if (!data.empty()) {
-            const size_t at = out.size();
-            out.resize(at + data.size());
-            memcpy(out.data() + at, data.data(), data.size());
+          if (raw.capacity() && free_raw_.size() < window_ + 2) free_raw_.push_back(std::move(raw));
+          raw = std::move(job.out);
+          framed = job.framed;
+          if (framed) {
+            block = std::move(job.block);
+            end_state = std::move(job.end_state);
           }
-          pos_ = end;
-          if (data.empty() && out.empty()) return read_more(out);  // an empty member
+          pos_ = job.end;
           return true;
         }
       }
@@ -116,15 +173,36 @@ class GzSource : public ByteSource {
       }
       cv_work_.notify_all();
     }
-    return read_sequential(out);
+    return read_sequential(raw);
   }
 
  private:
   struct Job {
-    std::vector<char> out;
+    Bytes out;
     size_t end = 0;
     bool ok = false, done = false, taken = false;
+    // record framing of the member, assuming it starts on a record boundary
+    bool framed = false;
+    SeqBlock block;
+    SeqParser::State end_state;
   };
+
+  // '>' -> 2, '@' -> 4, anything else (or an empty first member) -> 0: no framing by the workers,
+  // the consumer's own parser reports what is wrong
+  int peek_lines_per_record() {
+    z_stream zs{};
+    if (inflateInit2(&zs, 15 + 16) != Z_OK) return 0;
+    unsigned char first = 0;
+    zs.next_in = const_cast<unsigned char*>(data_);
+    zs.avail_in = (uInt)std::min<size_t>(size_, 1u << 16);
+    zs.next_out = &first;
+    zs.avail_out = 1;
+    inflate(&zs, Z_NO_FLUSH);
+    const bool got = zs.avail_out == 0;
+    inflateEnd(&zs);
+    return !got ? 0 : (first == '>' ? 2 : (first == '@' ? 4 : 0));
+  }
+
 
   void find_candidates() {
     const unsigned char* p = data_;
@@ -139,7 +217,7 @@ class GzSource : public ByteSource {
   }
 
   // inflate ONE member starting at `from`; false if the bytes there are not a complete member
-  bool inflate_member(size_t from, std::vector<char>& out, size_t& end) {
+  bool inflate_member(size_t from, Bytes& out, size_t& end) {
     z_stream zs{};
     if (inflateInit2(&zs, 15 + 16) != Z_OK) return false;
     zs.next_in = const_cast<unsigned char*>(data_ + from);
@@ -177,7 +255,19 @@ class GzSource : public ByteSource {
         if (stop_) return;
         j = next_job_++;
       }
-      std::vector<char> out;
+      Bytes out;
+      SeqBlock block;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!free_raw_.empty()) {
+          out = std::move(free_raw_.back());
+          free_raw_.pop_back();
+        }
+        if (frame_lpr_ && !free_blocks_.empty()) {
+          block = std::move(free_blocks_.back());
+          free_blocks_.pop_back();
+        }
+      }
       // size hint: ISIZE of a member that ends where the next candidate starts
       const size_t nxt = j + 1 < cand_.size() ? cand_[j + 1] : size_;
       if (nxt >= cand_[j] + 18) {
@@ -187,8 +277,19 @@ class GzSource : public ByteSource {
       }
       size_t end = 0;
       const bool ok = inflate_member(cand_[j], out, end);
+      SeqParser framer;
+      if (ok && frame_lpr_) {
+        framer.st.lines_per_record = frame_lpr_;
+        block.lines.reserve(out.size() / 2);
+        framer.feed(out.data(), out.size(), block);
+      }
       {
         std::lock_guard<std::mutex> lk(mu_);
+        if (ok && frame_lpr_) {
+          jobs_[j].framed = true;
+          jobs_[j].block = std::move(block);
+          jobs_[j].end_state = std::move(framer.st);
+        }
         jobs_[j].out = std::move(out);
         jobs_[j].end = end;
         jobs_[j].ok = ok;
@@ -198,7 +299,7 @@ class GzSource : public ByteSource {
     }
   }
 
-  bool read_sequential(std::vector<char>& out) {
+  bool read_sequential(Bytes& out) {
     if (!seq_init_) {
       if (inflateInit2(&seq_, 15 + 16) != Z_OK) throw FastxError("inflateInit2 failed");
       seq_init_ = true;
@@ -240,6 +341,9 @@ class GzSource : public ByteSource {
   std::condition_variable cv_work_, cv_done_;
   size_t next_job_ = 0, consumer_at_ = 0, window_ = 2;
   bool stop_ = false, sequential_ = false;
+  int frame_lpr_ = 0;  // lines per record the workers frame with; 0 = they do not
+  std::vector<Bytes> free_raw_;        // recycled buffers (under mu_)
+  std::vector<SeqBlock> free_blocks_;
   z_stream seq_{};
   bool seq_init_ = false;
 };
@@ -279,6 +383,117 @@ bool LineSource::next(const char*& begin, size_t& len) {
     pos_ = buf_.size();
     return true;
   }
+}
+
+// ---- packed sequence lines ---------------------------------------------------------------------
+void SeqBlock::push(const char* seq, size_t l) {
+  if (l >= 0xFFFFFFFFull) throw FastxError("a sequence line of 4 GiB or more");
+  if (n == 0)
+    first_len = (uint32_t)l;
+  else
+    uniform &= l == first_len;
+  lines.insert(lines.end(), seq, seq + l);
+  lines.push_back('\n');
+  len.push_back((uint32_t)l);
+  ++n;
+}
+
+void SeqParser::line(const char* p, size_t len, SeqBlock& out) {
+  if (st.lines_per_record == 0) {
+    if (len == 0) throw FastxError("empty first line: not FASTA/FASTQ");
+    if (p[0] == '>')
+      st.lines_per_record = 2;
+    else if (p[0] == '@')
+      st.lines_per_record = 4;
+    else
+      throw FastxError("first byte is neither '>' nor '@'");
+  }
+  if (st.phase == 1) out.push(p, len);
+  if (++st.phase == st.lines_per_record) st.phase = 0;
+}
+
+void SeqParser::feed(const char* data, size_t len, SeqBlock& out) {
+  const char* p = data;
+  const char* const end = data + len;
+  if (!st.carry.empty()) {  // finish the line the previous chunk left open
+    const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+    if (!nl) {
+      st.carry.append(p, end);
+      return;
+    }
+    st.carry.append(p, nl);
+    line(st.carry.data(), st.carry.size(), out);
+    st.carry.clear();
+    p = nl + 1;
+  }
+  while (p < end) {
+    const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+    if (!nl) {
+      st.carry.assign(p, end);
+      return;
+    }
+    line(p, (size_t)(nl - p), out);
+    p = nl + 1;
+  }
+}
+
+void SeqParser::finish(SeqBlock& out) {
+  if (!st.carry.empty()) {  // last line without a newline
+    line(st.carry.data(), st.carry.size(), out);
+    st.carry.clear();
+  }
+  if (st.phase == 1) throw FastxError("truncated record: header without a sequence line");
+  if (st.phase != 0) throw FastxError("truncated FASTQ record");
+}
+
+struct SeqBlockReader::Impl {
+  std::unique_ptr<GzSource> gz;
+  std::unique_ptr<ByteSource> plain;
+  SeqParser parser;
+  Bytes raw;                  // gzip: the member / chunk being framed
+  std::vector<char> raw_plain;
+  bool eof = false;
+};
+
+SeqBlockReader::SeqBlockReader(const std::string& path, unsigned inflate_threads) : impl_(new Impl()) {
+  if (ends_with(path, ".gz"))
+    impl_->gz.reset(new GzSource(path, inflate_threads, /*frame_records=*/true));
+  else
+    impl_->plain.reset(new PlainSource(path));
+}
+SeqBlockReader::~SeqBlockReader() = default;
+
+bool SeqBlockReader::next(SeqBlock& out) {
+  Impl& m = *impl_;
+  out.clear();
+  if (m.eof) return false;
+  bool more;
+  if (m.gz) {
+    bool framed = false;
+    SeqBlock block;
+    SeqParser::State end_state;
+    more = m.gz->next_member(m.raw, framed, block, end_state);
+    if (more) {
+      // the worker framed this member from a clean state: valid iff that is where we are
+      const SeqParser::State& st = m.parser.st;
+      if (framed && st.clean() && (st.lines_per_record == 0 || st.lines_per_record == end_state.lines_per_record)) {
+        std::swap(out, block);  // the caller's previous block goes back to the inflate threads
+        m.parser.st = std::move(end_state);
+      } else {
+        m.parser.feed(m.raw.data(), m.raw.size(), out);
+      }
+      m.gz->recycle(Bytes(), std::move(block));
+    }
+  } else {
+    m.raw_plain.clear();
+    more = m.plain->read_more(m.raw_plain);
+    if (more) m.parser.feed(m.raw_plain.data(), m.raw_plain.size(), out);
+  }
+  if (!more) {
+    m.parser.finish(out);
+    m.eof = true;
+  }
+  return true;
 }
 
 FastxReader::FastxReader(const std::string& path, unsigned inflate_threads) : src_(path, inflate_threads) {}

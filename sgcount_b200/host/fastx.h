@@ -17,9 +17,11 @@
 #include <deque>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 namespace sgh {
@@ -52,6 +54,92 @@ class LineSource {
   std::vector<char> buf_;
   size_t pos_ = 0;
   bool eof_ = false;
+};
+
+// Allocator of the big ingest buffers (a member's decompressed bytes, its sequence lines):
+// large blocks come from mmap with MADV_HUGEPAGE, so that sixteen inflate threads writing fresh
+// buffers do not serialise on 4 KiB page faults, and elements are default-initialised (resize()
+// does not zero memory that inflate is about to overwrite).
+template <typename T>
+struct BigAlloc {
+  using value_type = T;
+  BigAlloc() = default;
+  template <typename U>
+  BigAlloc(const BigAlloc<U>&) {}
+  T* allocate(size_t n);
+  void deallocate(T* p, size_t n);
+  template <typename U, typename... Args>
+  void construct(U* p, Args&&... args) {
+    if constexpr (sizeof...(Args) == 0)
+      ::new (static_cast<void*>(p)) U;
+    else
+      ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+  }
+  template <typename U>
+  bool operator==(const BigAlloc<U>&) const { return true; }
+  template <typename U>
+  bool operator!=(const BigAlloc<U>&) const { return false; }
+};
+void* big_alloc_bytes(size_t bytes);
+void big_free_bytes(void* p, size_t bytes);
+template <typename T>
+T* BigAlloc<T>::allocate(size_t n) { return static_cast<T*>(big_alloc_bytes(n * sizeof(T))); }
+template <typename T>
+void BigAlloc<T>::deallocate(T* p, size_t n) { big_free_bytes(p, n * sizeof(T)); }
+using Bytes = std::vector<char, BigAlloc<char>>;
+
+// Sequence lines of a run of whole records, packed the way the count kernels take them: every
+// sequence followed by '\n'.
+struct SeqBlock {
+  Bytes lines;
+  std::vector<uint32_t> len;  // length of every sequence (without the '\n')
+  uint64_t n = 0;
+  bool uniform = true;  // every sequence is as long as the first
+  uint32_t first_len = 0;
+  void clear() {
+    lines.clear();
+    len.clear();
+    n = 0;
+    uniform = true;
+    first_len = 0;
+  }
+  void push(const char* seq, size_t l);
+};
+
+// Incremental record framing: bytes in (cut anywhere), sequence lines out.  Same framing as
+// FastxReader: '>' = 2-line FASTA, '@' = 4-line FASTQ, sniffed from the first byte.
+class SeqParser {
+ public:
+  struct State {
+    int lines_per_record = 0;  // 0 = not sniffed yet
+    int phase = 0;             // line of the record the next line is
+    std::string carry;         // bytes of a line whose '\n' has not arrived
+    bool clean() const { return phase == 0 && carry.empty(); }
+  };
+  State st;
+  void feed(const char* data, size_t len, SeqBlock& out);
+  // end of input: a last line without '\n' counts; throws FastxError on a truncated record
+  void finish(SeqBlock& out);
+
+ private:
+  void line(const char* p, size_t len, SeqBlock& out);
+};
+
+// The hot ingest path of count_sample (count.rs:15-45 hands `Counter::new` a record iterator;
+// here the kernels want packed sequence lines): blocks of sequence lines in file order.  For a
+// multi-member gzip file every inflate thread also frames its member's records, assuming the
+// member starts on a record boundary; the consumer checks that assumption against the real
+// framing state and re-frames the member's bytes itself when it does not hold.
+class SeqBlockReader {
+ public:
+  explicit SeqBlockReader(const std::string& path, unsigned inflate_threads = 1);
+  ~SeqBlockReader();
+  // Next block (possibly of zero records); false at the end of the input.
+  bool next(SeqBlock& out);
+
+ private:
+  struct Impl;
+  std::unique_ptr<Impl> impl_;
 };
 
 class FastxReader {

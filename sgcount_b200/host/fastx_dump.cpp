@@ -1,4 +1,4 @@
-// fastx_dump <path> <inflate threads> [seq] — record count and FNV-1a of ids+sequences as the
+// fastx_dump <path> <inflate threads> [seq|blocks] — record count and FNV-1a of ids+sequences as the
 // host reader yields them (test helper for tests/test_host_reader.py).
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +9,42 @@
 int main(int argc, char** argv) {
   if (argc < 3) return 2;
   try {
+    if (argc > 3 && (!strcmp(argv[3], "blockcount") || !strcmp(argv[3], "seqcount"))) {  // timing: framing only
+      unsigned long long n = 0, bytes = 0;
+      if (!strcmp(argv[3], "blockcount")) {
+        sgh::SeqBlockReader br(argv[1], (unsigned)atoi(argv[2]));
+        sgh::SeqBlock b;
+        while (br.next(b)) n += b.n, bytes += b.lines.size();
+      } else {
+        sgh::FastxReader r(argv[1], (unsigned)atoi(argv[2]));
+        const char* seq;
+        size_t sl;
+        while (r.next_seq(seq, sl)) ++n, bytes += sl + 1;
+      }
+      printf("%llu %llu\n", n, bytes);
+      return 0;
+    }
+    if (argc > 3 && !strcmp(argv[3], "blocks")) {  // the packed-sequence-line path of count_sample
+      sgh::SeqBlockReader br(argv[1], (unsigned)atoi(argv[2]));
+      sgh::SeqBlock b;
+      unsigned long long n = 0, h = 1469598103934665603ull;
+      while (br.next(b)) {
+        size_t at = 0;
+        bool uniform = true;
+        for (unsigned long long i = 0; i < b.n; ++i) {
+          const size_t l = b.len[i];
+          uniform &= l == b.first_len;
+          for (size_t j = 0; j < l; ++j) h = (h ^ (unsigned char)b.lines[at + j]) * 1099511628211ull;
+          if (b.lines[at + l] != '\n') return 3;
+          h = (h ^ 0xFFu) * 1099511628211ull;
+          at += l + 1;
+        }
+        if (at != b.lines.size() || b.len.size() != b.n || uniform != b.uniform) return 3;
+        n += b.n;
+      }
+      printf("%llu %llx\n", n, h);
+      return 0;
+    }
     sgh::FastxReader r(argv[1], (unsigned)atoi(argv[2]));
     const bool seq_only = argc > 3 && !strcmp(argv[3], "seq");
     const char *id = nullptr, *seq;

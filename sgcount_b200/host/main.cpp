@@ -200,11 +200,11 @@ std::unordered_map<std::string, std::string> load_genemap(const std::string& pat
   return map;
 }
 
-// Sequence lines of a run of records, as the kernels take them.
+// Sequence lines of a run of records, as the kernels take them (pinned host memory).
 struct Batch {
   uint8_t* lines = nullptr;  // pinned
   size_t cap = 0, used = 0;
-  std::vector<uint32_t> off;  // n + 1 line starts
+  std::vector<uint32_t> off;  // n + 1 line starts; kept only once the batch is not uniform
   bool uniform = true;        // every read as long as the first
   size_t first_len = 0;
   uint64_t n = 0;
@@ -213,17 +213,47 @@ struct Batch {
     used = 0;
     n = 0;
     uniform = true;
-    off.assign(1, 0u);
+    off.clear();
   }
+  bool fits(size_t bytes) const { return used + bytes <= cap && used + bytes < (1ull << 32); }
   bool push(const char* seq, size_t len) {
-    if (used + len + 1 > cap || used + len + 1 >= (1ull << 32)) return false;
+    if (!fits(len + 1)) return false;
     if (n == 0) first_len = len;
-    uniform &= len == first_len;
+    if (uniform && len != first_len) {  // from here on the kernels need the line starts
+      uniform = false;
+      off.resize(n + 1);
+      for (uint64_t i = 0; i <= n; ++i) off[i] = (uint32_t)(i * (first_len + 1));
+    }
     memcpy(lines + used, seq, len);
     lines[used + len] = '\n';
     used += len + 1;
-    off.push_back((uint32_t)used);
+    if (!uniform) off.push_back((uint32_t)used);
     ++n;
+    return true;
+  }
+  // Records [rec, blk.n) of a block, as many as fit; `byte` is where record `rec` starts in the
+  // block.  Returns false when the batch is full before the block is used up.
+  bool append(const sgh::SeqBlock& blk, uint64_t& rec, size_t& byte) {
+    while (rec < blk.n) {
+      if (uniform && blk.uniform && (n == 0 || first_len == blk.first_len)) {
+        const size_t stride = (size_t)blk.first_len + 1;
+        size_t room = cap - used;
+        if (used + room >= (1ull << 32)) room = (1ull << 32) - 1 - used;
+        const uint64_t fit = std::min<uint64_t>(blk.n - rec, room / stride);
+        if (fit == 0) return false;
+        memcpy(lines + used, blk.lines.data() + byte, fit * stride);
+        first_len = blk.first_len;
+        used += fit * stride;
+        n += fit;
+        rec += fit;
+        byte += fit * stride;
+      } else {
+        const size_t l = blk.len[rec];
+        if (!push(blk.lines.data() + byte, l)) return false;
+        ++rec;
+        byte += l + 1;
+      }
+    }
     return true;
   }
 };
@@ -290,20 +320,21 @@ SampleResult count_sample(const sgc_library* lib, uint32_t n_guides, const std::
     b.cap = cap;
     b.reset();
   }
-  sgh::FastxReader reader(path, ingest_threads);
-  const char* seq;
-  size_t seq_len;
+  // blocks of packed sequence lines, framed by the inflate threads (fastx.h)
+  sgh::SeqBlockReader reader(path, ingest_threads);
+  sgh::SeqBlock blk;
   int cur = 0;
   bool other_in_flight = false;
-  while (reader.next_seq(seq, seq_len)) {
-    if (seq_len + 1 > cap) fail("a sequence line longer than %zu bytes", cap);
-    if (!g.b[cur].push(seq, seq_len)) {
+  while (reader.next(blk)) {
+    uint64_t rec = 0;
+    size_t byte = 0;
+    while (!g.b[cur].append(blk, rec, byte)) {
+      if (g.b[cur].n == 0) fail("a sequence line longer than %zu bytes", cap);
       submit(c, g.b[cur]);
       cur ^= 1;
       if (other_in_flight) check(sgc_counter_sync(c));  // the buffer we are about to refill has been consumed
       other_in_flight = true;
       g.b[cur].reset();
-      g.b[cur].push(seq, seq_len);
     }
   }
   submit(c, g.b[cur]);

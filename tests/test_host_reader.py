@@ -92,3 +92,50 @@ def test_malformed_inputs_are_errors(tmp_path):
     assert dump(tmp_path / "cut2.fq.gz", 4)[0] == 1
     (tmp_path / "notgz.fq.gz").write_bytes(b"@r\nACGT\n+\nIIII\n")
     assert dump(tmp_path / "notgz.fq.gz", 2)[0] == 1
+
+
+# ---- SeqBlockReader: the packed-sequence-line path of count_sample ----------------------------
+@pytest.mark.parametrize("fastq", [True, False])
+def test_blocks_agree_with_record_reader(tmp_path, fastq):
+    """Members cut inside records (the workers' record-boundary assumption fails and the consumer
+    re-frames), members cut ON record boundaries (the workers' blocks are used as they are), an
+    empty member, plain and single-member input: always the sequences of the record reader."""
+    recs, text = make_records(30000, 11 + fastq, fastq)
+    want = fnv(recs, with_ids=False)
+    rng = random.Random(2)
+    cuts = sorted(rng.sample(range(1, len(text)), 9))
+    inside = [text[a:b] for a, b in zip([0] + cuts, cuts + [len(text)])]
+    starts = [m.start() for m in __import__("re").finditer(rb"^[@>]r\d+ extra$", text, flags=__import__("re").M)]
+    bounds = sorted(rng.sample(starts[1:], 9))
+    aligned = [text[a:b] for a, b in zip([0] + bounds, bounds + [len(text)])]
+    mixed = aligned[:4] + [aligned[4][:50], aligned[4][50:]] + aligned[5:]  # one boundary inside a record
+    files = {"plain.fx": text, "single.fx.gz": gzip.compress(text, 1),
+             "inside.fx.gz": b"".join(gzip.compress(m, 1) for m in inside),
+             "aligned.fx.gz": b"".join(gzip.compress(m, 1) for m in aligned),
+             "mixed.fx.gz": b"".join(gzip.compress(m, 1) for m in mixed),
+             "with_empty_member.fx.gz": b"".join(gzip.compress(m, 1) for m in aligned[:3] + [b""] + aligned[3:])}
+    for name, blob in files.items():
+        (tmp_path / name).write_bytes(blob)
+        for threads in (1, 3, 16):
+            rc, out, err = dump(tmp_path / name, threads, "blocks")
+            assert (rc, out) == (0, want), (name, threads, err)
+
+
+def test_blocks_edge_cases(tmp_path):
+    (tmp_path / "a.fa").write_bytes(b">x\nACGT\n>y\nGG")
+    assert dump(tmp_path / "a.fa", 1, "blocks")[1] == fnv([(b"x", b"ACGT"), (b"y", b"GG")], with_ids=False)
+    (tmp_path / "empty.fq").write_bytes(b"")
+    assert dump(tmp_path / "empty.fq", 1, "blocks")[:2] == (0, fnv([]))
+    # last member ends without a newline, several members, several threads
+    big = b"@r\nACGT\n+\nIIII\n" * 6000
+    blob = gzip.compress(big, 1) + gzip.compress(big, 1) + gzip.compress(b"@z\nAC\n+\nII", 1)
+    (tmp_path / "tail.fq.gz").write_bytes(blob)
+    assert dump(tmp_path / "tail.fq.gz", 4, "blocks")[1] == fnv([(b"", b"ACGT")] * 12000 + [(b"", b"AC")], with_ids=False)
+    (tmp_path / "bad.fq").write_bytes(b"ACGT\nACGT\n")
+    assert dump(tmp_path / "bad.fq", 1, "blocks")[0] == 1
+    (tmp_path / "trunc.fq").write_bytes(b"@r\nACGT\n+\n")
+    assert "truncated" in dump(tmp_path / "trunc.fq", 1, "blocks")[2]
+    (tmp_path / "trunc.fq.gz").write_bytes(gzip.compress(big, 1) + gzip.compress(big + b"@r\nACGT\n", 1))
+    assert "truncated" in dump(tmp_path / "trunc.fq.gz", 4, "blocks")[2]
+    (tmp_path / "cut.fq.gz").write_bytes(blob[:len(blob) // 3])
+    assert dump(tmp_path / "cut.fq.gz", 4, "blocks")[0] == 1
