@@ -117,3 +117,57 @@ def test_config4_gene_map_and_config5_read_sharding(tmp_path):
     total = total.cpu().numpy()
     assert np.array_equal(total[:-2].astype(np.uint64), counters[0].counts_by_index())
     assert (int(total[-2]), int(total[-1])) == (counters[0].total_reads(), counters[0].matched_reads())
+
+
+def test_config2_full_size_properties():
+    """Config 2 at its FULL size (77 441 guides, 50 M x 75 bp reads generated in HBM): the oracle
+    cannot finish 50 M reads in a test, so the whole-sample table is pinned through
+    size-independent properties: totals, additivity over read shards (each shard small enough to
+    be oracle-checked), and a second pass doubling every count."""
+    import torch
+
+    import sgcount_b200 as sg
+
+    seed, n_guides, n_reads, stride = 0xB2000002, 77441, 50_000_000, 76
+    arr = synth.make_library(seed, n_guides, 20)
+    library = sg.Library([arr[i].tobytes() for i in range(n_guides)], [b"lib.%d" % i for i in range(n_guides)])
+    permuter = sg.Permuter.new(library)
+    sample = synth.Sample(seed, 0, arr, 75, 5, False)
+    d = torch.empty(n_reads * stride + 256, dtype=torch.uint8, device="cuda")
+    sample.fill_device(0, n_reads, d.data_ptr())
+    torch.cuda.synchronize()
+
+    whole = sg.Counter(library, permuter, sg.Offset.Forward(5))
+    whole.submit_device(d.data_ptr(), n_reads * stride, n_reads, stride, 75)
+    counts, total, matched = whole.finish()
+    assert total == n_reads and matched == int(counts.sum()) and 0.9 < matched / total < 0.97
+    assert whole.launch_info().kernel == 0  # the streaming kernel
+
+    # additivity: 25 shards of 2 M reads (ragged last tile boundaries included) sum to the whole;
+    # the first shard is checked against the oracle read by read
+    acc = np.zeros(n_guides, dtype=np.uint64)
+    acc_total = acc_matched = 0
+    bounds = [0] + [2_000_000 * i + 17 * i for i in range(1, 25)] + [n_reads]
+    for a, b in zip(bounds, bounds[1:]):
+        c = sg.Counter(library, permuter, sg.Offset.Forward(5))
+        c.submit_device(d.data_ptr() + a * stride, (b - a) * stride, b - a, stride, 75)
+        sc, st, sm = c.finish()
+        acc += sc.astype(np.uint64)
+        acc_total += st
+        acc_matched += sm
+        if a == 0:
+            lib_recs = orc.Records.from_bytes(b"".join(b">lib.%d\n%s\n" % (i, arr[i].tobytes()) for i in range(n_guides)))
+            olib = orc.Library.from_reader(lib_recs)
+            lines = sample.fill_host(0, b)
+            recs = orc.Records.from_lines(lines, np.arange(0, lines.nbytes + 1, stride, dtype=np.uint64))
+            oc = orc.Counter.new(recs, olib, orc.Permuter.new(olib), orc.Offset.Forward(5), None, True,
+                                 n_threads=os.cpu_count() or 4)
+            assert np.array_equal(sc.astype(np.uint64), oc.counts_by_index())
+            assert (st, sm) == (oc.total_reads(), oc.matched_reads())
+        del c
+    assert np.array_equal(acc, counts.astype(np.uint64)) and (acc_total, acc_matched) == (total, matched)
+
+    # a second pass over the same reads doubles every counter (no state leaks between launches)
+    whole.submit_device(d.data_ptr(), n_reads * stride, n_reads, stride, 75)
+    counts2, total2, matched2 = whole.finish()
+    assert np.array_equal(counts2, 2 * counts) and (total2, matched2) == (2 * total, 2 * matched)
