@@ -4,11 +4,37 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <vector>
+
 #include "fastx.h"
+#include "inflate.h"
 
 int main(int argc, char** argv) {
   if (argc < 3) return 2;
   try {
+    if (argc > 3 && !strcmp(argv[3], "inflate")) {  // the whole-member decoder alone, member after member
+      FILE* f = fopen(argv[1], "rb");
+      if (!f) return 2;
+      std::vector<unsigned char> data;
+      unsigned char buf[1 << 16];
+      for (size_t got; (got = fread(buf, 1, sizeof buf, f)) > 0;) data.insert(data.end(), buf, buf + got);
+      fclose(f);
+      size_t pos = 0;
+      unsigned long long total = 0, h = 1469598103934665603ull;
+      while (pos < data.size()) {
+        sgh::Bytes out;
+        size_t used = 0;
+        if (!sgh::gunzip_member(data.data() + pos, data.size() - pos, out, used)) {
+          printf("declined at %zu\n", pos);
+          return 4;
+        }
+        for (char c : out) h = (h ^ (unsigned char)c) * 1099511628211ull;
+        total += out.size();
+        pos += used;
+      }
+      printf("%llu %llx\n", total, h);
+      return 0;
+    }
     if (argc > 3 && (!strcmp(argv[3], "blockcount") || !strcmp(argv[3], "seqcount"))) {  // timing: framing only
       unsigned long long n = 0, bytes = 0;
       if (!strcmp(argv[3], "blockcount")) {
