@@ -200,6 +200,25 @@ std::unordered_map<std::string, std::string> load_genemap(const std::string& pat
   return map;
 }
 
+// The counting thread's copy of a member's sequence lines into pinned memory is the one serial
+// stretch of the ingest; big copies are cut in four.
+void copy_lines(uint8_t* dst, const char* src, size_t bytes) {
+  constexpr size_t kParallelFrom = 8u << 20;
+  constexpr int kParts = 4;
+  if (bytes < kParallelFrom) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t part = (bytes / kParts + 4095) & ~(size_t)4095;
+  std::thread helpers[kParts - 1];
+  for (int i = 1; i < kParts; ++i) {
+    const size_t at = std::min(bytes, part * i), n = std::min(bytes - at, part);
+    helpers[i - 1] = std::thread([=] { memcpy(dst + at, src + at, n); });
+  }
+  memcpy(dst, src, std::min(bytes, part));
+  for (auto& t : helpers) t.join();
+}
+
 // Sequence lines of a run of records, as the kernels take them (pinned host memory).
 struct Batch {
   uint8_t* lines = nullptr;  // pinned
@@ -241,7 +260,7 @@ struct Batch {
         if (used + room >= (1ull << 32)) room = (1ull << 32) - 1 - used;
         const uint64_t fit = std::min<uint64_t>(blk.n - rec, room / stride);
         if (fit == 0) return false;
-        memcpy(lines + used, blk.lines.data() + byte, fit * stride);
+        copy_lines(lines + used, blk.lines.data() + byte, fit * stride);
         first_len = blk.first_len;
         used += fit * stride;
         n += fit;
@@ -295,6 +314,9 @@ OffsetValue detect_offset(const sgc_library* lib, const std::string& path, unsig
 struct SampleResult {
   std::vector<uint64_t> counts;
   uint64_t total = 0, matched = 0;
+  // where the counting thread spent its time (--timing): waiting for the inflate threads,
+  // copying sequence lines into pinned memory, in sgc_counter_submit / sync / finish
+  double wait_s = 0, copy_s = 0, submit_s = 0;
 };
 
 // count_sample (count.rs:15-45): parse on this thread into two pinned buffers; the copy and
@@ -325,22 +347,36 @@ SampleResult count_sample(const sgc_library* lib, uint32_t n_guides, const std::
   sgh::SeqBlock blk;
   int cur = 0;
   bool other_in_flight = false;
-  while (reader.next(blk)) {
+  SampleResult r;
+  using Clock = std::chrono::steady_clock;
+  auto since = [](Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); };
+  for (;;) {
+    auto t0 = Clock::now();
+    const bool more = reader.next(blk);
+    r.wait_s += since(t0);
+    if (!more) break;
     uint64_t rec = 0;
     size_t byte = 0;
-    while (!g.b[cur].append(blk, rec, byte)) {
+    for (;;) {
+      t0 = Clock::now();
+      const bool done = g.b[cur].append(blk, rec, byte);
+      r.copy_s += since(t0);
+      if (done) break;
       if (g.b[cur].n == 0) fail("a sequence line longer than %zu bytes", cap);
+      t0 = Clock::now();
       submit(c, g.b[cur]);
       cur ^= 1;
       if (other_in_flight) check(sgc_counter_sync(c));  // the buffer we are about to refill has been consumed
+      r.submit_s += since(t0);
       other_in_flight = true;
       g.b[cur].reset();
     }
   }
+  auto t0 = Clock::now();
   submit(c, g.b[cur]);
-  SampleResult r;
   r.counts.resize(n_guides);
   check(sgc_counter_finish(c, r.counts.data(), &r.total, &r.matched));
+  r.submit_s += since(t0);
   return r;
 }
 
@@ -446,9 +482,12 @@ int main(int argc, char** argv) {
     if (args.timing) {
       const double count_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_count0).count();
       unsigned long long reads = 0;
-      for (const auto& r : results) reads += r.total;
+      double wait_s = 0, copy_s = 0, submit_s = 0;
+      for (const auto& r : results) reads += r.total, wait_s += r.wait_s, copy_s += r.copy_s, submit_s += r.submit_s;
       fprintf(stderr, "{\"count_s\": %.6f, \"reads\": %llu, \"samples\": %zu, \"sample_workers\": %u, "
-              "\"ingest_threads\": %u, \"gpus\": %d}\n", count_s, reads, n_samples, workers, ingest_threads, gpus);
+              "\"ingest_threads\": %u, \"gpus\": %d, \"wait_inflate_s\": %.6f, \"copy_to_pinned_s\": %.6f, "
+              "\"submit_sync_s\": %.6f}\n", count_s, reads, n_samples, workers, ingest_threads, gpus, wait_s, copy_s,
+              submit_s);
     }
 
     // write_results (results.rs:71-99).  Counts are keyed by alias (counter.rs:232-235):

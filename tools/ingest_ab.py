@@ -29,4 +29,4 @@ for rep in range(2):
         p = subprocess.run([exe, "-l", lib, "-i", fq, "-a", "5", "-q", "-o", os.path.join(tmp, "o.tsv"), "--timing"],
                            capture_output=True, text=True, env=env)
         t = json.loads([l for l in p.stderr.splitlines() if l.startswith("{")][-1])
-        print(f"{mode}: count_s {t['count_s']:.3f}  {t['reads'] / t['count_s'] / 1e6:.1f} M reads/s  threads {t['ingest_threads']}", flush=True)
+        print(f"{mode}: count_s {t['count_s']:.3f}  {t['reads'] / t['count_s'] / 1e6:.1f} M reads/s  threads {t['ingest_threads']}  wait {t['wait_inflate_s']:.3f} copy {t['copy_to_pinned_s']:.3f} submit {t['submit_sync_s']:.3f}", flush=True)
