@@ -207,15 +207,30 @@ class GzSource : public ByteSource {
   }
 
 
-  void find_candidates() {
-    const unsigned char* p = data_;
-    const unsigned char* const last = data_ + size_ - 18;  // smallest member: 10 header + 8 trailer
+  // positions in [from, to) that look like the start of a member
+  void scan_candidates(size_t from, size_t to, std::vector<size_t>& found) const {
+    const unsigned char* p = data_ + from;
+    const unsigned char* const last = data_ + to;
     while (p < last) {
       p = static_cast<const unsigned char*>(memchr(p, 0x1f, (size_t)(last - p)));
       if (!p) break;
-      if (p[1] == 0x8b && p[2] == 0x08 && (p[3] & 0xE0) == 0) cand_.push_back((size_t)(p - data_));
+      if (p[1] == 0x8b && p[2] == 0x08 && (p[3] & 0xE0) == 0) found.push_back((size_t)(p - data_));
       ++p;
     }
+  }
+  void find_candidates() {
+    const size_t last = size_ - 18;  // smallest member: 10 header + 8 trailer
+    // the scan touches every page of the file once: worth spreading over the threads that are
+    // about to inflate it
+    const unsigned parts = size_ < (64u << 20) ? 1u : std::min(threads_, 16u);
+    std::vector<std::vector<size_t>> found(parts);
+    std::vector<std::thread> pool;
+    const size_t step = last / parts + 1;
+    for (unsigned i = 1; i < parts; ++i)
+      pool.emplace_back([&, i] { scan_candidates(step * i, std::min(last, step * (i + 1)), found[i]); });
+    scan_candidates(0, std::min(last, step), found[0]);
+    for (auto& t : pool) t.join();
+    for (auto& f : found) cand_.insert(cand_.end(), f.begin(), f.end());
     if (cand_.empty() || cand_[0] != 0) cand_.clear();  // not a gzip file: let zlib report it
   }
 

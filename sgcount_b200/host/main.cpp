@@ -334,6 +334,9 @@ SampleResult count_sample(const sgc_library* lib, uint32_t n_guides, const std::
         if (x.lines) sgc_host_free(x.lines);
     }
   } g{c, {}};
+  // blocks of packed sequence lines, framed by the inflate threads (fastx.h); they start
+  // inflating while the pinned buffers are being allocated
+  sgh::SeqBlockReader reader(path, ingest_threads);
   const size_t cap = 64u << 20;
   for (auto& b : g.b) {
     void* p = nullptr;
@@ -342,8 +345,6 @@ SampleResult count_sample(const sgc_library* lib, uint32_t n_guides, const std::
     b.cap = cap;
     b.reset();
   }
-  // blocks of packed sequence lines, framed by the inflate threads (fastx.h)
-  sgh::SeqBlockReader reader(path, ingest_threads);
   sgh::SeqBlock blk;
   int cur = 0;
   bool other_in_flight = false;
