@@ -45,6 +45,7 @@ struct CountParams {
   uint32_t n_guides;
   int32_t* assign_out;
   uint32_t debug;  // SGC_DEBUG bit mask (tuning only): 1 no count atomics, 2 no table probe, 4 no slow path
+  uint32_t zero;   // always 0, and unknown to the compiler: see the buffer hand-back in step A
 };
 
 // MODE 0: production (no per-read output, no tuning switches); 1: also writes the per-read
@@ -365,7 +366,10 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
                                                               uint32_t stage_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  // read from lane 0 so that the compiler knows the warp index — and the ring addresses, tile
+  // indices and source pointers derived from it — to be warp-uniform: they then live in uniform
+  // registers and the bulk copy is issued without a lane-by-lane broadcast loop
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int warps_per_cta = blockDim.x >> 5;
   // shared layout: [warp][stage] tile buffers | [warp][stage] mbarriers | [warp] queues
   uint8_t* my_tiles = smem + (size_t)warp * n_stages * stage_bytes;
@@ -380,23 +384,24 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   const uint8_t* next_src = p.lines + (uint64_t)gwarp * tile_bytes;  // source of the next tile to request
 
   const uint32_t tiles_sm = smem_u32(my_tiles), bars_sm = smem_u32(my_bar);
-  uint64_t policy = 0;
-  uint32_t requested = gwarp;  // tile index of the next request (n_wtiles + gwarps < 2^32)
+  const uint64_t policy = l2_evict_first_policy();
+  uint32_t requested = gwarp;  // tile index of the next request (n_wtiles + gwarps < 2^32); every lane keeps it
   if (lane == 0) {
     for (int s = 0; s < n_stages; ++s) mbar_init(&my_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    policy = l2_evict_first_policy();
-    for (int s = 0; s < n_stages; ++s) {
-      if (requested < n_wtiles) {
-        mbar_expect_tx(bars_sm + 8u * (uint32_t)s, tile_bytes);
-        bulk_load(tiles_sm + (uint32_t)s * stage_bytes, next_src, tile_bytes, bars_sm + 8u * (uint32_t)s, policy);
-        requested += gwarps;
-        next_src += src_step;
-      }
-    }
   }
   __syncwarp();
+  for (int s = 0; s < n_stages; ++s) {
+    if (requested < n_wtiles) {
+      if (lane == 0) {
+        mbar_expect_tx(bars_sm + 8u * (uint32_t)s, tile_bytes);
+        bulk_load(tiles_sm + (uint32_t)s * stage_bytes, next_src, tile_bytes, bars_sm + 8u * (uint32_t)s, policy);
+      }
+      requested += gwarps;
+      next_src += src_step;
+    }
+  }
 
   // every read has the same length n, so the geometry is uniform; the host sends reads whose
   // Centered window does not fit (every one of them fails its first trim) to the generic kernel
@@ -450,25 +455,21 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
     mbar_wait(cur_bar, parity);
     uint32_t W[NW + 2];
     LoadWords<0, NW + 2>::run(cur_tile + lane_off, W);
-    {
-      // The buffer may be refilled once every lane's loads have RETURNED.  A warp vote on a
-      // value computed from all of them is that point: it cannot issue before the data is in
-      // registers, which orders the generic-proxy reads before the async-proxy write without
-      // a CTA-wide membar per tile.
-      uint32_t allw = W[0];
+    // The buffer may be refilled once every lane's loads have RETURNED (the refill is an
+    // async-proxy write, the loads are generic-proxy reads: nothing orders them by itself).  The
+    // byte count of the refill is made to DEPEND on a warp vote over a value computed from all
+    // the loaded words (`& p.zero` keeps it what it was): the copy cannot be issued, in program
+    // order or after any rescheduling by ptxas, before the data is in registers.  No CTA-wide
+    // membar per tile.
+    uint32_t allw = W[0];
 #pragma unroll
-      for (int i = 1; i < NW + 2; ++i) allw &= W[i];
-      uint32_t vote;
-      asm volatile(
-          "{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\nvote.sync.ballot.b32 %0, p, 0xffffffff;\n}\n"
-          : "=r"(vote)
-          : "r"(allw)
-          : "memory");
-      (void)vote;
-    }
-    if (lane == 0 && requested < n_wtiles) {
-      mbar_expect_tx(cur_bar, tile_bytes);
-      bulk_load(cur_tile, next_src, tile_bytes, cur_bar, policy);
+    for (int i = 1; i < NW + 2; ++i) allw &= W[i];
+    const uint32_t arrived = __ballot_sync(0xffffffffu, allw != 0) & p.zero;
+    if (requested < n_wtiles) {
+      if (lane == 0) {
+        mbar_expect_tx(cur_bar, tile_bytes + arrived);
+        bulk_load(cur_tile, next_src, tile_bytes + arrived, cur_bar, policy);
+      }
       requested += gwarps;
       next_src += src_step;
     }

@@ -171,3 +171,10 @@ def test_config2_full_size_properties():
     whole.submit_device(d.data_ptr(), n_reads * stride, n_reads, stride, 75)
     counts2, total2, matched2 = whole.finish()
     assert np.array_equal(counts2, 2 * counts) and (total2, matched2) == (2 * total, 2 * matched)
+
+    # ... and so do 18 more: a hand-back of a ring buffer that races with the lanes still reading
+    # it loses a read in a hundred million, which only repetition at full size shows
+    for _ in range(18):
+        whole.submit_device(d.data_ptr(), n_reads * stride, n_reads, stride, 75)
+    counts20, total20, matched20 = whole.finish()
+    assert np.array_equal(counts20, 20 * counts) and (total20, matched20) == (20 * total, 20 * matched)

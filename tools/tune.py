@@ -43,6 +43,9 @@ for warps, ctas, stages, debug, carve in configs:
     if ref is None and debug == 0:
         ref = counts.copy()
     ok = ref is not None and (counts == ref).all()
+    if debug == 0 and N_READS == 50_000_000 and matched != 46992470 * iters:
+        # the oracle-checked total of this workload: anything else is a lost or double-counted read
+        print(f"!!! matched {matched} != {46992470 * iters}: WRONG RESULT", flush=True)
     print(f"warps={warps} ctas={ctas} stages={stages} debug={debug} carve={carve} grid={li.grid} smem={li.smem_bytes} "
           f"{ms:.3f} ms  {N_READS/ms/1e6:.2f} Greads/s  {N_READS*76/ms/1e6:.0f} GB/s "
           f"frac={N_READS*76/ms/1e6/6547.2:.3f} matched={matched//iters} same={ok}", flush=True)
