@@ -30,6 +30,48 @@
 namespace sgc {
 namespace {
 
+// Geometry of the streaming kernel: every read has the same length, so it is the same for every
+// read of a launch.  It is worked out on the host and travels as a kernel parameter, so that the
+// kernel reads its fields straight from the constant bank instead of re-deriving them per tile.
+// Positions are in STORED coordinates: for a reverse read the oriented window [o, o+k) is the
+// stored window [n-o-k, n-o), Plus (o+1) is one byte EARLIER and Minus one byte later.
+struct StreamGeom {
+  int k, n, o;
+  uint32_t with_perm;
+  int win_src;             // stored position of the Centered window
+  int lead;                // 1 if the span starts one byte before the Centered window
+  uint32_t shift_bits[3];  // where the Centered / Plus / Minus window starts in the span, in bits
+  uint32_t try_plus, try_minus;  // the position exists (its trim succeeds) and recursion is on
+  int n_words;             // words holding the k window bytes
+  uint32_t last_mask;
+  uint32_t wild_byte;      // the stored byte the lookup sees as 'N'
+};
+
+inline StreamGeom make_geom(uint32_t k, uint32_t read_len, int offset, bool with_perm, bool reverse, bool recursion,
+                            int rc_mode) {
+  StreamGeom g;
+  g.k = (int)k;
+  g.n = (int)read_len;
+  g.o = offset;
+  g.with_perm = with_perm;
+  // Plus is tried after a Centered miss if its trim succeeds; Minus after a Plus miss if
+  // offset >= 1 (a failed trim returns, counter.rs:105-108: no Plus means no Minus either)
+  g.try_plus = recursion && g.o + 1 + g.k <= g.n;
+  g.try_minus = g.try_plus && g.o >= 1;
+  g.win_src = reverse ? g.n - g.o - g.k : g.o;
+  const int d_plus = reverse ? -1 : 1;  // stored displacement of the Plus window
+  const bool before = (g.try_plus && d_plus < 0) || (g.try_minus && d_plus > 0);
+  g.lead = before ? 1 : 0;
+  g.shift_bits[0] = 8u * (uint32_t)g.lead;
+  g.shift_bits[1] = 8u * (uint32_t)(g.lead + d_plus);
+  g.shift_bits[2] = 8u * (uint32_t)(g.lead - d_plus);
+  g.n_words = (g.k + 3) >> 2;
+  g.last_mask = (g.k & 3) ? ((1u << (8 * (g.k & 3))) - 1) : ~0u;
+  // under the fxread bit trick a reverse-complemented 'J' reads as 'N' (and 'N' as 'J')
+  g.wild_byte = (reverse && rc_mode == SGC_RC_BITTRICK) ? (uint32_t)'J' : (uint32_t)'N';
+  return g;
+}
+
 struct CountParams {
   LibView lib;
   const uint8_t* lines;
@@ -46,6 +88,7 @@ struct CountParams {
   int32_t* assign_out;
   uint32_t debug;  // SGC_DEBUG bit mask (tuning only): 1 no count atomics, 2 no table probe, 4 no slow path
   uint32_t zero;   // always 0, and unknown to the compiler: see the buffer hand-back in step A
+  StreamGeom geom; // streaming kernel only
 };
 
 // MODE 0: production (no per-read output, no tuning switches); 1: also writes the per-read
@@ -256,7 +299,12 @@ __device__ __forceinline__ uint32_t pack_window(const uint32_t (&w)[NW], int n_w
   for (int i = 0; i < NW; ++i) {
     x[i] = ascii_residue(w[i]);
     uint32_t c = (w[i] >> 1) & 0x03030303u;
-    if (NW != 5 || i == NW - 1) {  // bytes past the window (NW = 5: only the last word can have any)
+    if (NW == 5) {  // k = 17..20: all five words are in use and only the last can hold bytes past the window
+      if (i == NW - 1) {
+        x[i] &= last_mask;
+        c &= last_mask;
+      }
+    } else {
       const uint32_t mk = i < n_words - 1 ? ~0u : (i == n_words - 1 ? last_mask : 0u);
       x[i] &= mk;
       c &= mk;
@@ -279,45 +327,6 @@ struct WarpQueueT {
   uint32_t w[NW + 1][kQueueCap];
   uint32_t tag[kQueueCap];
 };
-
-// Geometry of the streaming kernel: every read has the same length, so it is warp uniform.
-// Positions are in STORED coordinates: for a reverse read the oriented window [o, o+k) is the
-// stored window [n-o-k, n-o), Plus (o+1) is one byte EARLIER and Minus one byte later.
-struct StreamGeom {
-  int k, n, o;
-  bool with_perm;
-  int win_src;             // stored position of the Centered window
-  int lead;                // 1 if the span starts one byte before the Centered window
-  uint32_t shift_bits[3];  // where the Centered / Plus / Minus window starts in the span, in bits
-  bool try_plus, try_minus;  // the position exists (its trim succeeds) and recursion is on
-  int n_words;             // words holding the k window bytes
-  uint32_t last_mask;
-  uint32_t wild_byte;      // the stored byte the lookup sees as 'N'
-};
-
-__device__ __forceinline__ StreamGeom make_geom(const CountParams& p) {
-  StreamGeom g;
-  g.k = (int)p.lib.k;
-  g.n = (int)p.read_len;
-  g.o = p.offset;
-  g.with_perm = p.with_perm;
-  // Plus is tried after a Centered miss if its trim succeeds; Minus after a Plus miss if
-  // offset >= 1 (a failed trim returns, counter.rs:105-108: no Plus means no Minus either)
-  g.try_plus = p.recursion && g.o + 1 + g.k <= g.n;
-  g.try_minus = g.try_plus && g.o >= 1;
-  g.win_src = p.reverse ? g.n - g.o - g.k : g.o;
-  const int d_plus = p.reverse ? -1 : 1;  // stored displacement of the Plus window
-  const bool before = (g.try_plus && d_plus < 0) || (g.try_minus && d_plus > 0);
-  g.lead = before ? 1 : 0;
-  g.shift_bits[0] = 8u * (uint32_t)g.lead;
-  g.shift_bits[1] = 8u * (uint32_t)(g.lead + d_plus);
-  g.shift_bits[2] = 8u * (uint32_t)(g.lead - d_plus);
-  g.n_words = (g.k + 3) >> 2;
-  g.last_mask = (g.k & 3) ? ((1u << (8 * (g.k & 3))) - 1) : ~0u;
-  // under the fxread bit trick a reverse-complemented 'J' reads as 'N' (and 'N' as 'J')
-  g.wild_byte = (p.reverse && p.rc_mode == SGC_RC_BITTRICK) ? (uint32_t)'J' : (uint32_t)'N';
-  return g;
-}
 
 // One position of Counter::assign (counter.rs:111-117) for one parked read: the window that
 // starts `shift` bits into the span S.
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
 
   // every read has the same length n, so the geometry is uniform; the host sends reads whose
   // Centered window does not fit (every one of them fails its first trim) to the generic kernel
-  const StreamGeom g = make_geom(p);
+  const StreamGeom& g = p.geom;
   const uint32_t sbyte = (uint32_t)lane * p.stride + (uint32_t)(g.win_src - g.lead);  // first span byte
   const uint32_t lane_off = sbyte & ~3u;  // byte offset of this lane's first span word in a tile
   const uint32_t off_bits = (sbyte & 3u) * 8;
@@ -661,6 +670,8 @@ CountParams make_params(const sgc_counter* c, const uint8_t* d_lines, const uint
   p.n_guides = c->lib->n;
   p.assign_out = d_assign;
   p.debug = (uint32_t)env_int("SGC_DEBUG", 0);
+  p.geom = make_geom(c->lib->k, read_len, (int)c->offset, c->lib->with_perm, c->is_reverse != 0, c->recursion != 0,
+                     c->rc_mode);
   return p;
 }
 
