@@ -240,6 +240,12 @@ class ClockSampler(threading.Thread):
     def run(self):
         if not self.ok:
             return
+        try:  # the first queries of a process are slow: take them before anything is timed
+            for _ in range(3):
+                self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            pass
         while not self.stop_flag:
             if self.active.is_set():
                 try:
@@ -537,7 +543,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads-per-gpu", type=int, default=READS_PER_GPU)
