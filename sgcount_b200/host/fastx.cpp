@@ -302,16 +302,25 @@ class GzSource : public ByteSource {
         if (isize < (1u << 30)) out.reserve((size_t)isize + 1024);
       }
       size_t end = 0;
-      const bool ok = inflate_member(cand_[j], out, end);
+      bool ok = false, framed = false;
       SeqParser framer;
-      if (ok && frame_lpr_) {
-        framer.st.lines_per_record = frame_lpr_;
-        block.lines.reserve(out.size() / 2);
-        framer.feed(out.data(), out.size(), block);
+      try {  // nothing may escape a worker: a failed job sends the consumer down the sequential path
+        ok = inflate_member(cand_[j], out, end);
+        if (ok && frame_lpr_) {
+          framer.st.lines_per_record = frame_lpr_;
+          block.lines.reserve(out.size() / 2);
+          try {
+            framer.feed(out.data(), out.size(), block);
+            framed = true;
+          } catch (const std::exception&) {  // the consumer frames these bytes itself and reports
+          }
+        }
+      } catch (const std::exception&) {
+        ok = false;
       }
       {
         std::lock_guard<std::mutex> lk(mu_);
-        if (ok && frame_lpr_) {
+        if (framed) {
           jobs_[j].framed = true;
           jobs_[j].block = std::move(block);
           jobs_[j].end_state = std::move(framer.st);
