@@ -256,49 +256,164 @@ struct Decoder {
            build_table(lens + hlit, hdist, kSymbols.dist, kDistRoot, dist, kDistCap);
   }
 
-  // the symbols of one block, up to and including its end-of-block code
+  // The symbols of one block, up to and including its end-of-block code.
+  //
+  // Fast loop, while at least 16 input bytes and a worst-case symbol of output room are left:
+  // the state lives in locals (byte stores through `op` may alias the decoder's own fields, so
+  // members would be reloaded after every literal), every iteration starts with a full bit
+  // buffer and the NEXT symbol's table entry already loaded — the load is issued before the
+  // match copy of the current symbol, off the critical path — and a match first copies 32 bytes
+  // unconditionally, which covers most matches without a data-dependent loop.  Everything else
+  // (the last bytes of the input, a nearly full buffer) goes through the careful loop below.
   bool block_body(const uint32_t* lt, const uint32_t* dt) {
     constexpr uint32_t lit_mask = (1u << kLitRoot) - 1, dist_mask = (1u << kDistRoot) - 1;
-    constexpr size_t kSlack = 3 + 258 + 8;  // three literals, or the longest match + copy overshoot
-    auto lookup = [&](const uint32_t* table, uint32_t mask, int root) {
-      uint32_t e = table[bits & mask];
-      if (e & kSecondLevel) {
-        bits >>= root;
-        n_bits -= root;
-        e = table[(e >> 16) + (bits & ((1u << ((e >> 8) & 15)) - 1))];
-      }
-      return e;
-    };
+    constexpr size_t kSlack = 3 + 258 + 40;  // three literals, or the longest match + copy overshoot
     for (;;) {
-      if ((size_t)(out_end - op) < kSlack) grow(kSlack);
-      const bool roomy = in_end - ip >= 8;  // the refill below leaves at least 56 bits
+      if ((size_t)(out_end - op) < 2 * kSlack) grow(2 * kSlack);
+      if (in_end - ip >= 16) {
+        uint64_t b = bits;
+        int nb = n_bits;
+        const unsigned char* in = ip;
+        unsigned char* o = op;
+        const unsigned char* const in_fast_end = in_end - 16;
+        unsigned char* const out_fast_end = out_end - kSlack;
+        int status = 0;  // 1 end of block, -1 invalid
+#define SGH_REFILL()                 \
+  do {                               \
+    b |= load64(in) << nb;           \
+    in += (63 - nb) >> 3;            \
+    nb |= 56;                        \
+  } while (0)
+        SGH_REFILL();
+        uint32_t e = lt[b & lit_mask];
+        while (in <= in_fast_end && o <= out_fast_end) {
+          if (e & kSecondLevel) {
+            b >>= kLitRoot;
+            nb -= kLitRoot;
+            e = lt[(e >> 16) + (b & ((1u << ((e >> 8) & 15)) - 1))];
+          }
+          if (e & kLiteral) {
+            b >>= (e & 0xFF);
+            nb -= (int)(e & 0xFF);
+            *o++ = (unsigned char)(e >> 16);
+            // a second literal straight away when the bits allow it (>= 41 are left)
+            e = lt[b & lit_mask];
+            if ((e & (kLiteral | kSecondLevel)) == kLiteral) {
+              b >>= (e & 0xFF);
+              nb -= (int)(e & 0xFF);
+              *o++ = (unsigned char)(e >> 16);
+            }
+            SGH_REFILL();
+            e = lt[b & lit_mask];
+            continue;
+          }
+          if (e & kSpecial) {
+            if (e & kEndOfBlock) {
+              b >>= (e & 0xFF);
+              nb -= (int)(e & 0xFF);
+              status = 1;
+            } else {
+              status = -1;
+            }
+            break;
+          }
+          // a match: <= 20 bits of length code + extra, <= 28 of distance code + extra: the 56
+          // bits every iteration starts with cover both (a second-level entry re-shifted above)
+          b >>= (e & 0xFF);
+          nb -= (int)(e & 0xFF);
+          const uint32_t len_extra = (e >> 8) & 15;
+          const uint32_t length = (e >> 16) + (uint32_t)(b & ((1u << len_extra) - 1));
+          b >>= len_extra;
+          nb -= (int)len_extra;
+          if (nb < 32) SGH_REFILL();  // only after a second-level length code
+          uint32_t d = dt[b & dist_mask];
+          if (d & kSecondLevel) {
+            b >>= kDistRoot;
+            nb -= kDistRoot;
+            d = dt[(d >> 16) + (b & ((1u << ((d >> 8) & 15)) - 1))];
+          }
+          if (d & kSpecial) {
+            status = -1;
+            break;
+          }
+          b >>= (d & 0xFF);
+          nb -= (int)(d & 0xFF);
+          const uint32_t dist_extra = (d >> 8) & 15;
+          const size_t distance = (d >> 16) + (size_t)(b & ((1u << dist_extra) - 1));
+          b >>= dist_extra;
+          nb -= (int)dist_extra;
+          if (distance > (size_t)(o - out_begin)) {
+            status = -1;
+            break;
+          }
+          // next symbol's entry: in flight during the copy
+          SGH_REFILL();
+          e = lt[b & lit_mask];
+          const unsigned char* src = o - distance;
+          unsigned char* dst = o;
+          o += length;
+          if (distance >= 8) {
+            store64(dst, load64(src));
+            store64(dst + 8, load64(src + 8));
+            store64(dst + 16, load64(src + 16));
+            store64(dst + 24, load64(src + 24));
+            if (length > 32) {
+              dst += 32;
+              src += 32;
+              do {
+                store64(dst, load64(src));
+                store64(dst + 8, load64(src + 8));
+                dst += 16;
+                src += 16;
+              } while (dst < o);
+            }
+          } else if (distance == 1) {
+            const uint64_t v = 0x0101010101010101ull * src[0];
+            do {
+              store64(dst, v);
+              store64(dst + 8, v);
+              dst += 16;
+            } while (dst < o);
+          } else {
+            do {
+              *dst++ = *src++;
+            } while (dst < o);
+          }
+        }
+#undef SGH_REFILL
+        // the entry in `e` was only looked up, not consumed: the bit buffer is exactly where the
+        // next symbol starts
+        bits = b;
+        n_bits = nb;
+        ip = in;
+        op = o;
+        if (status < 0) return false;
+        if (status > 0) return true;
+        continue;  // out of input or output room for the fast loop: re-check, then go careful
+      }
+      // ---- careful: the last bytes of the input (n_bits may run negative: truncated stream) ----
+      auto lookup = [&](const uint32_t* table, uint32_t mask, int root) {
+        uint32_t e = table[bits & mask];
+        if (e & kSecondLevel) {
+          bits >>= root;
+          n_bits -= root;
+          e = table[(e >> 16) + (bits & ((1u << ((e >> 8) & 15)) - 1))];
+        }
+        return e;
+      };
       refill();
       uint32_t e = lookup(lt, lit_mask, kLitRoot);
       if (e & kLiteral) {
         take((int)(e & 0xFF));
         *op++ = (unsigned char)(e >> 16);
-        if (!roomy) {
-          if (n_bits < 0) return false;
-          continue;
-        }
-        e = lookup(lt, lit_mask, kLitRoot);  // >= 41 bits left
-        if (e & kLiteral) {
-          take((int)(e & 0xFF));
-          *op++ = (unsigned char)(e >> 16);
-          e = lookup(lt, lit_mask, kLitRoot);  // >= 26 bits left
-          if (e & kLiteral) {
-            take((int)(e & 0xFF));
-            *op++ = (unsigned char)(e >> 16);
-            continue;
-          }
-        }
+        if (n_bits < 0) return false;
+        continue;
       }
       if (e & kSpecial) {
         if (!(e & kEndOfBlock)) return false;
         take((int)(e & 0xFF));
         return n_bits >= 0;
       }
-      // a match: length code (+ extra bits) here, at least 11 bits are left for them
       take((int)(e & 0xFF));
       const uint32_t length = (e >> 16) + take((int)((e >> 8) & 15));
       refill();
@@ -310,23 +425,9 @@ struct Decoder {
       const unsigned char* src = op - distance;
       unsigned char* dst = op;
       op += length;
-      if (distance >= 8) {
-        do {
-          store64(dst, load64(src));
-          dst += 8;
-          src += 8;
-        } while (dst < op);
-      } else if (distance == 1) {
-        const uint64_t v = 0x0101010101010101ull * src[0];
-        do {
-          store64(dst, v);
-          dst += 8;
-        } while (dst < op);
-      } else {
-        do {
-          *dst++ = *src++;
-        } while (dst < op);
-      }
+      do {
+        *dst++ = *src++;
+      } while (dst < op);
     }
   }
 

@@ -386,6 +386,9 @@ SampleResult count_sample(const sgc_library* lib, uint32_t n_guides, const std::
 int main(int argc, char** argv) {
   try {
     Args args = parse_args(argc, argv);
+    const auto t_start = std::chrono::steady_clock::now();
+    auto seconds_since_start = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
+    double t_inputs = 0, t_tables = 0, t_offsets = 0;
     for (const auto& p : args.input_paths)
       if (!exists(p)) fail("Provided filepath does not exist: %s", p.c_str());  // main.rs:130-140
     std::vector<std::string> names;
@@ -418,6 +421,7 @@ int main(int argc, char** argv) {
              "adapters.)");
     }
 
+    t_inputs = seconds_since_start();
     int ndev = 0;
     check(sgc_device_count(&ndev));
     if (ndev == 0) fail("no CUDA device: this build has no CPU fallback");
@@ -435,6 +439,7 @@ int main(int argc, char** argv) {
       check(sgc_library_create(args.device + d, reinterpret_cast<const uint8_t*>(hlib.seqs.data()), hlib.n, hlib.k,
                                args.exact ? 0 : 1, &libs[d]));
 
+    t_tables = seconds_since_start();
     std::vector<OffsetValue> offsets(n_samples);
     if (args.have_offset) {
       for (auto& o : offsets) o = OffsetValue{args.reverse, (uint32_t)args.offset};  // main.rs:163-170
@@ -447,6 +452,7 @@ int main(int argc, char** argv) {
       }
     }
 
+    t_offsets = seconds_since_start();
     // the reference's only fan-out: samples in parallel (count.rs:117-136)
     std::vector<SampleResult> results(n_samples);
     std::atomic<size_t> next{0};
@@ -487,8 +493,9 @@ int main(int argc, char** argv) {
       for (const auto& r : results) reads += r.total, wait_s += r.wait_s, copy_s += r.copy_s, submit_s += r.submit_s;
       fprintf(stderr, "{\"count_s\": %.6f, \"reads\": %llu, \"samples\": %zu, \"sample_workers\": %u, "
               "\"ingest_threads\": %u, \"gpus\": %d, \"wait_inflate_s\": %.6f, \"copy_to_pinned_s\": %.6f, "
-              "\"submit_sync_s\": %.6f}\n", count_s, reads, n_samples, workers, ingest_threads, gpus, wait_s, copy_s,
-              submit_s);
+              "\"submit_sync_s\": %.6f, \"read_inputs_s\": %.3f, \"device_tables_s\": %.3f, \"offsets_s\": %.3f}\n",
+              count_s, reads, n_samples, workers, ingest_threads, gpus, wait_s, copy_s, submit_s, t_inputs,
+              t_tables - t_inputs, t_offsets - t_tables);
     }
 
     // write_results (results.rs:71-99).  Counts are keyed by alias (counter.rs:232-235):
