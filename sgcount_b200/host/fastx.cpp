@@ -94,7 +94,9 @@ class GzSource : public ByteSource {
     if (threads_ > 1 && frame_records) frame_lpr_ = peek_lines_per_record();
     if (threads_ > 1) {
       jobs_.resize(cand_.size());
-      window_ = 2 * threads_;
+      // members in flight: one per thread plus a few finished ones waiting for the consumer, which
+      // only copies and is never the slow side (each holds ~1.5x the member's decompressed size)
+      window_ = threads_ + 2;
       for (unsigned t = 0; t < threads_; ++t) pool_.emplace_back([this] { worker(); });
     }
   }
