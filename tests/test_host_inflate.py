@@ -106,3 +106,64 @@ def test_reader_output_is_the_same_with_and_without_the_fast_decoder(tmp_path):
         assert p.returncode == 0, p.stderr
         outs.add(p.stdout.strip())
     assert len(outs) == 1 and outs.pop().startswith("40000 ")
+
+
+def test_differential_fuzz_against_zlib(tmp_path):
+    """Random structured inputs x random deflate parameters: the decoder must reproduce zlib's
+    output; random corruptions of valid members must be declined or decode to exactly the original
+    (a flip in the gzip header's ignored fields) — never to something else."""
+    rng = random.Random(20240521)
+
+    def chunk():
+        kind = rng.randrange(6)
+        n = rng.choice([1, 2, 7, 50, 300, 5000, 40000])
+        if kind == 0:
+            return os.urandom(n)
+        if kind == 1:
+            return bytes([rng.randrange(256)]) * n
+        if kind == 2:
+            alphabet = bytes(rng.sample(range(256), rng.choice([2, 4, 20])))
+            return bytes(rng.choice(alphabet) for _ in range(n))
+        if kind == 3:
+            unit = os.urandom(rng.choice([2, 3, 5, 9, 40]))
+            return (unit * (n // len(unit) + 1))[:n]
+        if kind == 4:
+            return b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rng.choice(b"ACGTN") for _ in range(40)), b"F" * 40) for i in range(n // 90 + 1))
+        return bytes(min(255, int(rng.expovariate(0.05))) for _ in range(n))
+
+    blobs, datas = [], []
+    for case in range(60):
+        data = b"".join(chunk() for _ in range(rng.randrange(1, 6)))
+        level = rng.choice([0, 1, 1, 3, 6, 9])
+        strategy = rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED])
+        c = zlib.compressobj(level, zlib.DEFLATED, 31, rng.choice([1, 5, 8, 9]), strategy)
+        blob = b""
+        at = 0
+        while at < len(data):  # several blocks per member: flush at random points
+            step = rng.randrange(1, len(data) + 1)
+            blob += c.compress(data[at:at + step])
+            if rng.random() < 0.5:
+                blob += c.flush(rng.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH]))
+            at += step
+        blob += c.flush()
+        assert gzip.decompress(blob) == data
+        blobs.append(blob)
+        datas.append(data)
+        path = tmp_path / f"case{case}.gz"
+        path.write_bytes(blob)
+        assert run(path) == (0, fnv(data)), case
+    # all of them as one multi-member file
+    (tmp_path / "all.gz").write_bytes(b"".join(blobs))
+    assert run(tmp_path / "all.gz") == (0, fnv(b"".join(datas)))
+    # corruptions
+    for case in range(80):
+        i = rng.randrange(len(blobs))
+        blob = bytearray(blobs[i])
+        if len(blob) < 30:
+            continue
+        for _ in range(rng.choice([1, 1, 2, 5])):
+            blob[rng.randrange(len(blob))] ^= 1 << rng.randrange(8)
+        path = tmp_path / f"bad{case}.gz"
+        path.write_bytes(bytes(blob))
+        rc, out = run(path)
+        assert rc == 4 or (rc == 0 and out == fnv(datas[i])), (case, rc, out)
