@@ -21,8 +21,10 @@
 // instead; the two are the same comparison).
 //
 // 1. SEED INDEX (exact semantics of the whole lookup)
-//    The bases are cut into kSeeds = 3 parts: window words 0-1 (bases 0..7), words 2-3
-//    (bases 8..15) and the rest (`hi`).  A token within Hamming distance 1 of a member differs
+//    The bases are cut into kSeeds = 3 parts of (nearly) equal size, [0, e0), [e0, e1), [e1, k)
+//    (SeedParts, worked out per library: with fixed parts a short guide would leave one part
+//    empty and the other seeds too short to tell the members apart).  A token within Hamming
+//    distance 1 of a member differs
 //    from it inside at most one part, so it agrees with the member on the COMPLEMENT of that
 //    part.  Seed i is that complement: directory i hashes the token with part i masked out to a
 //    bucket (start | count | tag) of postings (member key + guide index) sorted by bucket.  A
@@ -84,13 +86,6 @@ struct Key {
   uint32_t lo, hi;
 };
 
-// what seed i keeps of a key
-__host__ __device__ __forceinline__ Key seed_of(Key k, int i) {
-  return i == 0 ? Key{k.lo & 0xF0F0F0F0u, k.hi} : (i == 1 ? Key{k.lo & 0x0F0F0F0Fu, k.hi} : Key{k.lo, 0u});
-}
-// part (= list) a base position belongs to
-__host__ __device__ __forceinline__ int part_of_base(uint32_t j) { return j < 8 ? 0 : (j < 16 ? 1 : 2); }
-
 // the 2-bit field of base j inside a key
 __host__ __device__ __forceinline__ Key base_field(uint32_t j, bool wide) {
   const uint32_t word = j >> 2, byte = j & 3u;
@@ -106,6 +101,64 @@ __host__ __device__ __forceinline__ void key_set_base(Key& k, uint32_t j, bool w
 __host__ __device__ __forceinline__ uint32_t key_get_base(Key k, uint32_t j, bool wide) {
   const Key f = base_field(j, wide);
   return f.lo ? (k.lo & f.lo) / (f.lo & (~f.lo + 1)) : (k.hi & f.hi) / (f.hi & (~f.hi + 1));
+}
+
+// The three parts of the k bases and, per list, the key bits its seed KEEPS (everything outside
+// its own part).
+constexpr uint32_t kFixedPartsMinK = 17;
+struct SeedParts {
+  uint32_t end[2];  // part 0 = bases [0, end[0]), part 1 = [end[0], end[1]), part 2 = the rest
+  uint32_t keep_lo[kSeeds], keep_hi[kSeeds];
+};
+inline SeedParts make_seed_parts(uint32_t k, bool wide) {
+  SeedParts sp{};
+  // k >= kFixedPartsMinK: two parts of 8 bases (whole window words, i.e. alternating nibbles of
+  // `lo`) and the rest — the streaming kernel has these masks as immediates (seed_of_t<true>);
+  // shorter guides: three parts of nearly equal size, masks read from here
+  const bool fixed = k >= kFixedPartsMinK;
+  const uint32_t p0 = fixed ? 8 : (k + 2) / 3, p1 = fixed ? 8 : (k - p0 + 1) / 2;
+  sp.end[0] = p0;
+  sp.end[1] = p0 + p1;
+  for (uint32_t j = 0; j < k; ++j) {
+    const int part = j < sp.end[0] ? 0 : (j < sp.end[1] ? 1 : 2);
+    const Key f = base_field(j, wide);
+    for (int i = 0; i < kSeeds; ++i)
+      if (i != part) {
+        sp.keep_lo[i] |= f.lo;
+        sp.keep_hi[i] |= f.hi;
+      }
+  }
+  return sp;
+}
+// what seed i keeps of a key
+__host__ __device__ __forceinline__ Key seed_of(const SeedParts& sp, Key k, int i) {
+  return Key{k.lo & sp.keep_lo[i], k.hi & sp.keep_hi[i]};
+}
+// part (= list) a base position belongs to
+__host__ __device__ __forceinline__ int part_of_base(const SeedParts& sp, uint32_t j) {
+  return j < sp.end[0] ? 0 : (j < sp.end[1] ? 1 : 2);
+}
+
+// The same with the parts of a k >= kFixedPartsMinK library as compile-time constants (FIXED),
+// for the streaming kernel's hot instantiations; FIXED = false reads them from the library.
+template <bool FIXED>
+__host__ __device__ __forceinline__ Key seed_of_t(const SeedParts& sp, Key k, int i) {
+  if (FIXED) return i == 0 ? Key{k.lo & 0xF0F0F0F0u, k.hi} : (i == 1 ? Key{k.lo & 0x0F0F0F0Fu, k.hi} : Key{k.lo, 0u});
+  return seed_of(sp, k, i);
+}
+template <bool FIXED>
+__host__ __device__ __forceinline__ int part_of_base_t(const SeedParts& sp, uint32_t j) {
+  if (FIXED) return j < 8 ? 0 : (j < 16 ? 1 : 2);
+  return part_of_base(sp, j);
+}
+// the bits of a key difference that lie in what list `list` keeps
+template <bool FIXED>
+__host__ __device__ __forceinline__ uint32_t kept_difference(const SeedParts& sp, Key x, int list) {
+  if (FIXED) {
+    const uint32_t keep_lo = list == 0 ? 0xF0F0F0F0u : (list == 1 ? 0x0F0F0F0Fu : 0xFFFFFFFFu);
+    return (x.lo & keep_lo) | (list < 2 ? x.hi : 0u);
+  }
+  return (x.lo & sp.keep_lo[list]) | (x.hi & sp.keep_hi[list]);
 }
 
 // bucket hash of a (masked) key; the top bits are used
@@ -139,6 +192,7 @@ struct LibView {
   uint32_t wide;         // k > 20: 16-byte postings and front slots
   uint32_t dir_shift;    // bucket = seed_hash >> dir_shift (>= 8)
   uint32_t front_shift;  // bucket = front_hash >> front_shift
+  SeedParts parts;
   IndexView fwd;         // guides as written
   IndexView rev;         // reverse complements of the guides
 };
@@ -222,7 +276,7 @@ __device__ __forceinline__ void load_posting(const IndexView& ix, uint32_t at, u
 template <bool WIDE, typename F>
 __device__ __forceinline__ void for_each_posting(const LibView& v, const IndexView& ix, int seed, Key key,
                                                  uint64_t policy, F&& visit) {
-  const uint32_t h = seed_hash(seed_of(key, seed));
+  const uint32_t h = seed_hash(seed_of(v.parts, key, seed));
   SeedRun r;
   if (WIDE) {
     r = seed_run(v, ix, seed, h, ldg_u32(ix.dir[seed] + (h >> v.dir_shift), policy));
@@ -254,7 +308,7 @@ __device__ __forceinline__ void for_each_posting(const LibView& v, const IndexVi
 //                   lists keep the hole base in their seed and are not consulted).
 //   !active         nothing is loaded, the answer is kMiss.
 // Returns the guide index or kMiss; *kind = 1 member, 2 one-mismatch variant.
-template <bool WIDE>
+template <bool WIDE, bool FIXED = false>
 __device__ __forceinline__ int32_t lookup_token(const LibView& v, const IndexView& ix, bool with_perm, Key key, Key hole,
                                                 int hole_list, bool active, int* kind, uint64_t policy) {
   static_assert(kSeeds == 3, "written for three lists");
@@ -266,8 +320,7 @@ __device__ __forceinline__ int32_t lookup_token(const LibView& v, const IndexVie
   // on what the list keeps; a difference of one base lies inside the part this list leaves out
   auto consider = [&](int list, Key mk, uint32_t idx) {
     const Key x{(mk.lo ^ key.lo) & ~hole.lo, (mk.hi ^ key.hi) & ~hole.hi};
-    const uint32_t keep_lo = list == 0 ? 0xF0F0F0F0u : (list == 1 ? 0x0F0F0F0Fu : 0xFFFFFFFFu);
-    if (((x.lo & keep_lo) | (list < 2 ? x.hi : 0u)) != 0) return;
+    if (kept_difference<FIXED>(v.parts, x, list) != 0) return;
     if ((x.lo | x.hi) == 0) {
       if (wild) {
         ++parents;
@@ -291,7 +344,7 @@ __device__ __forceinline__ int32_t lookup_token(const LibView& v, const IndexVie
 #pragma unroll
   for (int i = 0; i < kSeeds; ++i) {
     use[i] = active && (wild ? i == hole_list : (i == 0 || with_perm));
-    h[i] = seed_hash(seed_of(key, i));
+    h[i] = seed_hash(seed_of_t<FIXED>(v.parts, key, i));
   }
   if (WIDE) {
     uint32_t entry[kSeeds];
@@ -351,7 +404,7 @@ __device__ __forceinline__ int32_t lookup_wild(const LibView& v, const IndexView
   const Key hole = base_field(pos, WIDE);
   key.lo &= ~hole.lo;
   key.hi &= ~hole.hi;
-  return lookup_token<WIDE>(v, ix, true, key, hole, part_of_base(pos), true, kind, policy);
+  return lookup_token<WIDE>(v, ix, true, key, hole, part_of_base(v.parts, pos), true, kind, policy);
 }
 
 // Decision for ONE window given its key, the number of bytes in it that

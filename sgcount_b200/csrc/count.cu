@@ -365,8 +365,12 @@ __device__ __forceinline__ int32_t try_position(const LibView& v, const IndexVie
     key.lo &= ~hole.lo;
     key.hi &= ~hole.hi;
   }
-  return lookup_token<WIDE>(v, ix, g.with_perm, key, hole, wild ? part_of_base(pos) : -1, any == 0 || wild, nullptr,
-                            policy);
+  // NW = 5 and the wide kernels only ever see k >= 17: the index's parts are the fixed ones
+  constexpr bool kFixedParts = NW == 5 || WIDE;
+  static_assert(kFixedPartsMinK <= 17, "k = 17..30 must use the fixed parts");
+  return lookup_token<WIDE, kFixedParts>(v, ix, g.with_perm, key, hole,
+                                         wild ? part_of_base_t<kFixedParts>(v.parts, pos) : -1, any == 0 || wild,
+                                         nullptr, policy);
 }
 
 // NW = words that hold the k window bytes: 5 (k = 17..20, the common guide lengths) or 8.

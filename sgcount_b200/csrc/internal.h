@@ -58,6 +58,7 @@ struct sgc_library {
     uint64_t* d_front = nullptr;
   } ix[2];
   uint32_t dir_shift = 0, front_shift = 0;
+  sgc::SeedParts parts{};
   size_t front_bytes = 0;
   uint32_t* d_lib_hist = nullptr;  // k*4 positional counts over guides 1..n-1 (offsetter.rs:190-191)
   int sm_count = 0;
@@ -70,6 +71,7 @@ struct sgc_library {
     v.wide = wide ? 1u : 0u;
     v.dir_shift = dir_shift;
     v.front_shift = front_shift;
+    v.parts = parts;
     sgc::IndexView* views[2] = {&v.fwd, &v.rev};
     for (int o = 0; o < 2; ++o) {
       for (int i = 0; i < sgc::kSeeds; ++i) {

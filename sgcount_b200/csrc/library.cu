@@ -72,14 +72,14 @@ struct SeedArrays {
 // pass 1: members per bucket, and the bucket's tag: the first member's, with bit 8 raised when a
 // member with another tag joins
 constexpr uint32_t kNoTag = 0xFFFFFFFFu, kTagConflict = 0x100u;
-__global__ void seed_count_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t dir_shift, SeedArrays cnt,
-                                  SeedArrays tags) {
+__global__ void seed_count_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t dir_shift, SeedParts parts,
+                                  SeedArrays cnt, SeedArrays tags) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Key key = as_key(keys[i]);
 #pragma unroll
   for (int s = 0; s < kSeeds; ++s) {
-    const uint32_t h = seed_hash(seed_of(key, s));
+    const uint32_t h = seed_hash(seed_of(parts, key, s));
     const uint32_t b = h >> dir_shift, tag = (h >> (dir_shift - 8)) & 0xFFu;
     atomicAdd(cnt.a[s] + b, 1u);
     const uint32_t old = atomicCAS(tags.a[s] + b, kNoTag, tag);
@@ -170,15 +170,15 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(const uint32_t
 // pass 3: postings.  `cursor` starts as a copy of `start`; the order inside one bucket is
 // whatever the atomics give, which no lookup depends on.
 template <bool WIDE>
-__global__ void seed_fill_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t dir_shift, SeedArrays cursor,
-                                 uint64_t* __restrict__ post) {
+__global__ void seed_fill_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t dir_shift, SeedParts parts,
+                                 SeedArrays cursor, uint64_t* __restrict__ post) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t w = keys[i];
   const Key key = as_key(w);
 #pragma unroll
   for (int s = 0; s < kSeeds; ++s) {
-    const size_t a = (size_t)s * n + atomicAdd(cursor.a[s] + (seed_hash(seed_of(key, s)) >> dir_shift), 1u);
+    const size_t a = (size_t)s * n + atomicAdd(cursor.a[s] + (seed_hash(seed_of(parts, key, s)) >> dir_shift), 1u);
     if (WIDE) {
       post[2 * a] = w;
       post[2 * a + 1] = i;
@@ -248,9 +248,9 @@ __global__ void variant_stats_kernel(LibView v, const uint64_t* __restrict__ key
       bool member = false;
       uint32_t parents = 0, smallest = 0xFFFFFFFFu;
       for (int s = 0; s < kSeeds && !member; ++s) {
-        const Key qs = seed_of(q, s);
+        const Key qs = seed_of(v.parts, q, s);
         for_each_posting<WIDE>(v, v.fwd, s, q, pol, [&](Key mk, uint32_t idx) {
-          const Key ms = seed_of(mk, s);
+          const Key ms = seed_of(v.parts, mk, s);
           if (ms.lo != qs.lo || ms.hi != qs.hi) return false;  // another seed in this bucket
           const Key x{mk.lo ^ q.lo, mk.hi ^ q.hi};
           if ((x.lo | x.hi) == 0) member = true;
@@ -441,13 +441,13 @@ int build_index(sgc_library* lib, int o, BuildScratch& sc, BuildStatus* d_st) {
     cursor.a[i] = sc.cur[i].p;
     tags.a[i] = sc.tag[i].p;
   }
-  seed_count_kernel<<<blocks_for(n, T), T>>>(ix.d_keys, n, lib->dir_shift, cnt, tags);
+  seed_count_kernel<<<blocks_for(n, T), T>>>(ix.d_keys, n, lib->dir_shift, lib->parts, cnt, tags);
   for (int i = 0; i < kSeeds; ++i) {
     int rc = exclusive_scan(ix.d_dir_count[i], entries, sc.start[i].p, sc.sums.p);
     if (rc) return rc;
     SGC_CUDA_TRY(cudaMemcpyAsync(sc.cur[i].p, sc.start[i].p, (size_t)entries * 4, cudaMemcpyDeviceToDevice, 0));
   }
-  seed_fill_kernel<WIDE><<<blocks_for(n, T), T>>>(ix.d_keys, n, lib->dir_shift, cursor, ix.d_post);
+  seed_fill_kernel<WIDE><<<blocks_for(n, T), T>>>(ix.d_keys, n, lib->dir_shift, lib->parts, cursor, ix.d_post);
   for (int i = 0; i < kSeeds; ++i) {
     if (WIDE)
       seed_dir_kernel<<<blocks_for(entries, T), T>>>(sc.start[i].p, ix.d_dir_count[i], sc.tag[i].p, ix.d_dir[i],
@@ -499,6 +499,7 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   lib->k = k;
   lib->with_perm = with_permutations != 0;
   lib->wide = k > kNarrowMaxK;
+  lib->parts = make_seed_parts(k, lib->wide);
   struct Cleanup {
     sgc_library* l;
     ~Cleanup() {
