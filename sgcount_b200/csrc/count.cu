@@ -373,7 +373,7 @@ __device__ __forceinline__ int32_t try_position(const LibView& v, const IndexVie
                                          nullptr, policy);
 }
 
-// NW = words that hold the k window bytes: 5 (k = 17..20, the common guide lengths) or 8.
+// NW = words that hold the k window bytes: 4, 5 (k = 17..20, the common guide lengths), 6 or 8.
 template <int NW, bool WIDE, int MODE>
 __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams p, uint32_t n_wtiles, int n_stages,
                                                               uint32_t stage_bytes) {
@@ -722,8 +722,12 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
   const uint32_t stage_bytes = (tile_bytes + 48 + 15) & ~15u;  // +48: span words may run past the tile
   const bool stageable = d_off == nullptr && ((uintptr_t)d_lines & 15u) == 0 && stride >= read_len &&
                          (uint64_t)c->offset + c->lib->k <= read_len;
-  const bool nw5 = !c->lib->wide && c->lib->k > 16;
-  const size_t queue_bytes = nw5 ? sizeof(WarpQueueT<5>) : sizeof(WarpQueueT<8>);
+  // kernel family by the words that hold the k window bytes: narrow keys 4 (k <= 16) or 5
+  // (k = 17..20, the common guide lengths); wide keys 6 (k = 21..24) or 8 (k = 25..30)
+  const int family = !c->lib->wide ? (c->lib->k <= 16 ? 0 : 1) : (c->lib->k <= 24 ? 2 : 3);
+  static const size_t family_queue_bytes[4] = {sizeof(WarpQueueT<4>), sizeof(WarpQueueT<5>), sizeof(WarpQueueT<6>),
+                                               sizeof(WarpQueueT<8>)};
+  const size_t queue_bytes = family_queue_bytes[family];
   StreamConfig cfg = stageable ? pick_stream_config(stage_bytes, queue_bytes) : StreamConfig{};
   // whole tiles only, and never a bulk copy that would run past n_bytes; one launch handles at
   // most 2^30 reads (the queue words keep a 30-bit read index)
@@ -735,14 +739,16 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
     // straight to the state vector (p.rep == p.state then, see make_params)
     const int mode = p.debug ? 2 : (d_assign ? 1 : (c->n_rep > 1 ? 3 : 0));
     using Kernel = void (*)(const CountParams, uint32_t, int, uint32_t);
-    static const Kernel kernels[3][4] = {
+    static const Kernel kernels[4][4] = {
+        {count_stream_kernel<4, false, 0>, count_stream_kernel<4, false, 1>, count_stream_kernel<4, false, 2>,
+         count_stream_kernel<4, false, 3>},
         {count_stream_kernel<5, false, 0>, count_stream_kernel<5, false, 1>, count_stream_kernel<5, false, 2>,
          count_stream_kernel<5, false, 3>},
-        {count_stream_kernel<8, false, 0>, count_stream_kernel<8, false, 1>, count_stream_kernel<8, false, 2>,
-         count_stream_kernel<8, false, 3>},
+        {count_stream_kernel<6, true, 0>, count_stream_kernel<6, true, 1>, count_stream_kernel<6, true, 2>,
+         count_stream_kernel<6, true, 3>},
         {count_stream_kernel<8, true, 0>, count_stream_kernel<8, true, 1>, count_stream_kernel<8, true, 2>,
          count_stream_kernel<8, true, 3>}};
-    Kernel kernel = kernels[c->lib->wide ? 2 : (nw5 ? 0 : 1)][mode];
+    Kernel kernel = kernels[family][mode];
     const size_t smem = stream_smem_bytes(cfg, stage_bytes, queue_bytes);
     SGC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (const int carve = env_int("SGC_CARVEOUT", -1); carve >= 0)  // tuning: shared-memory share of the L1, percent

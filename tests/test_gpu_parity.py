@@ -103,6 +103,10 @@ CASES = [
     (25, 200, 75, 7, True, False),
     (30, 100, 64, 1, False, True),
     (30, 100, 64, 33, True, False),
+    (16, 300, 75, 9, False, False),     # last k of the 4-word kernel, balanced seed parts
+    (17, 300, 75, 9, True, False),      # first k of the fixed seed parts: a third part of one base
+    (24, 200, 75, 2, False, False),     # last k of the 6-word wide kernel
+    (24, 200, 75, 40, True, False),
 ]
 
 
