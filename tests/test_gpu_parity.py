@@ -241,3 +241,32 @@ def test_count_replicas_give_the_same_table_on_a_skewed_sample():
             c.set_replicas(1)
             c.submit(batch)
             assert np.array_equal(c.finish()[0], 3 * want[1])
+
+
+def test_randomised_geometries_match_oracle():
+    """Forty random (k, library size and density, read length, offset, orientation, fixed/variable
+    length, Permuter, recursion, rc_mode) combinations, 1 500 reads each, per-read assignment
+    against the oracle: the kernel families (4/5/6/8 window words), both seed-part policies,
+    windows flush with either end of the read, odd strides, dense libraries full of ambiguous
+    variants."""
+    rng = np.random.default_rng(20250711)
+    for case in range(40):
+        k = int(rng.choice([4, 7, 11, 15, 16, 17, 18, 19, 20, 20, 20, 21, 23, 24, 25, 28, 30]))
+        n_guides = int(rng.choice([30, 200, 1500])) if k > 6 else int(rng.choice([20, 60]))
+        read_len = int(rng.integers(k + 1, k + 70))
+        offset = int(rng.integers(0, read_len - k + 1))
+        reverse, variable = bool(rng.integers(2)), bool(rng.random() < 0.3)
+        with_perm, recursion = bool(rng.random() < 0.75), bool(rng.random() < 0.75)
+        rc_mode = _cabi.RC_BITTRICK if rng.random() < 0.7 else _cabi.RC_KEEP_N
+        guides = make_library(rng, n_guides, k, plant=float(rng.choice([0.0, 0.02, 0.15])))
+        wild = b"J" if (reverse and rc_mode == _cabi.RC_BITTRICK) else b"N"
+        seqs = make_reads(rng, guides, 1500, read_len, offset, reverse, variable, wild=wild)
+        library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+        permuter = sg.Permuter.new(library) if with_perm else None
+        off = sg.Offset(reverse, offset)
+        got = gpu_assign(library, permuter, sg.ReadBatch.from_seqs(seqs), off, recursion, rc_mode)
+        want = oracle_count(guides, seqs, with_perm, off, recursion, rc_mode)
+        label = (case, k, n_guides, read_len, offset, reverse, variable, with_perm, recursion, rc_mode)
+        assert np.array_equal(got[0], want[0]), label
+        assert np.array_equal(got[1], want[1]) and got[2:4] == want[2:4], label
+        assert got[4].kernel == (1 if variable else 0), label
