@@ -65,14 +65,11 @@ constexpr int32_t kMiss = -1;
 //   2  a run of postings: [21:0] first posting, [53:22] count
 constexpr uint64_t kDirKindInline = 1ull << 62, kDirKindRun = 2ull << 62;
 constexpr int kDirKindShift = 62;
-// WIDE directory entry (k = 21..30), 32 bit: [21:0] first posting of the bucket, [23:22] number
-// of postings, [31:24] tag (the 8 hash bits below the bucket bits) shared by every posting of
-// the bucket.  Count 3 marks a GENERAL bucket: more than two postings, or postings of different
-// tags; its exact size is in IndexView::dir_count and its tag is not used.
+// WIDE directory entry (k = 21..30), 2 x 64 bit, the same three kinds in [63:62] of word 0:
+//   1  the bucket's only posting inline: word 0 [61:0] = hi << 32 | lo (a 30-base key leaves the
+//      two top bits of `hi` free), word 1 = guide index
+//   2  a run of postings: word 1 = first posting | count << 22
 constexpr uint32_t kDirStartMask = 0x3FFFFFu;
-constexpr int kDirCountShift = 22;
-constexpr uint32_t kDirGeneral = 3u;
-constexpr int kDirTagShift = 24;
 
 // narrow posting: [31:0] lo, [39:32] hi, [61:40] guide index.  Wide posting: {hi << 32 | lo, guide index}.
 constexpr int kPostIdxShift = 40;
@@ -179,9 +176,8 @@ __host__ __device__ __forceinline__ uint32_t code_of(uint8_t c) { return (c >> 1
 
 // One orientation's structures.
 struct IndexView {
-  const uint64_t* __restrict__ dir64[kSeeds];      // narrow: 1 << dir_bits entries each
-  const uint32_t* __restrict__ dir[kSeeds];        // wide: 1 << dir_bits entries each
-  const uint32_t* __restrict__ dir_count[kSeeds];  // wide: exact bucket sizes (read for general buckets only)
+  const uint64_t* __restrict__ dir64[kSeeds];      // narrow: 1 << dir_bits entries of one word each
+  const ulonglong2* __restrict__ dir128[kSeeds];   // wide: 1 << dir_bits entries of two words each
   const uint64_t* __restrict__ post;               // kSeeds x n postings, list i at i * n, each sorted by bucket
                                                    // (2 words per posting when wide)
   const uint64_t* __restrict__ front;              // front table
@@ -213,6 +209,13 @@ __device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p, uint64_t policy) 
   asm volatile("ld.global.nc" SGC_L1_HINT ".L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
   return v;
 }
+__device__ __forceinline__ ulonglong2 ldg_u128(const ulonglong2* p, uint64_t policy) {
+  ulonglong2 v;
+  asm volatile("ld.global.nc" SGC_L1_HINT ".L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;"
+               : "=l"(v.x), "=l"(v.y)
+               : "l"(p), "l"(policy));
+  return v;
+}
 // one 32-byte bucket = one sector, fetched with a single 256-bit read-only load (LDG.256)
 __device__ __forceinline__ void load_bucket(const uint64_t* p, uint64_t (&w)[4], uint64_t policy) {
   asm volatile("ld.global.nc" SGC_L1_HINT ".L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
@@ -240,15 +243,11 @@ struct SeedRun {
   uint32_t first;  // index of the first posting in IndexView::post (list offset included)
   uint32_t count;
 };
-// wide entries
-__device__ __forceinline__ SeedRun seed_run(const LibView& v, const IndexView& ix, int seed, uint32_t h, uint32_t entry) {
+// wide entries of kind 2 (any other kind: an empty run)
+__device__ __forceinline__ SeedRun seed_run128(const LibView& v, int seed, ulonglong2 entry) {
   SeedRun r;
-  r.first = (uint32_t)seed * v.n + (entry & kDirStartMask);
-  r.count = (entry >> kDirCountShift) & 3u;
-  if (r.count == kDirGeneral)
-    r.count = ix.dir_count[seed][h >> v.dir_shift];
-  else if ((entry >> kDirTagShift) != ((h >> (v.dir_shift - 8)) & 0xFFu))
-    r.count = 0;  // the bucket belongs to another seed
+  r.first = (uint32_t)seed * v.n + ((uint32_t)entry.y & kDirStartMask);
+  r.count = (entry.x >> kDirKindShift) == 2 ? (uint32_t)(entry.y >> 22) : 0u;
   return r;
 }
 // narrow entries of kind 2 (any other kind: an empty run)
@@ -279,7 +278,12 @@ __device__ __forceinline__ void for_each_posting(const LibView& v, const IndexVi
   const uint32_t h = seed_hash(seed_of(v.parts, key, seed));
   SeedRun r;
   if (WIDE) {
-    r = seed_run(v, ix, seed, h, ldg_u32(ix.dir[seed] + (h >> v.dir_shift), policy));
+    const ulonglong2 e = ldg_u128(ix.dir128[seed] + (h >> v.dir_shift), policy);
+    if ((e.x >> kDirKindShift) == 1) {
+      visit(Key{(uint32_t)e.x, (uint32_t)(e.x >> 32) & 0x3FFFFFFFu}, (uint32_t)e.y);
+      return;
+    }
+    r = seed_run128(v, seed, e);
   } else {
     const uint64_t e = ldg_u64(ix.dir64[seed] + (h >> v.dir_shift), policy);
     if ((e >> kDirKindShift) == 1) {
@@ -347,13 +351,15 @@ __device__ __forceinline__ int32_t lookup_token(const LibView& v, const IndexVie
     h[i] = seed_hash(seed_of_t<FIXED>(v.parts, key, i));
   }
   if (WIDE) {
-    uint32_t entry[kSeeds];
+    ulonglong2 entry[kSeeds];
 #pragma unroll
-    for (int i = 0; i < kSeeds; ++i) entry[i] = use[i] ? ldg_u32(ix.dir[i] + (h[i] >> v.dir_shift), policy) : 0u;
+    for (int i = 0; i < kSeeds; ++i)
+      entry[i] = use[i] ? ldg_u128(ix.dir128[i] + (h[i] >> v.dir_shift), policy) : ulonglong2{0ull, 0ull};
 #pragma unroll
     for (int i = 0; i < kSeeds; ++i) {
-      r[i].first = r[i].count = 0;
-      if (use[i]) r[i] = seed_run(v, ix, i, h[i], entry[i]);
+      if ((entry[i].x >> kDirKindShift) == 1)
+        consider(i, Key{(uint32_t)entry[i].x, (uint32_t)(entry[i].x >> 32) & 0x3FFFFFFFu}, (uint32_t)entry[i].y);
+      r[i] = seed_run128(v, i, entry[i]);
     }
   } else {
     uint64_t entry[kSeeds];

@@ -51,9 +51,8 @@ struct sgc_library {
   // seed index + front table per read orientation (common.cuh): [0] forward, [1] reverse
   struct Index {
     uint64_t* d_keys = nullptr;  // n interleaved keys (hi << 32 | lo), library order
-    uint64_t* d_dir64[sgc::kSeeds] = {};  // narrow keys
-    uint32_t* d_dir[sgc::kSeeds] = {};    // wide keys
-    uint32_t* d_dir_count[sgc::kSeeds] = {};
+    uint64_t* d_dir64[sgc::kSeeds] = {};      // narrow keys
+    ulonglong2* d_dir128[sgc::kSeeds] = {};   // wide keys
     uint64_t* d_post = nullptr;  // kSeeds lists of n postings
     uint64_t* d_front = nullptr;
   } ix[2];
@@ -76,8 +75,7 @@ struct sgc_library {
     for (int o = 0; o < 2; ++o) {
       for (int i = 0; i < sgc::kSeeds; ++i) {
         views[o]->dir64[i] = ix[o].d_dir64[i];
-        views[o]->dir[i] = ix[o].d_dir[i];
-        views[o]->dir_count[i] = ix[o].d_dir_count[i];
+        views[o]->dir128[i] = ix[o].d_dir128[i];
       }
       views[o]->post = ix[o].d_post;
       views[o]->front = ix[o].d_front;

@@ -69,22 +69,14 @@ struct SeedArrays {
   uint32_t* a[kSeeds];
 };
 
-// pass 1: members per bucket, and the bucket's tag: the first member's, with bit 8 raised when a
-// member with another tag joins
-constexpr uint32_t kNoTag = 0xFFFFFFFFu, kTagConflict = 0x100u;
+// pass 1: members per bucket
 __global__ void seed_count_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t dir_shift, SeedParts parts,
-                                  SeedArrays cnt, SeedArrays tags) {
+                                  SeedArrays cnt) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Key key = as_key(keys[i]);
 #pragma unroll
-  for (int s = 0; s < kSeeds; ++s) {
-    const uint32_t h = seed_hash(seed_of(parts, key, s));
-    const uint32_t b = h >> dir_shift, tag = (h >> (dir_shift - 8)) & 0xFFu;
-    atomicAdd(cnt.a[s] + b, 1u);
-    const uint32_t old = atomicCAS(tags.a[s] + b, kNoTag, tag);
-    if (old != kNoTag && (old & 0xFFu) != tag) atomicOr(tags.a[s] + b, kTagConflict);
-  }
+  for (int s = 0; s < kSeeds; ++s) atomicAdd(cnt.a[s] + (seed_hash(seed_of(parts, key, s)) >> dir_shift), 1u);
 }
 
 // pass 2: exclusive prefix sum of the counts (three small kernels: tile sums, scan of the
@@ -188,17 +180,25 @@ __global__ void seed_fill_kernel(const uint64_t* __restrict__ keys, uint32_t n, 
   }
 }
 
-// pass 4: directory entry = start | count << 22 | tag << 24 (count 3 = general bucket)
-__global__ void seed_dir_kernel(const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt,
-                                const uint32_t* __restrict__ tags, uint32_t* __restrict__ dir, uint32_t n_entries) {
+// pass 4: directory entries; a bucket with one posting carries the posting itself.
+// wide keys: two words per entry
+__global__ void seed_dir128_kernel(const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt,
+                                   const uint64_t* __restrict__ post, ulonglong2* __restrict__ dir, uint32_t n_entries) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_entries) return;
-  const uint32_t c = cnt[i], t = tags[i];
-  const bool general = c >= kDirGeneral || (t != kNoTag && (t & kTagConflict));
-  dir[i] = start[i] | ((general ? kDirGeneral : c) << kDirCountShift) | ((t & 0xFFu) << kDirTagShift);
+  const uint32_t c = cnt[i];
+  ulonglong2 e{0ull, 0ull};
+  if (c == 1) {
+    e.x = kDirKindInline | (post[2 * (size_t)start[i]] & (kDirKindInline - 1));
+    e.y = post[2 * (size_t)start[i] + 1];
+  } else if (c >= 2) {
+    e.x = kDirKindRun;
+    e.y = start[i] | ((uint64_t)c << 22);
+  }
+  dir[i] = e;
 }
 
-// narrow keys: 64-bit entries; a bucket with one posting carries the posting itself
+// narrow keys: one word per entry
 __global__ void seed_dir64_kernel(const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt,
                                   const uint64_t* __restrict__ post, uint64_t* __restrict__ dir, uint32_t n_entries) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -387,8 +387,7 @@ void sgc_library_destroy(sgc_library* lib) {
   for (int o = 0; o < 2; ++o) {
     for (int i = 0; i < kSeeds; ++i) {
       cudaFree(lib->ix[o].d_dir64[i]);
-      cudaFree(lib->ix[o].d_dir[i]);
-      cudaFree(lib->ix[o].d_dir_count[i]);
+      cudaFree(lib->ix[o].d_dir128[i]);
     }
     cudaFree(lib->ix[o].d_post);
     cudaFree(lib->ix[o].d_front);
@@ -414,13 +413,13 @@ int exclusive_scan(const uint32_t* d_cnt, uint32_t n, uint32_t* d_start, uint32_
 
 // temporaries of one build, allocated before the timed region
 struct BuildScratch {
-  DeviceBuffer<uint32_t> start[kSeeds], cur[kSeeds], tag[kSeeds], sums;
+  DeviceBuffer<uint32_t> start[kSeeds], cur[kSeeds], cnt[kSeeds], sums;
   int alloc(uint32_t entries) {
     SGC_CUDA_TRY(sums.alloc((entries + kScanTile - 1) / kScanTile + 1));
     for (int i = 0; i < kSeeds; ++i) {
       SGC_CUDA_TRY(start[i].alloc(entries));
       SGC_CUDA_TRY(cur[i].alloc(entries));
-      SGC_CUDA_TRY(tag[i].alloc(entries));
+      SGC_CUDA_TRY(cnt[i].alloc(entries));
     }
     return SGC_OK;
   }
@@ -433,27 +432,25 @@ int build_index(sgc_library* lib, int o, BuildScratch& sc, BuildStatus* d_st) {
   const unsigned T = 256;
   const uint32_t entries = 1u << (32 - lib->dir_shift);
   sgc_library::Index& ix = lib->ix[o];
-  SeedArrays cnt, cursor, tags;
+  SeedArrays cnt, cursor;
   for (int i = 0; i < kSeeds; ++i) {
-    SGC_CUDA_TRY(cudaMemsetAsync(ix.d_dir_count[i], 0, (size_t)entries * 4, 0));
-    SGC_CUDA_TRY(cudaMemsetAsync(sc.tag[i].p, 0xFF, (size_t)entries * 4, 0));
-    cnt.a[i] = ix.d_dir_count[i];
+    SGC_CUDA_TRY(cudaMemsetAsync(sc.cnt[i].p, 0, (size_t)entries * 4, 0));
+    cnt.a[i] = sc.cnt[i].p;
     cursor.a[i] = sc.cur[i].p;
-    tags.a[i] = sc.tag[i].p;
   }
-  seed_count_kernel<<<blocks_for(n, T), T>>>(ix.d_keys, n, lib->dir_shift, lib->parts, cnt, tags);
+  seed_count_kernel<<<blocks_for(n, T), T>>>(ix.d_keys, n, lib->dir_shift, lib->parts, cnt);
   for (int i = 0; i < kSeeds; ++i) {
-    int rc = exclusive_scan(ix.d_dir_count[i], entries, sc.start[i].p, sc.sums.p);
+    int rc = exclusive_scan(sc.cnt[i].p, entries, sc.start[i].p, sc.sums.p);
     if (rc) return rc;
     SGC_CUDA_TRY(cudaMemcpyAsync(sc.cur[i].p, sc.start[i].p, (size_t)entries * 4, cudaMemcpyDeviceToDevice, 0));
   }
   seed_fill_kernel<WIDE><<<blocks_for(n, T), T>>>(ix.d_keys, n, lib->dir_shift, lib->parts, cursor, ix.d_post);
   for (int i = 0; i < kSeeds; ++i) {
     if (WIDE)
-      seed_dir_kernel<<<blocks_for(entries, T), T>>>(sc.start[i].p, ix.d_dir_count[i], sc.tag[i].p, ix.d_dir[i],
-                                                     entries);
+      seed_dir128_kernel<<<blocks_for(entries, T), T>>>(sc.start[i].p, sc.cnt[i].p, ix.d_post + 2 * (size_t)i * n,
+                                                        ix.d_dir128[i], entries);
     else
-      seed_dir64_kernel<<<blocks_for(entries, T), T>>>(sc.start[i].p, ix.d_dir_count[i], ix.d_post + (size_t)i * n,
+      seed_dir64_kernel<<<blocks_for(entries, T), T>>>(sc.start[i].p, sc.cnt[i].p, ix.d_post + (size_t)i * n,
                                                        ix.d_dir64[i], entries);
   }
   SGC_CUDA_TRY(cudaMemsetAsync(ix.d_front, 0, lib->front_bytes, 0));
@@ -534,10 +531,9 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
     SGC_CUDA_TRY(cudaMalloc(&ix.d_keys, (size_t)n * sizeof(uint64_t)));
     for (int i = 0; i < kSeeds; ++i) {
       if (lib->wide)
-        SGC_CUDA_TRY(cudaMalloc(&ix.d_dir[i], dir_entries * 4));
+        SGC_CUDA_TRY(cudaMalloc(&ix.d_dir128[i], dir_entries * 16));
       else
         SGC_CUDA_TRY(cudaMalloc(&ix.d_dir64[i], dir_entries * 8));
-      SGC_CUDA_TRY(cudaMalloc(&ix.d_dir_count[i], dir_entries * 4));
     }
     SGC_CUDA_TRY(cudaMalloc(&ix.d_post, kSeeds * post_words * 8));
     SGC_CUDA_TRY(cudaMalloc(&ix.d_front, lib->front_bytes));
@@ -588,7 +584,7 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   lib->info.n_ambiguous = st.n_ambiguous;
   lib->info.n_slots = ((size_t)1 << log_buckets) * (lib->wide ? 2 : 4);
   // what one counter touches: the directories, postings and front table of its orientation
-  lib->info.table_bytes = kSeeds * (dir_entries * (lib->wide ? 4 : 8) + post_words * 8) + lib->front_bytes;
+  lib->info.table_bytes = kSeeds * (dir_entries * (lib->wide ? 16 : 8) + post_words * 8) + lib->front_bytes;
   lib->info.build_ms = ms;
   lib->info.front_left_out = st.front_left_out;
   cleanup.l = nullptr;
