@@ -258,6 +258,14 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
       "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
+// One lane of the (converged) warp.  With `elect.sync` ptxas knows that a single thread runs the
+// guarded code and issues the bulk copy once from uniform registers; `lane == 0` made it wrap the
+// copy in a loop over the active lanes with a broadcast of every operand.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 template <int OFFSET>
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
@@ -407,7 +415,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   __syncwarp();
   for (int s = 0; s < n_stages; ++s) {
     if (requested < n_wtiles) {
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_expect_tx(bars_sm + 8u * (uint32_t)s, tile_bytes);
         bulk_load(tiles_sm + (uint32_t)s * stage_bytes, next_src, tile_bytes, bars_sm + 8u * (uint32_t)s, policy);
       }
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
     for (int i = 1; i < NW + 2; ++i) allw &= W[i];
     const uint32_t arrived = __ballot_sync(0xffffffffu, allw != 0) & p.zero;
     if (requested < n_wtiles) {
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_expect_tx(cur_bar, tile_bytes + arrived);
         bulk_load(cur_tile, next_src, tile_bytes + arrived, cur_bar, policy);
       }
