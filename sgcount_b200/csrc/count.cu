@@ -693,21 +693,31 @@ struct StreamConfig {
 size_t stream_smem_bytes(const StreamConfig& c, uint32_t stage_bytes, size_t queue_bytes) {
   return (size_t)c.warps * ((size_t)c.stages * stage_bytes + kMaxStages * sizeof(uint64_t) + queue_bytes);
 }
-// Largest ring that fits: prefer 2 resident CTAs of 12 warps with 2 buffers per warp (measured: the shared
-// memory a third buffer takes is worth more as L1 for the table loads).
-// SGC_WARPS / SGC_STAGES / SGC_CTAS override the choice (tuning only).
+// How many warps per CTA and CTAs per SM.  Two things were measured to matter: the
+// number of resident warps, and the L1 that the shared-memory carve-out leaves for the scattered
+// table loads — the carve-out comes in steps, and the step that leaves 28 KB costs 15 % where
+// the ones that leave 60 KB or more cost 1 % or nothing.  Every (warps, CTAs) pair that fits is
+// scored as resident warps x that factor; 2 ring buffers per warp (a third is worth less than
+// the L1 it takes).  SGC_WARPS / SGC_STAGES / SGC_CTAS pin the choice (tuning only).
 StreamConfig pick_stream_config(uint32_t stage_bytes, size_t queue_bytes) {
   const size_t sm_budget = 227 * 1024;
+  const int pin_warps = env_int("SGC_WARPS", 0), pin_ctas = env_int("SGC_CTAS", 0);
+  const int stages = std::max(2, std::min(env_int("SGC_STAGES", 2), kMaxStages));
   StreamConfig best{};
-  const int want_warps = env_int("SGC_WARPS", 12), want_ctas = env_int("SGC_CTAS", 2);
-  const int want_stages = env_int("SGC_STAGES", 2);
-  for (int ctas = want_ctas; ctas >= 1 && !best.stages; --ctas) {
-    for (int stages = std::min(want_stages, kMaxStages); stages >= 2; --stages) {
-      StreamConfig c{want_warps, stages, ctas};
-      if (c.warps < 1 || c.warps > 12) c.warps = 12;
-      if ((stream_smem_bytes(c, stage_bytes, queue_bytes) + 1024) * ctas <= sm_budget) {
+  double best_score = 0;
+  for (int ctas = 2; ctas >= 1; --ctas) {
+    if (pin_ctas && ctas != pin_ctas) continue;
+    for (int warps = 12; warps >= 1; --warps) {
+      if (pin_warps >= 1 && pin_warps <= 12 && warps != pin_warps) continue;
+      const StreamConfig c{warps, stages, ctas};
+      const size_t total = (stream_smem_bytes(c, stage_bytes, queue_bytes) + 1024) * ctas;
+      if (total > sm_budget) continue;
+      // carve-out steps of sm_100: ... 132, 164, 196, 228 KB out of 256 KB
+      const double l1_factor = total <= 164 * 1024 ? 1.0 : (total <= 196 * 1024 ? 0.99 : 0.85);
+      const double score = warps * ctas * l1_factor;
+      if (score > best_score) {
+        best_score = score;
         best = c;
-        break;
       }
     }
   }
