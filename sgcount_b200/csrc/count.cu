@@ -104,16 +104,17 @@ __device__ __forceinline__ void flush_matched(const CountParams& p, uint32_t mat
 //
 // Skewed screens.  When one guide carries a large share of the reads, its atomics serialise on
 // ONE L2 address (about 1.4 G same-address REDs per second): measured on 50 M device-resident
-// reads, 1 % of the reads on one guide cost +29 %, 10 % made the kernel 5.7x slower, 90 % 35x.
-// Warp-level remedies were measured and rejected for the per-read path: grouping lanes with
-// MATCH.ANY costs 20 % of the kernel on ordinary data, and even a one-entry register cache of
-// the warp's hot guide (vote + popcount per step) costs 9 %, because any warp-collective
-// forces the lanes to reconverge between the table probe and the RED.  What is free on the
-// per-read path is to spread the atomics: sgc_counter_set_replicas(c, R) makes warp w count
-// into copy (w mod R) of the count vector, and fold_replicas_kernel adds the copies into the
-// state vector after the count kernel (measured with R = 16: -6 % on ordinary data, 4-6x
-// faster at 10-90 % skew).  It is off by default: through sgc_counter_submit the kernel hides
-// behind the host-to-device copy whatever the skew.
+// reads (tools/hot.py), 1 % of the reads on one guide cost +42 %, 10 % made the kernel 6.5x
+// slower, 90 % 41x.  Warp-level remedies were measured and rejected for the per-read path:
+// grouping lanes with MATCH.ANY costs 20 % of the kernel on ordinary data, and even a one-entry
+// register cache of the warp's hot guide (vote + popcount per step) costs 9 %, because any
+// warp-collective forces the lanes to reconverge between the table probe and the RED.  What is
+// nearly free on the per-read path is to spread the atomics: sgc_counter_set_replicas(c, R)
+// makes warp w count into copy (w mod R) of the count vector, and fold_replicas_kernel adds the
+// copies into the state vector after the count kernel (measured with R = 16: +2.5 % on ordinary
+// data, 1.15 ms instead of 5.1 ms at 10 % skew, 3.6 ms instead of 32 ms at 90 %).  It is off by
+// default: through sgc_counter_submit the kernel hides behind the host-to-device copy (69 ms
+// per 50 M reads) whatever the skew.
 template <int MODE>
 __device__ __forceinline__ void count_hit(const CountParams& p, unsigned long long* my_counts, int32_t hit,
                                           uint32_t& matched) {
