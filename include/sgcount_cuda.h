@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SGC_ABI_VERSION 1
+#define SGC_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------- */
 #define SGC_OK 0
@@ -43,6 +43,7 @@ extern "C" {
 #define SGC_ERR_EMPTY_READER 8       /* panic "empty reader", offsetter.rs:38 */
 #define SGC_ERR_TOO_MANY_GUIDES 9    /* more than SGC_MAX_GUIDES library sequences */
 #define SGC_ERR_BATCH_TOO_LARGE 10   /* a variable-length batch must stay below 4 GiB (u32 line offsets) */
+#define SGC_ERR_NCCL 11              /* libnccl.so.2 could not be loaded, or an NCCL call failed (sgc_reduce_counts) */
 
 #define SGC_MAX_GUIDES 4194302u
 #define SGC_MAX_K 30u
@@ -124,8 +125,10 @@ int sgc_offset_detect(const sgc_library*, const uint8_t* lines, uint64_t n_bytes
  * read shard of a sample.
  *
  * is_reverse/offset: the Offset (offsetter.rs:10-15).  position_recursion: !-p.
- * rc_mode: SGC_RC_*.  stream: the cudaStream_t every kernel of this counter runs on (NULL = the CUDA
- * default stream).
+ * rc_mode: SGC_RC_*.  stream: the cudaStream_t every kernel of this counter runs on; NULL = a
+ * stream of its own, created (blocking: ordered after earlier work on the legacy default stream)
+ * and destroyed with the counter, so that counters of concurrent samples neither serialise nor
+ * wait for each other.
  * d_state: optional device buffer of (n_guides + 2) uint64 owned by the caller — counts in
  * guide-index order, then total_reads, then matched_reads — so a collective (NCCL) can sum
  * shards in place; NULL = owned by the counter.  The buffer is zeroed by create.
@@ -147,13 +150,21 @@ int sgc_counter_submit_device(sgc_counter*, const uint8_t* d_lines, uint64_t n_b
                               const uint32_t* d_line_off, uint32_t stride, uint32_t read_len,
                               uint64_t n_reads, int32_t* d_assign_out);
 
-/* Skewed screens: count into `replicas` copies of the count vector (rounded down to a power of
- * two, at most 64 copies / 64 MB; 1 = off, the default), folded into the state vector after
- * every count launch.  Spreads the atomics of a guide that carries a large share of the reads
- * over several L2 addresses; see count.cu count_hit for the measurements. */
+/* Skewed screens.  The reference's fold (counter.rs:232-235) costs the same whatever the guide
+ * abundances; on the GPU a guide that carries a large share of the reads serialises its atomics
+ * on one L2 address.  By DEFAULT (replicas = 0) a counter looks at the first 65 536 reads of its
+ * first batch of >= 262 144 reads and, when a guide stands out, counts into 16 copies of the count
+ * vector (folded into the state vector after every launch) and keeps the guides with >= 1 % of
+ * the reads in registers; see count.cu count_hit / plan_skew for the measurements.  This call
+ * overrides the plan: 1 = never, >1 = that many copies (rounded down to a power of two, at most
+ * 64 copies / 64 MB), 0 = back to automatic.  The counts never depend on it. */
 int sgc_counter_set_replicas(sgc_counter*, uint32_t replicas);
 
 int sgc_counter_sync(sgc_counter*);
+/* Wait until all but the last `keep_in_flight` sgc_counter_submit calls have had their host
+ * buffers copied to the device (those buffers may be refilled), without waiting for the kernels
+ * that count them: with two buffers, refill one while the other's copy is still running. */
+int sgc_counter_wait_copies(sgc_counter*, uint32_t keep_in_flight);
 int sgc_counter_reset(sgc_counter*); /* zero the state vector */
 
 /* Wait, then copy out counts[n_guides] (guide-index order), total_reads, matched_reads
@@ -161,14 +172,28 @@ int sgc_counter_reset(sgc_counter*); /* zero the state vector */
  * maps index -> alias and sums indices that share one. */
 int sgc_counter_finish(sgc_counter*, uint64_t* counts, uint64_t* total, uint64_t* matched);
 
-/* Device pointer / length (in uint64 words) of the state vector, for the caller's collective. */
+/* Device pointer / length (in uint64 words) of the state vector, for the caller's collective
+ * (one process per GPU: torch.distributed / MPI / NCCL owned by the caller). */
 int sgc_counter_state(sgc_counter*, uint64_t** d_state, uint64_t* n_words);
+
+/* Read shards of ONE sample counted by several counters of THIS process (the reference collects
+ * its per-sample Counters at count.rs:136; a sample cut into read shards needs them summed):
+ * state[root] = sum over i of state[i], i.e. counts, total_reads and matched_reads of the whole
+ * sample land in shards[root]; the other shards' vectors are left unspecified (reset them before
+ * reuse).  Shards on different devices are summed with ONE ncclReduce(ncclUint64, ncclSum) of
+ * n_guides + 2 words over NVLink, each rank's call enqueued on its counter's own stream (libnccl.so.2
+ * is loaded on first use; communicators are cached per device set); shards that share a device
+ * are folded on that device first.  Asynchronous: sgc_counter_finish(shards[root]) waits for it.
+ * Every counter must come from a library of the same guides.  Errors: SGC_ERR_NCCL. */
+int sgc_reduce_counts(sgc_counter* const* shards, int n_shards, int root);
 
 /* Statistics of the last sgc_counter_submit_device call, for benchmarking. */
 typedef struct sgc_launch_info {
   uint32_t grid, block, smem_bytes;
   uint32_t kernel; /* 0 = streaming fixed-stride kernel, 1 = generic kernel */
   uint64_t launches_total;
+  uint32_t replicas;   /* copies of the count vector in use (1 = none) */
+  uint32_t hot_guides; /* guides counted in registers */
 } sgc_launch_info;
 int sgc_counter_launch_info(const sgc_counter*, sgc_launch_info* out);
 

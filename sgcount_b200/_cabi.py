@@ -24,6 +24,7 @@ ERR_NAN_ENTROPY = 7
 ERR_EMPTY_READER = 8
 ERR_TOO_MANY_GUIDES = 9
 ERR_BATCH_TOO_LARGE = 10
+ERR_NCCL = 11
 
 RC_BITTRICK = 0
 RC_KEEP_N = 1
@@ -57,6 +58,8 @@ class LaunchInfo(C.Structure):
         ("smem_bytes", C.c_uint32),
         ("kernel", C.c_uint32),
         ("launches_total", C.c_uint64),
+        ("replicas", C.c_uint32),
+        ("hot_guides", C.c_uint32),
     ]
 
 
@@ -80,6 +83,8 @@ SIGNATURES = {
     "sgc_counter_submit_device": (_int, [_vp, _vp, _u64, _vp, _u32, _u32, _u64, _vp]),
     "sgc_counter_set_replicas": (_int, [_vp, _u32]),
     "sgc_counter_sync": (_int, [_vp]),
+    "sgc_counter_wait_copies": (_int, [_vp, _u32]),
+    "sgc_reduce_counts": (_int, [C.POINTER(_vp), _int, _int]),
     "sgc_counter_reset": (_int, [_vp]),
     "sgc_counter_finish": (_int, [_vp, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "sgc_counter_state": (_int, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),
@@ -104,7 +109,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args
-        if lib.sgc_abi_version() != 1:
+        if lib.sgc_abi_version() != 2:
             raise ImportError("libsgcount_cuda.so ABI version mismatch")
         _lib = lib
     return _lib

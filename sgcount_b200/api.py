@@ -211,6 +211,15 @@ class Permuter:
         return self._handle.info()
 
 
+def reduce_counts(shards: Sequence["Counter"], root: int = 0) -> None:
+    """Sum of the read shards' count vectors into shards[root] (sgc_reduce_counts: NCCL across
+    devices, a fold kernel within one) — count.rs:136's collect for a sample cut into shards."""
+    arr = (C.c_void_p * len(shards))(*[c._ptr for c in shards])
+    check(_cabi.load().sgc_reduce_counts(arr, len(shards), int(root)))
+    for c in shards:
+        c._result = None
+
+
 def position_counts(reader: ReadBatch, device: int = 0) -> np.ndarray:
     """offsetter.rs:55-79 on the device -> uint32[size][4]"""
     lib = _cabi.load()
@@ -277,8 +286,12 @@ class Counter:
         self._result = None
 
     def set_replicas(self, replicas: int) -> None:
-        """spread the count atomics over `replicas` copies of the count vector (skewed screens)"""
+        """override the skew plan: 0 = automatic (default), 1 = never, >1 = that many copies of the
+        count vector"""
         check(_cabi.load().sgc_counter_set_replicas(self._ptr, int(replicas)))
+
+    def wait_copies(self, keep_in_flight: int = 0) -> None:
+        check(_cabi.load().sgc_counter_wait_copies(self._ptr, int(keep_in_flight)))
 
     def sync(self) -> None:
         check(_cabi.load().sgc_counter_sync(self._ptr))

@@ -27,7 +27,8 @@
 //    distance 1 of a member differs
 //    from it inside at most one part, so it agrees with the member on the COMPLEMENT of that
 //    part.  Seed i is that complement: directory i hashes the token with part i masked out to a
-//    bucket (start | count | tag) of postings (member key + guide index) sorted by bucket.  A
+//    bucket: its only posting inline, or (first | count) of a run of postings (member key + guide
+//    index) sorted by bucket.  A
 //    member at distance 1 whose difference lies in part i sits in list i; the member itself
 //    (distance 0) sits in all of them.  One window costs three directory loads plus about one
 //    posting load:

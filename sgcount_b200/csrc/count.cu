@@ -23,6 +23,9 @@
 // accumulated in registers and flushed once per warp.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <vector>
 
 #include "internal.h"
@@ -72,6 +75,8 @@ inline StreamGeom make_geom(uint32_t k, uint32_t read_len, int offset, bool with
   return g;
 }
 
+constexpr int kHotGuides = 4;
+
 struct CountParams {
   LibView lib;
   const uint8_t* lines;
@@ -85,43 +90,72 @@ struct CountParams {
   unsigned long long* rep;    // n_rep replicas of counts[n_guides] (see count_hit)
   uint32_t n_rep;             // power of two
   uint32_t n_guides;
+  int32_t hot[kHotGuides];    // MODE 4: guides counted in registers (-2 = unused slot), see count_hit
+  uint32_t off_base;          // line_off values are relative to lines - off_base (chunks of a host batch)
   int32_t* assign_out;
-  uint32_t debug;  // SGC_DEBUG bit mask (tuning only): 1 no count atomics, 2 no table probe, 4 no slow path
+  uint32_t debug;  // SGC_DEBUG bit mask (tuning build only): 1 no count atomics, 2 no table probe, 4 no slow path
   uint32_t zero;   // always 0, and unknown to the compiler: see the buffer hand-back in step A
   StreamGeom geom; // streaming kernel only
 };
 
 // MODE 0: production (no per-read output, no tuning switches); 1: also writes the per-read
-// assignment; 2: tuning build that honours SGC_DEBUG as well; 3: production with count replicas.
-__device__ __forceinline__ void flush_matched(const CountParams& p, uint32_t matched) {
+// assignment; 2: tuning build (-DSGC_TUNING) that honours SGC_DEBUG as well; 3: production with
+// count replicas; 4: replicas + the sample's hot guides counted in registers.
+struct HotCounts {
+  uint32_t c[kHotGuides];
+};
+
+template <int MODE>
+__device__ __forceinline__ void flush_matched(const CountParams& p, uint32_t matched, const HotCounts& hot) {
   matched = __reduce_add_sync(0xffffffffu, matched);
   if ((threadIdx.x & 31) == 0 && matched) atomicAdd(p.state + p.n_guides + 1, (unsigned long long)matched);
+  if (MODE == 4) {
+#pragma unroll
+    for (int j = 0; j < kHotGuides; ++j) {
+      const uint32_t h = __reduce_add_sync(0xffffffffu, hot.c[j]);
+      if ((threadIdx.x & 31) == 0 && h) atomicAdd(p.state + p.hot[j], (unsigned long long)h);
+    }
+  }
   // total_reads counts every record this launch walked (counter.rs:223-226)
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.state + p.n_guides, (unsigned long long)p.n_reads);
 }
 
 // Count update (counter.rs:232-235): one RED.64 per matched read, fire and forget, resolved in L2.
 //
-// Skewed screens.  When one guide carries a large share of the reads, its atomics serialise on
-// ONE L2 address (about 1.4 G same-address REDs per second): measured on 50 M device-resident
-// reads (tools/hot.py), 1 % of the reads on one guide cost +42 %, 10 % made the kernel 6.5x
-// slower, 90 % 41x.  Warp-level remedies were measured and rejected for the per-read path:
-// grouping lanes with MATCH.ANY costs 20 % of the kernel on ordinary data, and even a one-entry
-// register cache of the warp's hot guide (vote + popcount per step) costs 9 %, because any
-// warp-collective forces the lanes to reconverge between the table probe and the RED.  What is
-// nearly free on the per-read path is to spread the atomics: sgc_counter_set_replicas(c, R)
-// makes warp w count into copy (w mod R) of the count vector, and fold_replicas_kernel adds the
-// copies into the state vector after the count kernel (measured with R = 16: +2.5 % on ordinary
-// data, 1.15 ms instead of 5.1 ms at 10 % skew, 3.6 ms instead of 32 ms at 90 %).  It is off by
-// default: through sgc_counter_submit the kernel hides behind the host-to-device copy (69 ms
-// per 50 M reads) whatever the skew.
+// Skewed screens.  The reference's fold costs the same whatever the abundances are; here, when
+// one guide carries a large share of the reads, its atomics serialise on ONE L2 address (about
+// 1.4 G same-address REDs per second): measured on 50 M device-resident reads (tools/hot.py),
+// 1 % of the reads on one guide cost +42 %, 10 % made the plain kernel 6.5x slower, 90 % 41x.
+// Warp-level remedies were measured and rejected for the per-read path: grouping lanes with
+// MATCH.ANY costs 20 % of the kernel on ordinary data, and even a one-entry register cache of the
+// warp's hot guide found by vote + popcount costs 9 %, because any warp-collective forces the lanes
+// to reconverge between the table probe and the RED.  Two things are nearly free per read:
+//   replicas (MODE 3)  warp w counts into copy (w mod R) of the count vector; fold_replicas_kernel
+//                      adds the copies into the state vector after the count kernel (R = 16: +2.5 %
+//                      on ordinary data, 1.15 ms instead of 5.1 ms at 10 % skew);
+//   hot guides (MODE 4) up to four guide indices known BEFORE the launch are compared per lane and
+//                      counted in a register each (no vote: the lane just skips its RED), flushed
+//                      once per warp.
+// Which of them a counter uses is decided from a sample of its first batch (plan_skew below), so
+// the caller does nothing; sgc_counter_set_replicas overrides the decision.
 template <int MODE>
 __device__ __forceinline__ void count_hit(const CountParams& p, unsigned long long* my_counts, int32_t hit,
-                                          uint32_t& matched) {
+                                          uint32_t& matched, HotCounts& hot) {
   if (hit >= 0) {
     ++matched;
-    // without replicas the base is the kernel parameter itself (a uniform register)
-    if (MODE != 2 || !(p.debug & 1u)) atomicAdd((MODE == 3 ? my_counts : p.state) + hit, 1ull);
+    if (MODE == 4) {
+      bool is_hot = false;
+#pragma unroll
+      for (int j = 0; j < kHotGuides; ++j) {
+        const bool h = hit == p.hot[j];
+        hot.c[j] += h;
+        is_hot |= h;
+      }
+      if (!is_hot) atomicAdd(my_counts + hit, 1ull);
+    } else {
+      // without replicas the base is the kernel parameter itself (a uniform register)
+      if (MODE != 2 || !(p.debug & 1u)) atomicAdd((MODE == 3 ? my_counts : p.state) + hit, 1ull);
+    }
   }
 }
 
@@ -158,6 +192,7 @@ __device__ __forceinline__ uint8_t complement_byte(uint8_t c, int rc_mode) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
   uint32_t matched = 0;
+  HotCounts hot{};
   const uint64_t policy = l2_evict_last_policy();
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
   const int k = (int)p.lib.k;
@@ -170,7 +205,7 @@ __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
       uint64_t start;
       int n;
       if (p.line_off) {
-        start = p.line_off[r];
+        start = p.line_off[r] - p.off_base;
         n = (int)(p.line_off[r + 1] - p.line_off[r]) - 1;
       } else {
         start = r * p.stride;
@@ -210,9 +245,9 @@ __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
       }
       if (p.assign_out) p.assign_out[r] = hit;
     }
-    count_hit<3>(p, my_counts, hit, matched);
+    count_hit<4>(p, my_counts, hit, matched, hot);
   }
-  flush_matched(p, matched);
+  flush_matched<4>(p, matched, hot);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -442,6 +477,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   const bool any_next = centered_again || g.try_plus;
 
   uint32_t matched = 0;
+  HotCounts hot{};
   unsigned long long* my_counts = p.rep + (size_t)(gwarp & (p.n_rep - 1)) * p.n_guides;
   uint32_t qn = 0;  // parked reads (warp-uniform)
   int s = 0;
@@ -471,7 +507,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   // a read is settled: its assignment (tests), its guide's counter
   auto settle = [&](int32_t hit, uint32_t ridx) {
     if ((MODE == 1 || MODE == 2) && p.assign_out) p.assign_out[ridx] = hit;
-    count_hit<MODE>(p, my_counts, hit, matched);
+    count_hit<MODE>(p, my_counts, hit, matched, hot);
   };
   auto step_a = [&](Pending& pd) {
     mbar_wait(cur_bar, parity);
@@ -622,7 +658,59 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
     read_idx += read_step;
   }
   drain(true);
-  flush_matched(p, matched);
+  flush_matched<MODE>(p, matched, hot);
+}
+
+}  // namespace
+}  // namespace sgc
+
+// ------------------------------------------------------------------------------------------
+// skew plan: which guides (if any) carry a large share of a sample's reads
+// ------------------------------------------------------------------------------------------
+namespace sgc {
+namespace {
+
+struct TopGuides {
+  unsigned long long packed[kHotGuides];  // count << 32 | guide index, descending
+  unsigned long long matched;
+};
+
+// One block: the kHotGuides largest entries of counts[0..n).  Every thread keeps its own sorted
+// short list over a strided slice; the lists are merged through shared memory by thread 0
+// (n <= 4 M guides, 1024 threads: the merge walks 4096 candidates once).
+__global__ void __launch_bounds__(1024) top_guides_kernel(const unsigned long long* __restrict__ counts, uint32_t n,
+                                                         TopGuides* out) {
+  __shared__ unsigned long long cand[1024 * kHotGuides];
+  unsigned long long best[kHotGuides] = {};
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    unsigned long long v = counts[i];
+    if (v == 0) continue;
+    v = (v << 32) | i;
+#pragma unroll
+    for (int j = 0; j < kHotGuides; ++j)
+      if (v > best[j]) {
+        const unsigned long long t = best[j];
+        best[j] = v;
+        v = t;
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < kHotGuides; ++j) cand[threadIdx.x * kHotGuides + j] = best[j];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long top[kHotGuides] = {};
+    for (uint32_t c = 0; c < blockDim.x * kHotGuides; ++c) {
+      unsigned long long v = cand[c];
+      for (int j = 0; j < kHotGuides; ++j)
+        if (v > top[j]) {
+          const unsigned long long t = top[j];
+          top[j] = v;
+          v = t;
+        }
+    }
+    for (int j = 0; j < kHotGuides; ++j) out->packed[j] = top[j];
+    out->matched = counts[n + 1];
+  }
 }
 
 }  // namespace
@@ -631,37 +719,31 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
 // ------------------------------------------------------------------------------------------
 // sgc_counter
 // ------------------------------------------------------------------------------------------
-struct sgc_counter {
-  const sgc_library* lib = nullptr;
-  int is_reverse = 0;
-  uint32_t offset = 0;
-  int recursion = 1;
-  int rc_mode = SGC_RC_BITTRICK;
-  cudaStream_t stream = nullptr;
-  unsigned long long* d_state = nullptr;
-  bool own_state = false;
-  unsigned long long* d_rep = nullptr;  // n_rep x n_guides words, zero between launches
-  uint32_t n_rep = 1;
-  // host-batch staging (sgc_counter_submit)
-  cudaStream_t copy_stream = nullptr;
-  uint8_t* d_stage[2] = {nullptr, nullptr};
-  uint32_t* d_stage_off[2] = {nullptr, nullptr};
-  size_t stage_cap = 0, stage_off_cap = 0;
-  cudaEvent_t copy_done[2] = {nullptr, nullptr}, kernel_done[2] = {nullptr, nullptr};
-  uint64_t chunks_submitted = 0;
-  sgc_launch_info last{};
-};
-
 using namespace sgc;
 
 namespace {
 
 constexpr size_t kChunkBytes = 64ull << 20;
 constexpr uint64_t kChunkAlignReads = 256;  // chunk starts stay 16-byte aligned for any stride
+constexpr uint64_t kSkewSampleReads = 65536;   // reads of the first batch the skew plan looks at
+constexpr uint64_t kSkewMinBatch = 4 * kSkewSampleReads;  // smaller first batches are not worth a plan
 
+// Tuning switches (SGC_DEBUG, SGC_WARPS, SGC_CTAS, SGC_STAGES, SGC_CARVEOUT, SGC_REPLICAS) exist only
+// in the tuning build (make tuning: -DSGC_TUNING -> libsgcount_cuda_tuning.so); the production
+// library never reads them.  SGC_MAX_LAUNCH_TILES is the one variable both builds honour: it only
+// changes how a batch is cut into launches (the tests use it to exercise the launch splitting
+// without 2^30 reads), never what is counted.
+#ifdef SGC_TUNING
 int env_int(const char* name, int fallback) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : fallback;
+}
+#else
+constexpr int env_int(const char*, int fallback) { return fallback; }
+#endif
+long long env_ll(const char* name, long long fallback) {
+  const char* v = getenv(name);
+  return v && *v ? atoll(v) : fallback;
 }
 
 CountParams make_params(const sgc_counter* c, const uint8_t* d_lines, const uint32_t* d_off, uint32_t stride,
@@ -681,6 +763,7 @@ CountParams make_params(const sgc_counter* c, const uint8_t* d_lines, const uint
   p.rep = c->n_rep > 1 ? c->d_rep : c->d_state;
   p.n_rep = c->n_rep;
   p.n_guides = c->lib->n;
+  for (int j = 0; j < kHotGuides; ++j) p.hot[j] = c->hot[j];
   p.assign_out = d_assign;
   p.debug = (uint32_t)env_int("SGC_DEBUG", 0);
   p.geom = make_geom(c->lib->k, read_len, (int)c->offset, c->lib->with_perm, c->is_reverse != 0, c->recursion != 0,
@@ -699,7 +782,7 @@ size_t stream_smem_bytes(const StreamConfig& c, uint32_t stage_bytes, size_t que
 // table loads — the carve-out comes in steps, and the step that leaves 28 KB costs 15 % where
 // the ones that leave 60 KB or more cost 1 % or nothing.  Every (warps, CTAs) pair that fits is
 // scored as resident warps x that factor; 2 ring buffers per warp (a third is worth less than
-// the L1 it takes).  SGC_WARPS / SGC_STAGES / SGC_CTAS pin the choice (tuning only).
+// the L1 it takes).  SGC_WARPS / SGC_STAGES / SGC_CTAS pin the choice (tuning build only).
 StreamConfig pick_stream_config(uint32_t stage_bytes, size_t queue_bytes) {
   const size_t sm_budget = 227 * 1024;
   const int pin_warps = env_int("SGC_WARPS", 0), pin_ctas = env_int("SGC_CTAS", 0);
@@ -725,16 +808,48 @@ StreamConfig pick_stream_config(uint32_t stage_bytes, size_t queue_bytes) {
   return best;
 }
 
+// The opt-in shared-memory limit of a kernel is a per-device, process-wide attribute: it is
+// raised ONCE per (device, kernel) to the most any launch can ask for, never per launch — two
+// counters with different read lengths on two host threads would otherwise lower it under each
+// other between the set and the launch.
+constexpr int kMaxOptinSmem = 227 * 1024;
+int ensure_smem_optin(int device, const void* kernel) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({device, kernel})) return SGC_OK;
+  SGC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmem));
+  done.insert({device, kernel});
+  return SGC_OK;
+}
+
+using StreamKernel = void (*)(const CountParams, uint32_t, int, uint32_t);
+#ifdef SGC_TUNING
+#define SGC_TUNING_KERNEL(NW, WIDE) count_stream_kernel<NW, WIDE, 2>
+#else
+#define SGC_TUNING_KERNEL(NW, WIDE) nullptr
+#endif
+#define SGC_FAMILY(NW, WIDE)                                                                               \
+  {                                                                                                        \
+    count_stream_kernel<NW, WIDE, 0>, count_stream_kernel<NW, WIDE, 1>, SGC_TUNING_KERNEL(NW, WIDE),       \
+        count_stream_kernel<NW, WIDE, 3>, count_stream_kernel<NW, WIDE, 4>                                 \
+  }
+const StreamKernel kStreamKernels[4][5] = {SGC_FAMILY(4, false), SGC_FAMILY(5, false), SGC_FAMILY(6, true),
+                                           SGC_FAMILY(8, true)};
+
 // Enqueue the kernels for one device-resident batch.
-int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const uint32_t* d_off, uint32_t stride,
-                 uint32_t read_len, uint64_t n_reads, int32_t* d_assign, cudaStream_t stream) {
+int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const uint32_t* d_off, uint32_t off_base,
+                 uint32_t stride, uint32_t read_len, uint64_t n_reads, int32_t* d_assign, cudaStream_t stream) {
   if (n_reads == 0) return SGC_OK;
   CountParams p = make_params(c, d_lines, d_off, stride, read_len, d_assign);
+  p.off_base = off_base;
   uint64_t done = 0;
   const uint64_t launches_before = c->last.launches_total;
   c->last = sgc_launch_info{};
   c->last.launches_total = launches_before;
   c->last.kernel = 1;
+  c->last.replicas = c->n_rep;
+  for (int j = 0; j < kHotGuides; ++j) c->last.hot_guides += c->hot[j] >= 0;
   // streaming kernel: fixed stride, 16-byte aligned base, whole warp tiles, < 2^32 reads per
   // launch, and a Centered window that fits (otherwise every read fails its first trim)
   const uint32_t tile_bytes = kWarpReads * stride;
@@ -751,27 +866,23 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
   // whole tiles only, and never a bulk copy that would run past n_bytes; one launch handles at
   // most 2^30 reads (the queue words keep a 30-bit read index)
   uint64_t tiles_left = stageable && cfg.stages ? std::min(n_reads / kWarpReads, n_bytes / tile_bytes) : 0;
-  const uint64_t max_tiles = (1ull << kReadIdxBits) / kWarpReads - 65536;
+  uint64_t max_tiles = (1ull << kReadIdxBits) / kWarpReads - 65536;
+  if (const long long cap = env_ll("SGC_MAX_LAUNCH_TILES", 0); cap > 0) max_tiles = std::min<uint64_t>(max_tiles, cap);
+  const bool any_hot = c->last.hot_guides > 0;
   while (tiles_left > 0) {
     const uint64_t n_wtiles = std::min(tiles_left, max_tiles);
-    // replicas are a production feature: with a per-read output or tuning switches the counts go
-    // straight to the state vector (p.rep == p.state then, see make_params)
-    const int mode = p.debug ? 2 : (d_assign ? 1 : (c->n_rep > 1 ? 3 : 0));
-    using Kernel = void (*)(const CountParams, uint32_t, int, uint32_t);
-    static const Kernel kernels[4][4] = {
-        {count_stream_kernel<4, false, 0>, count_stream_kernel<4, false, 1>, count_stream_kernel<4, false, 2>,
-         count_stream_kernel<4, false, 3>},
-        {count_stream_kernel<5, false, 0>, count_stream_kernel<5, false, 1>, count_stream_kernel<5, false, 2>,
-         count_stream_kernel<5, false, 3>},
-        {count_stream_kernel<6, true, 0>, count_stream_kernel<6, true, 1>, count_stream_kernel<6, true, 2>,
-         count_stream_kernel<6, true, 3>},
-        {count_stream_kernel<8, true, 0>, count_stream_kernel<8, true, 1>, count_stream_kernel<8, true, 2>,
-         count_stream_kernel<8, true, 3>}};
-    Kernel kernel = kernels[family][mode];
+    // replicas and hot guides are production features: with a per-read output or tuning switches
+    // the counts go straight to the state vector
+    int mode = d_assign ? 1 : (any_hot ? 4 : (c->n_rep > 1 ? 3 : 0));
+    if (p.debug) mode = 2;
+    StreamKernel kernel = kStreamKernels[family][mode];
     const size_t smem = stream_smem_bytes(cfg, stage_bytes, queue_bytes);
-    SGC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (const int carve = env_int("SGC_CARVEOUT", -1); carve >= 0)  // tuning: shared-memory share of the L1, percent
+    int rc = ensure_smem_optin(c->lib->device, (const void*)kernel);
+    if (rc) return rc;
+#ifdef SGC_TUNING
+    if (const int carve = env_int("SGC_CARVEOUT", -1); carve >= 0)  // shared-memory share of the L1, percent
       SGC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+#endif
     uint64_t grid = (uint64_t)c->lib->sm_count * cfg.ctas_per_sm;  // persistent: every CTA resident
     const uint64_t ctas_needed = (n_wtiles + cfg.warps - 1) / cfg.warps;
     if (grid > ctas_needed) grid = ctas_needed;
@@ -780,6 +891,10 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
     q.assign_out = d_assign ? d_assign + done : nullptr;
     q.n_reads = n_wtiles * kWarpReads;
     q.first_read = 0;
+    if (mode == 1 || mode == 2) {  // counts go straight to the state vector
+      q.rep = q.state;
+      q.n_rep = 1;
+    }
     kernel<<<(unsigned)grid, cfg.warps * 32, smem, stream>>>(q, (uint32_t)n_wtiles, cfg.stages, stage_bytes);
     SGC_CUDA_TRY(cudaGetLastError());
     done += n_wtiles * kWarpReads;
@@ -810,6 +925,78 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
     c->last.launches_total += 1;
   }
   return SGC_OK;
+}
+
+int alloc_replicas(sgc_counter* c, uint32_t replicas) {
+  // a power of two, at most 64 copies and 64 MB
+  uint32_t n_rep = 1;
+  while (n_rep * 2 <= replicas && n_rep < 64 && (size_t)n_rep * 2 * c->lib->n * sizeof(uint64_t) <= (64u << 20))
+    n_rep *= 2;
+  if (n_rep == c->n_rep) return SGC_OK;
+  SGC_CUDA_TRY(cudaStreamSynchronize(c->stream));  // the replicas are zero between launches
+  cudaFree(c->d_rep);
+  c->d_rep = nullptr;
+  c->n_rep = 1;
+  if (n_rep > 1) {
+    SGC_CUDA_TRY(cudaMalloc(&c->d_rep, (size_t)n_rep * c->lib->n * sizeof(uint64_t)));
+    SGC_CUDA_TRY(cudaMemsetAsync(c->d_rep, 0, (size_t)n_rep * c->lib->n * sizeof(uint64_t), c->stream));
+    c->n_rep = n_rep;
+  }
+  return SGC_OK;
+}
+
+// Skew plan of a counter, made once, from the first kSkewSampleReads reads of its first large
+// batch: they are counted into a scratch vector with the plain kernel, the four most frequent
+// guides are read back, and
+//   top share >= 1/256  -> 16 count replicas (or as many as 64 MB hold);
+//   every guide with a share >= 1 % is counted in registers (count_hit, MODE 4).
+// Costs one small launch and one stream synchronisation per counter (= per sample or sample
+// shard).  The counts do not depend on the plan.
+int plan_skew(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const uint32_t* d_off, uint32_t off_base,
+              uint32_t stride, uint32_t read_len, uint64_t n_reads, cudaStream_t stream) {
+  c->skew_planned = true;
+  const uint64_t sample = std::min<uint64_t>(n_reads, kSkewSampleReads);
+  const size_t words = (size_t)c->lib->n + 2;
+  unsigned long long* d_scratch = nullptr;
+  TopGuides* d_top = nullptr;
+  SGC_CUDA_TRY(cudaMalloc(&d_scratch, words * sizeof(uint64_t) + sizeof(TopGuides)));
+  struct Free {
+    void* p;
+    ~Free() { cudaFree(p); }
+  } free_scratch{d_scratch};
+  d_top = reinterpret_cast<TopGuides*>(d_scratch + words);
+  SGC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, words * sizeof(uint64_t), stream));
+  unsigned long long* const state = c->d_state;
+  const sgc_launch_info last = c->last;
+  c->d_state = d_scratch;
+  const uint64_t sample_bytes = d_off ? n_bytes : std::min<uint64_t>(n_bytes, sample * stride);
+  int rc = launch_count(c, d_lines, sample_bytes, d_off, off_base, stride, read_len, sample, nullptr, stream);
+  c->d_state = state;
+  c->last = last;
+  if (rc) return rc;
+  top_guides_kernel<<<1, 1024, 0, stream>>>(d_scratch, c->lib->n, d_top);
+  SGC_CUDA_TRY(cudaGetLastError());
+  TopGuides top;
+  SGC_CUDA_TRY(cudaMemcpyAsync(&top, d_top, sizeof top, cudaMemcpyDeviceToHost, stream));
+  SGC_CUDA_TRY(cudaStreamSynchronize(stream));
+  const uint64_t top_count = top.packed[0] >> 32;
+  if (top_count * 256 < sample) return SGC_OK;  // no guide stands out
+  rc = alloc_replicas(c, 16);
+  if (rc) return rc;
+  int n_hot = 0;
+  for (int j = 0; j < kHotGuides; ++j)
+    if ((top.packed[j] >> 32) * 100 >= sample) c->hot[n_hot++] = (int32_t)(uint32_t)top.packed[j];
+  return SGC_OK;
+}
+
+// launch_count preceded, for the counter's first large batch, by the skew plan
+int count_batch(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const uint32_t* d_off, uint32_t off_base,
+                uint32_t stride, uint32_t read_len, uint64_t n_reads, int32_t* d_assign, cudaStream_t stream) {
+  if (c->auto_skew && !c->skew_planned && !d_assign && n_reads >= kSkewMinBatch) {
+    int rc = plan_skew(c, d_lines, n_bytes, d_off, off_base, stride, read_len, n_reads, stream);
+    if (rc) return rc;
+  }
+  return launch_count(c, d_lines, n_bytes, d_off, off_base, stride, read_len, n_reads, d_assign, stream);
 }
 
 int check_batch(const sgc_counter* c, const uint8_t* lines, uint64_t n_bytes, const uint32_t* line_off,
@@ -844,13 +1031,23 @@ int sgc_counter_create(const sgc_library* lib, int is_reverse, uint32_t offset, 
   c->offset = offset;
   c->recursion = position_recursion != 0;
   c->rc_mode = rc_mode;
+  for (int j = 0; j < kHotGuides; ++j) c->hot[j] = -2;
   struct Cleanup {
     sgc_counter* c;
     ~Cleanup() {
       if (c) sgc_counter_destroy(c);
     }
   } cleanup{c};
-  c->stream = (cudaStream_t)stream;  // NULL is the CUDA default stream
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    // The counter's own stream: counters of concurrent samples on one device neither serialise
+    // their kernels nor wait for each other in sgc_counter_sync.  A BLOCKING stream, so that work
+    // the caller queued on the legacy default stream before a submit (a memcpy, a generator
+    // kernel) is still ordered before the counter's kernels, as it was with stream = NULL.
+    SGC_CUDA_TRY(cudaStreamCreate(&c->stream));
+    c->own_stream = true;
+  }
   const size_t words = (size_t)lib->n + 2;
   if (d_state) {
     c->d_state = reinterpret_cast<unsigned long long*>(d_state);
@@ -859,8 +1056,8 @@ int sgc_counter_create(const sgc_library* lib, int is_reverse, uint32_t offset, 
     c->own_state = true;
   }
   SGC_CUDA_TRY(cudaMemsetAsync(c->d_state, 0, words * sizeof(uint64_t), c->stream));
-  const int want_rep = env_int("SGC_REPLICAS", 1);  // tuning override of sgc_counter_set_replicas
-  if (want_rep > 1) {
+  const int want_rep = env_int("SGC_REPLICAS", 0);  // tuning build: override of sgc_counter_set_replicas
+  if (want_rep > 0) {
     int rc = sgc_counter_set_replicas(c, (uint32_t)want_rep);
     if (rc) return rc;
   }
@@ -883,8 +1080,11 @@ void sgc_counter_destroy(sgc_counter* c) {
     if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
     if (c->kernel_done[i]) cudaEventDestroy(c->kernel_done[i]);
   }
+  for (cudaEvent_t e : c->copy_tickets) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->free_tickets) cudaEventDestroy(e);
   cudaFree(c->d_rep);
   if (c->own_state) cudaFree(c->d_state);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
@@ -893,7 +1093,7 @@ int sgc_counter_submit_device(sgc_counter* c, const uint8_t* d_lines, uint64_t n
   int rc = check_batch(c, d_lines, n_bytes, d_line_off, stride, read_len, n_reads);
   if (rc) return rc;
   DeviceGuard guard(c->lib->device);
-  return launch_count(c, d_lines, n_bytes, d_line_off, stride, read_len, n_reads, d_assign_out, c->stream);
+  return count_batch(c, d_lines, n_bytes, d_line_off, 0, stride, read_len, n_reads, d_assign_out, c->stream);
 }
 
 int sgc_counter_submit(sgc_counter* c, const uint8_t* lines, uint64_t n_bytes, const uint32_t* line_off,
@@ -963,42 +1163,57 @@ int sgc_counter_submit(sgc_counter* c, const uint8_t* lines, uint64_t n_bytes, c
                                    c->copy_stream));
     SGC_CUDA_TRY(cudaEventRecord(c->copy_done[b], c->copy_stream));
     SGC_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->copy_done[b], 0));
-    // offsets stay relative to the batch start: shift the line base instead of rewriting them
-    const uint8_t* d_lines = line_off ? c->d_stage[b] - byte0 : c->d_stage[b];
-    rc = launch_count(c, d_lines, bytes, line_off ? c->d_stage_off[b] : nullptr, stride, read_len, r1 - r0, nullptr,
-                      c->stream);
+    // the chunk's offsets stay what they were in the batch: the kernel subtracts the chunk's base
+    rc = count_batch(c, c->d_stage[b], bytes, line_off ? c->d_stage_off[b] : nullptr, (uint32_t)(line_off ? byte0 : 0),
+                     stride, read_len, r1 - r0, nullptr, c->stream);
     if (rc) return rc;
     SGC_CUDA_TRY(cudaEventRecord(c->kernel_done[b], c->stream));
     c->chunks_submitted += 1;
     r0 = r1;
   }
+  // ticket of this call's copies (sgc_counter_wait_copies)
+  cudaEvent_t ticket = nullptr;
+  if (!c->free_tickets.empty()) {
+    ticket = c->free_tickets.back();
+    c->free_tickets.pop_back();
+  } else {
+    SGC_CUDA_TRY(cudaEventCreateWithFlags(&ticket, cudaEventDisableTiming));
+  }
+  c->copy_tickets.push_back(ticket);
+  SGC_CUDA_TRY(cudaEventRecord(ticket, c->copy_stream));
   return SGC_OK;
 }
 
 int sgc_counter_set_replicas(sgc_counter* c, uint32_t replicas) {
   if (!c) return set_error(SGC_ERR_INVALID_ARG, "counter is NULL");
   DeviceGuard guard(c->lib->device);
-  // a power of two, at most 64 copies and 64 MB
-  uint32_t n_rep = 1;
-  while (n_rep * 2 <= replicas && n_rep < 64 && (size_t)n_rep * 2 * c->lib->n * sizeof(uint64_t) <= (64u << 20))
-    n_rep *= 2;
-  if (n_rep == c->n_rep) return SGC_OK;
-  SGC_CUDA_TRY(cudaStreamSynchronize(c->stream));  // the replicas are zero between launches
-  cudaFree(c->d_rep);
-  c->d_rep = nullptr;
-  c->n_rep = 1;
-  if (n_rep > 1) {
-    SGC_CUDA_TRY(cudaMalloc(&c->d_rep, (size_t)n_rep * c->lib->n * sizeof(uint64_t)));
-    SGC_CUDA_TRY(cudaMemsetAsync(c->d_rep, 0, (size_t)n_rep * c->lib->n * sizeof(uint64_t), c->stream));
-    c->n_rep = n_rep;
+  if (replicas == 0) {  // back to the automatic plan, made again on the next large batch
+    c->auto_skew = true;
+    c->skew_planned = false;
+    for (int j = 0; j < kHotGuides; ++j) c->hot[j] = -2;
+    return alloc_replicas(c, 1);
   }
-  return SGC_OK;
+  c->auto_skew = false;
+  for (int j = 0; j < kHotGuides; ++j) c->hot[j] = -2;
+  return alloc_replicas(c, replicas);
 }
 
 int sgc_counter_sync(sgc_counter* c) {
   if (!c) return set_error(SGC_ERR_INVALID_ARG, "counter is NULL");
   DeviceGuard guard(c->lib->device);
   SGC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return SGC_OK;
+}
+
+int sgc_counter_wait_copies(sgc_counter* c, uint32_t keep_in_flight) {
+  if (!c) return set_error(SGC_ERR_INVALID_ARG, "counter is NULL");
+  DeviceGuard guard(c->lib->device);
+  while (c->copy_tickets.size() > keep_in_flight) {
+    cudaEvent_t ticket = c->copy_tickets.front();
+    SGC_CUDA_TRY(cudaEventSynchronize(ticket));
+    c->copy_tickets.pop_front();
+    c->free_tickets.push_back(ticket);
+  }
   return SGC_OK;
 }
 

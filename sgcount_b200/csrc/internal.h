@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <deque>
 #include <string>
+#include <vector>
 
 #include "../../include/sgcount_cuda.h"
 #include "common.cuh"
@@ -42,6 +44,35 @@ int position_counts_device(const uint8_t* d_lines, const uint32_t* d_line_off, u
                            cudaStream_t stream);
 
 }  // namespace sgc
+
+struct sgc_library;
+
+struct sgc_counter {
+  const sgc_library* lib = nullptr;
+  int is_reverse = 0;
+  uint32_t offset = 0;
+  int recursion = 1;
+  int rc_mode = SGC_RC_BITTRICK;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  unsigned long long* d_state = nullptr;
+  bool own_state = false;
+  // skew plan (count.cu plan_skew): replicas of the count vector and guides counted in registers
+  unsigned long long* d_rep = nullptr;  // n_rep x n_guides words, zero between launches
+  uint32_t n_rep = 1;
+  int32_t hot[4] = {-2, -2, -2, -2};
+  bool auto_skew = true, skew_planned = false;
+  // host-batch staging (sgc_counter_submit)
+  cudaStream_t copy_stream = nullptr;
+  uint8_t* d_stage[2] = {nullptr, nullptr};
+  uint32_t* d_stage_off[2] = {nullptr, nullptr};
+  size_t stage_cap = 0, stage_off_cap = 0;
+  cudaEvent_t copy_done[2] = {nullptr, nullptr}, kernel_done[2] = {nullptr, nullptr};
+  uint64_t chunks_submitted = 0;
+  std::deque<cudaEvent_t> copy_tickets;   // one per sgc_counter_submit call whose copies may still run
+  std::vector<cudaEvent_t> free_tickets;
+  sgc_launch_info last{};
+};
 
 struct sgc_library {
   int device = 0;

@@ -4,14 +4,12 @@
 // Replaces /root/reference/src/library.rs:17-99 and permutes.rs:47-158.  The reference's
 // stateful insert algorithm is order independent in its observable effect:
 // a token that is not a library member resolves iff exactly ONE library sequence lies at
-// Hamming distance 1.  The build below realises that directly and in parallel:
-//   1. pack every guide 2-bit, reject bytes outside A,C,G,T                    (pack_library)
-//   2. insert the guides as `library member` slots, detect duplicates          (insert_exact)
-//   3. insert the 3k ACGT variants of every guide; a variant whose key already
-//      belongs to a member is dropped, one that meets a different parent is
-//      marked AMBIG in place                                                    (insert_variants)
-// Variants with an 'N' are not stored: a read window with one N is answered by four member
-// probes (common.cuh window_lookup), which is exactly the set of parents of that token.
+// Hamming distance 1.  Nothing but the n members is stored (common.cuh): the build packs every
+// guide 2-bit in both orientations (pack_library), sorts the members into the three seed lists
+// of each orientation (seed_count / scan / seed_fill / seed_dir), fills the front tables
+// (front_insert), and then asks the finished index for duplicates (duplicate_check) and for the
+// Permuter's map / null sizes (variant_stats).  Variants — with or without an 'N' — are never
+// materialised: a window is resolved against the members at lookup time (lookup_token).
 #include <algorithm>
 #include <cstdio>
 #include <string>
@@ -505,8 +503,7 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   } cleanup{lib};
   SGC_CUDA_TRY(cudaDeviceGetAttribute(&lib->sm_count, cudaDevAttrMultiProcessorCount, device));
 
-  // each directory has a power of two of buckets, at least four per member (<= 2^24, so the 8
-  // tag bits fit below the bucket bits of the 32-bit hash)
+  // each directory has a power of two of buckets, at least four per member (<= 2^24)
   uint32_t dir_bits = 8;
   while (((uint64_t)1 << dir_bits) < 4ull * n) ++dir_bits;
   lib->dir_shift = 32 - dir_bits;
@@ -543,9 +540,16 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   BuildStatus st0{0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0};
   SGC_CUDA_TRY(cudaMemcpy(d_st.p, &st0, sizeof st0, cudaMemcpyHostToDevice));
 
-  cudaEvent_t e0, e1;
-  SGC_CUDA_TRY(cudaEventCreate(&e0));
-  SGC_CUDA_TRY(cudaEventCreate(&e1));
+  struct Events {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } events;
+  SGC_CUDA_TRY(cudaEventCreate(&events.a));
+  SGC_CUDA_TRY(cudaEventCreate(&events.b));
+  const cudaEvent_t e0 = events.a, e1 = events.b;
   SGC_CUDA_TRY(cudaEventRecord(e0, 0));
   pack_library_kernel<<<blocks_for(n, 256), 256>>>(d_seqs.p, n, k, lib->wide, lib->ix[0].d_keys, lib->ix[1].d_keys,
                                                    d_st.p);
@@ -562,8 +566,6 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   SGC_CUDA_TRY(cudaEventSynchronize(e1));
   float ms = 0;
   SGC_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
 
   BuildStatus st;
   SGC_CUDA_TRY(cudaMemcpy(&st, d_st.p, sizeof st, cudaMemcpyDeviceToHost));

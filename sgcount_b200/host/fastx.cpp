@@ -154,6 +154,11 @@ class GzSource : public ByteSource {
       if (it != cand_.end() && *it == pos_) {
         const size_t j = (size_t)(it - cand_.begin());
         std::unique_lock<std::mutex> lk(mu_);
+        // candidates the chain stepped over were coincidences: whatever they inflated to is dropped
+        for (size_t skipped = consumer_at_; skipped < j; ++skipped) {
+          Bytes().swap(jobs_[skipped].out);
+          jobs_[skipped].block = SeqBlock();
+        }
         consumer_at_ = j;
         cv_work_.notify_all();
         cv_done_.wait(lk, [&] { return jobs_[j].done; });
@@ -296,12 +301,15 @@ class GzSource : public ByteSource {
           free_blocks_.pop_back();
         }
       }
-      // size hint: ISIZE of a member that ends where the next candidate starts
+      // size hint: ISIZE of a member that ends where the next candidate starts.  If this or the
+      // next candidate is a coincidence inside compressed data those four bytes are noise: the hint
+      // is capped at 64x the compressed size (DEFLATE of sequence data stays far below that)
       const size_t nxt = j + 1 < cand_.size() ? cand_[j + 1] : size_;
       if (nxt >= cand_[j] + 18) {
         uint32_t isize;
         memcpy(&isize, data_ + nxt - 4, 4);
-        if (isize < (1u << 30)) out.reserve((size_t)isize + 1024);
+        const size_t cap = 64 * (nxt - cand_[j]);
+        if (isize < (1u << 30)) out.reserve(std::min<size_t>(isize, cap) + 1024);
       }
       size_t end = 0;
       bool ok = false, framed = false;
@@ -322,12 +330,14 @@ class GzSource : public ByteSource {
       }
       {
         std::lock_guard<std::mutex> lk(mu_);
+        // a failed candidate, or one the consumer has already stepped over, keeps no buffer
+        if (j < consumer_at_) ok = framed = false;
+        if (ok) jobs_[j].out = std::move(out);
         if (framed) {
           jobs_[j].framed = true;
           jobs_[j].block = std::move(block);
           jobs_[j].end_state = std::move(framer.st);
         }
-        jobs_[j].out = std::move(out);
         jobs_[j].end = end;
         jobs_[j].ok = ok;
         jobs_[j].done = true;

@@ -8,8 +8,10 @@
 //
 // Differences from the reference, all documented in DESIGN.md: rows are written in library-file
 // order (the reference iterates a randomly seeded HashMap); a library byte outside A,C,G,T is an
-// error; `-t` sets the number of samples processed concurrently (one host pipeline + one CUDA
-// stream each), `--gpus` spreads them over devices.
+// error; `-t` sets the number of samples processed concurrently (one host pipeline and one CUDA
+// stream per counter each), `--gpus` spreads the samples over devices and, when there are fewer
+// samples than devices, cuts every sample into read shards over gpus / samples devices whose
+// count vectors are summed with sgc_reduce_counts (NCCL).
 #include <atomic>
 #include <chrono>
 #include <cstdarg>
@@ -57,6 +59,7 @@ struct Args {
   unsigned long subsample = 5000;
   unsigned threads = 1;
   int gpus = 1, device = 0;
+  unsigned read_shards = 0;     // counters per sample; 0 = gpus / samples (at least 1)
   unsigned ingest_threads = 0;  // inflate threads per sample; 0 = hardware threads / concurrent samples
   bool timing = false;
   int rc_mode = SGC_RC_BITTRICK;
@@ -78,7 +81,8 @@ const char* kUsage =
     "  -t, --threads <THREADS>                Number of Threads to Use for Parallel Jobs [default: 1]\n"
     "  -q, --quiet                            Does not show progress\n"
     "  -z, --include-zero                     Include zero count sgRNAs in output table\n"
-    "      --gpus <N>                         Spread the samples over N devices [default: 1]\n"
+    "      --gpus <N>                         Spread the samples (and, with fewer samples than devices, read shards of each sample) over N devices [default: 1]\n"
+    "      --read-shards <N>                  Cut every sample into N read shards, dealt round the devices and summed with an NCCL reduce [default: gpus / samples]\n"
     "      --device <D>                       First device to use [default: 0]\n"
     "      --ingest-threads <N>               Threads inflating the gzip members of one sample [default: cores / samples in flight]\n"
     "      --rc-keep-n                        Reverse complement keeps N (default: the fxread bit trick, N -> J)\n"
@@ -120,6 +124,7 @@ Args parse_args(int argc, char** argv) {
     else if (f == "-q" || f == "--quiet") a.quiet = true;
     else if (f == "-z" || f == "--include-zero") a.include_zero = true;
     else if (f == "--gpus") a.gpus = (int)parse_uint(f, value());
+    else if (f == "--read-shards") a.read_shards = (unsigned)parse_uint(f, value());
     else if (f == "--device") a.device = (int)parse_uint(f, value());
     else if (f == "--ingest-threads") a.ingest_threads = (unsigned)parse_uint(f, value());
     else if (f == "--rc-keep-n") a.rc_mode = SGC_RC_KEEP_N;
@@ -192,6 +197,7 @@ std::unordered_map<std::string, std::string> load_genemap(const std::string& pat
   std::unordered_map<std::string, std::string> map;
   std::string line;
   while (std::getline(in, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();  // for_byte_line strips "\r\n" too (genemap.rs:55)
     const size_t tab = line.find('\t');
     if (tab == std::string::npos) fail("Missing '\\t' in gene map");
     std::string sgrna = line.substr(tab + 1);
@@ -293,21 +299,36 @@ std::string to_string(const OffsetValue& o) {
   return std::string(o.reverse ? "Reverse(" : "Forward(") + std::to_string(o.index) + ")";
 }
 
-// entropy_offset for one sample (offsetter.rs:192-200): the first `subsample` records
-OffsetValue detect_offset(const sgc_library* lib, const std::string& path, unsigned long subsample) {
-  sgh::FastxReader reader(path);
+// The first `subsample` records of a sample, read ONCE: validate_library_size looks at the first
+// (count.rs:62-71) and entropy_offset at all of them (offsetter.rs:192-200).
+struct SampleHead {
   std::vector<uint8_t> lines;
   std::vector<uint32_t> off{0};
+  size_t first_len = 0;
+  bool any = false;  // the file holds at least one record
+};
+SampleHead read_head(const std::string& path, unsigned long records) {
+  SampleHead h;
+  sgh::FastxReader reader(path);
   const char *id, *seq;
   size_t id_len, seq_len;
-  for (unsigned long i = 0; i < subsample && reader.next(id, id_len, seq, seq_len); ++i) {
-    lines.insert(lines.end(), seq, seq + seq_len);
-    lines.push_back('\n');
-    off.push_back((uint32_t)lines.size());
+  for (unsigned long i = 0; i < std::max(records, 1ul) && reader.next(id, id_len, seq, seq_len); ++i) {
+    if (i == 0) {
+      h.first_len = seq_len;
+      h.any = true;
+    }
+    if (i >= records) break;
+    h.lines.insert(h.lines.end(), seq, seq + seq_len);
+    h.lines.push_back('\n');
+    h.off.push_back((uint32_t)h.lines.size());
   }
+  return h;
+}
+
+OffsetValue detect_offset(const sgc_library* lib, const SampleHead& h) {
   int rev = 0;
   uint32_t idx = 0;
-  check(sgc_offset_detect(lib, lines.data(), lines.size(), off.data(), 0, 0, off.size() - 1, &rev, &idx));
+  check(sgc_offset_detect(lib, h.lines.data(), h.lines.size(), h.off.data(), 0, 0, h.off.size() - 1, &rev, &idx));
   return OffsetValue{rev != 0, idx};
 }
 
@@ -317,40 +338,56 @@ struct SampleResult {
   // where the counting thread spent its time (--timing): waiting for the inflate threads,
   // copying sequence lines into pinned memory, in sgc_counter_submit / sync / finish
   double wait_s = 0, copy_s = 0, submit_s = 0;
+  unsigned shards = 1;  // counters (devices) the sample's reads were spread over
 };
 
-// count_sample (count.rs:15-45): parse on this thread into two pinned buffers; the copy and
-// the kernel of one batch overlap the parsing of the next.
-SampleResult count_sample(const sgc_library* lib, uint32_t n_guides, const std::string& path, OffsetValue offset,
-                          bool recursion, int rc_mode, unsigned ingest_threads) {
-  sgc_counter* c = nullptr;
-  check(sgc_counter_create(lib, offset.reverse, offset.index, recursion, rc_mode, nullptr, nullptr, &c));
-  struct Guard {
-    sgc_counter* c;
+// count_sample (count.rs:15-45).  The inflate threads hand over blocks of sequence lines in file
+// order; this thread packs them into pinned batches and submits them.  With several devices the
+// batches of the ONE sample go round the devices (read shards, each its own counter, stream and
+// pair of pinned buffers) and the shard vectors are summed into the first device's at the end
+// (sgc_reduce_counts: one NCCL reduce of n_guides + 2 words) — the reference never splits a
+// sample; its per-sample Counters are simply collected (count.rs:136).
+SampleResult count_sample(const std::vector<const sgc_library*>& libs, uint32_t n_guides, const std::string& path,
+                          OffsetValue offset, bool recursion, int rc_mode, unsigned ingest_threads) {
+  struct Lane {
+    sgc_counter* c = nullptr;
     Batch b[2];
+    int cur = 0;
+    bool used = false;
+  };
+  struct Guard {
+    std::vector<Lane> lanes;
     ~Guard() {
-      sgc_counter_destroy(c);
-      for (auto& x : b)
-        if (x.lines) sgc_host_free(x.lines);
+      for (auto& l : lanes) {
+        sgc_counter_destroy(l.c);
+        for (auto& x : l.b)
+          if (x.lines) sgc_host_free(x.lines);
+      }
     }
-  } g{c, {}};
+  } g;
+  g.lanes.resize(libs.size());
+  for (size_t d = 0; d < libs.size(); ++d)
+    check(sgc_counter_create(libs[d], offset.reverse, offset.index, recursion, rc_mode, nullptr, nullptr, &g.lanes[d].c));
   // blocks of packed sequence lines, framed by the inflate threads (fastx.h); they start
   // inflating while the pinned buffers are being allocated
   sgh::SeqBlockReader reader(path, ingest_threads);
   const size_t cap = 64u << 20;
-  for (auto& b : g.b) {
-    void* p = nullptr;
-    check(sgc_host_alloc(&p, cap));
-    b.lines = static_cast<uint8_t*>(p);
-    b.cap = cap;
-    b.reset();
-  }
+  auto ready = [&](Lane& l) {  // the pinned buffers of a lane, on first use
+    if (l.b[0].lines) return;
+    for (auto& b : l.b) {
+      void* p = nullptr;
+      check(sgc_host_alloc(&p, cap));
+      b.lines = static_cast<uint8_t*>(p);
+      b.cap = cap;
+      b.reset();
+    }
+  };
   sgh::SeqBlock blk;
-  int cur = 0;
-  bool other_in_flight = false;
+  size_t d = 0;
   SampleResult r;
   using Clock = std::chrono::steady_clock;
   auto since = [](Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); };
+  ready(g.lanes[0]);
   for (;;) {
     auto t0 = Clock::now();
     const bool more = reader.next(blk);
@@ -359,24 +396,38 @@ SampleResult count_sample(const sgc_library* lib, uint32_t n_guides, const std::
     uint64_t rec = 0;
     size_t byte = 0;
     for (;;) {
+      Lane& l = g.lanes[d];
       t0 = Clock::now();
-      const bool done = g.b[cur].append(blk, rec, byte);
+      const bool done = l.b[l.cur].append(blk, rec, byte);
       r.copy_s += since(t0);
       if (done) break;
-      if (g.b[cur].n == 0) fail("a sequence line longer than %zu bytes", cap);
+      if (l.b[l.cur].n == 0) fail("a sequence line longer than %zu bytes", cap);
       t0 = Clock::now();
-      submit(c, g.b[cur]);
-      cur ^= 1;
-      if (other_in_flight) check(sgc_counter_sync(c));  // the buffer we are about to refill has been consumed
+      submit(l.c, l.b[l.cur]);
+      l.used = true;
+      l.cur ^= 1;
+      // the buffer about to be refilled was handed over one submit ago: its copy must have
+      // finished, the copy just queued (and every kernel) may still be running
+      check(sgc_counter_wait_copies(l.c, 1));
+      l.b[l.cur].reset();
+      d = (d + 1) % g.lanes.size();  // the next batch goes to the next device
+      ready(g.lanes[d]);
       r.submit_s += since(t0);
-      other_in_flight = true;
-      g.b[cur].reset();
     }
   }
   auto t0 = Clock::now();
-  submit(c, g.b[cur]);
+  for (auto& l : g.lanes)
+    if (l.b[0].lines && l.b[l.cur].n) {
+      submit(l.c, l.b[l.cur]);
+      l.used = true;
+    }
+  std::vector<sgc_counter*> shards;
+  for (auto& l : g.lanes)
+    if (l.used || &l == &g.lanes[0]) shards.push_back(l.c);
+  r.shards = (unsigned)shards.size();
+  if (shards.size() > 1) check(sgc_reduce_counts(shards.data(), (int)shards.size(), 0));
   r.counts.resize(n_guides);
-  check(sgc_counter_finish(c, r.counts.data(), &r.total, &r.matched));
+  check(sgc_counter_finish(shards[0], r.counts.data(), &r.total, &r.matched));
   r.submit_s += since(t0);
   return r;
 }
@@ -409,13 +460,12 @@ int main(int argc, char** argv) {
       for (const auto& alias : hlib.aliases)  // count.rs:90-95
         if (!genemap.count(alias)) fail("Missing sgRNA aliases in gene map: \"%s\"", alias.c_str());
     }
-    // validate_library_size (count.rs:62-71)
-    for (const auto& p : args.input_paths) {
-      sgh::FastxReader r(p);
-      const char *id, *seq;
-      size_t id_len, seq_len;
-      if (!r.next(id, id_len, seq, seq_len)) fail("empty reader: %s", p.c_str());
-      if (hlib.k > seq_len)
+    // validate_library_size (count.rs:62-71); the same records feed the offset detector below
+    std::vector<SampleHead> heads(n_samples);
+    for (size_t i = 0; i < n_samples; ++i) {
+      heads[i] = read_head(args.input_paths[i], args.have_offset ? 0 : args.subsample);
+      if (!heads[i].any) fail("empty reader: %s", args.input_paths[i].c_str());
+      if (hlib.k > heads[i].first_len)
         fail("Sequences in reference library are larger than the sequences in input.\n\nConsider reducing the length of "
              "your reference sequences (i.e. extracting the variable region of the sgRNA or reducing the length of the "
              "adapters.)");
@@ -444,7 +494,7 @@ int main(int argc, char** argv) {
     if (args.have_offset) {
       for (auto& o : offsets) o = OffsetValue{args.reverse, (uint32_t)args.offset};  // main.rs:163-170
     } else {
-      for (size_t s = 0; s < n_samples; ++s) offsets[s] = detect_offset(libs[0], args.input_paths[s], args.subsample);
+      for (size_t s = 0; s < n_samples; ++s) offsets[s] = detect_offset(libs[0], heads[s]);
       if (!args.quiet) {
         std::string msg = "Calculated Offsets: [";
         for (size_t s = 0; s < n_samples; ++s) msg += (s ? ", " : "") + to_string(offsets[s]);
@@ -458,7 +508,11 @@ int main(int argc, char** argv) {
     std::atomic<size_t> next{0};
     std::mutex err_mu;
     std::string first_error;
+    heads.clear();
     const unsigned workers = (unsigned)std::min<size_t>(std::max(args.threads, (unsigned)gpus), n_samples);
+    // fewer samples than devices: every sample is cut into read shards over `per_sample` devices
+    const size_t per_sample =
+        args.read_shards ? args.read_shards : (n_samples < (size_t)gpus ? (size_t)gpus / n_samples : 1);
     const unsigned ingest_threads =
         args.ingest_threads ? args.ingest_threads : std::max(1u, std::thread::hardware_concurrency() / workers);
     auto work = [&]() {
@@ -466,7 +520,9 @@ int main(int argc, char** argv) {
         const size_t s = next.fetch_add(1);
         if (s >= n_samples) return;
         try {
-          results[s] = count_sample(libs[s % gpus], hlib.n, args.input_paths[s], offsets[s], !args.no_position_recursion,
+          std::vector<const sgc_library*> sample_libs;
+          for (size_t j = 0; j < per_sample; ++j) sample_libs.push_back(libs[(s * per_sample + j) % gpus]);
+          results[s] = count_sample(sample_libs, hlib.n, args.input_paths[s], offsets[s], !args.no_position_recursion,
                                     args.rc_mode, ingest_threads);
           if (!args.quiet) {
             const SampleResult& r = results[s];
@@ -490,11 +546,16 @@ int main(int argc, char** argv) {
       const double count_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_count0).count();
       unsigned long long reads = 0;
       double wait_s = 0, copy_s = 0, submit_s = 0;
-      for (const auto& r : results) reads += r.total, wait_s += r.wait_s, copy_s += r.copy_s, submit_s += r.submit_s;
+      unsigned max_shards = 1;
+      for (const auto& r : results) {
+        reads += r.total, wait_s += r.wait_s, copy_s += r.copy_s, submit_s += r.submit_s;
+        max_shards = std::max(max_shards, r.shards);
+      }
       fprintf(stderr, "{\"count_s\": %.6f, \"reads\": %llu, \"samples\": %zu, \"sample_workers\": %u, "
-              "\"ingest_threads\": %u, \"gpus\": %d, \"wait_inflate_s\": %.6f, \"copy_to_pinned_s\": %.6f, "
-              "\"submit_sync_s\": %.6f, \"read_inputs_s\": %.3f, \"device_tables_s\": %.3f, \"offsets_s\": %.3f}\n",
-              count_s, reads, n_samples, workers, ingest_threads, gpus, wait_s, copy_s, submit_s, t_inputs,
+              "\"ingest_threads\": %u, \"gpus\": %d, \"read_shards_per_sample\": %u, \"wait_inflate_s\": %.6f, "
+              "\"copy_to_pinned_s\": %.6f, \"submit_sync_s\": %.6f, \"read_inputs_s\": %.3f, "
+              "\"device_tables_s\": %.3f, \"offsets_s\": %.3f}\n",
+              count_s, reads, n_samples, workers, ingest_threads, gpus, max_shards, wait_s, copy_s, submit_s, t_inputs,
               t_tables - t_inputs, t_offsets - t_tables);
     }
 

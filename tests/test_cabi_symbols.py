@@ -25,7 +25,7 @@ def test_library_exports_every_symbol():
     lib = _cabi.load()
     for name in header_symbols():
         assert getattr(lib, name) is not None
-    assert lib.sgc_abi_version() == 1
+    assert lib.sgc_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_gpu():

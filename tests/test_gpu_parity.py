@@ -15,6 +15,7 @@ from helpers import make_library, make_reads, oracle_library
 
 pytestmark = pytest.mark.gpu
 
+ACGT_BYTES = np.frombuffer(b"ACGT", dtype=np.uint8)
 FIXTURES = ["sequence", "zero.sequence", "diff.sequence", "offset", "offset_clipped"]
 
 
@@ -270,3 +271,159 @@ def test_randomised_geometries_match_oracle():
         assert np.array_equal(got[0], want[0]), label
         assert np.array_equal(got[1], want[1]) and got[2:4] == want[2:4], label
         assert got[4].kernel == (1 if variable else 0), label
+
+
+# ---- skew plan, launch splitting, read shards ------------------------------------------------
+
+def _skewed_sample(rng, guides, n_reads, share, offset=5, read_len=75):
+    """n_reads reads drawn from 20 000 distinct ones, `share` of them carrying guide 7 exactly"""
+    base = make_reads(rng, guides, 20000, read_len, offset)
+    hot = base[0][:offset] + guides[7] + base[0][offset + len(guides[7]):]
+    pick = rng.integers(0, len(base), n_reads)
+    is_hot = rng.random(n_reads) < share
+    return [hot if h else base[i] for h, i in zip(is_hot, pick)]
+
+
+@pytest.mark.parametrize("share", [0.0, 0.1, 0.9])
+def test_skew_plan_is_automatic_and_does_not_change_the_table(share):
+    """counter.rs:232-235 costs the same whatever the abundances; here a counter samples its first
+    batch and, when a guide stands out, spreads the atomics (16 replicas) and keeps the guides
+    with >= 1 % of the reads in registers.  No caller action; same table as the oracle."""
+    import torch
+
+    rng = np.random.default_rng(77)
+    guides = make_library(rng, 3000, 20)
+    seqs = _skewed_sample(rng, guides, 600_000, share)
+    library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+    permuter = sg.Permuter.new(library)
+    want = oracle_count(guides, seqs, True, sg.Offset.Forward(5), n_threads=os.cpu_count() or 4)
+    batch = sg.ReadBatch.from_seqs(seqs)
+    d = torch_dev(np.concatenate([batch.lines, np.zeros(64, np.uint8)]))
+    c = sg.Counter(library, permuter, sg.Offset.Forward(5))
+    for rounds in (1, 2):
+        c.submit_device(d.data_ptr(), batch.lines.nbytes, len(batch), batch.stride, batch.read_len)
+        counts, total, matched = c.finish()
+        assert np.array_equal(counts, rounds * want[1]) and (total, matched) == (rounds * want[2], rounds * want[3])
+    info = c.launch_info()
+    if share == 0.0:
+        assert (info.replicas, info.hot_guides) == (1, 0)
+    else:
+        assert info.replicas == 16 and info.hot_guides >= 1
+    # the host path plans on its first chunk as well
+    h = sg.Counter(library, permuter, sg.Offset.Forward(5))
+    h.submit(batch)
+    assert np.array_equal(h.finish()[0], want[1])
+    assert h.launch_info().replicas == info.replicas
+    # and the plan can be switched off
+    off = sg.Counter(library, permuter, sg.Offset.Forward(5))
+    off.set_replicas(1)
+    off.submit_device(d.data_ptr(), batch.lines.nbytes, len(batch), batch.stride, batch.read_len)
+    assert np.array_equal(off.finish()[0], want[1]) and off.launch_info().replicas == 1
+
+
+def test_a_batch_is_cut_into_several_launches(monkeypatch):
+    """count.cu cuts a batch into launches of at most 2^30 - 2 M reads (the parked-read queue
+    keeps a 30-bit read index); SGC_MAX_LAUNCH_TILES lowers the cap so the splitting runs here:
+    57 tiles of 32 reads per launch over 50 021 reads = 28 streaming launches + the remainder."""
+    rng = np.random.default_rng(8)
+    guides = make_library(rng, 800, 20)
+    seqs = make_reads(rng, guides, 50_021, 75, 5)
+    library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+    permuter = sg.Permuter.new(library)
+    want = oracle_count(guides, seqs, True, sg.Offset.Forward(5))
+    monkeypatch.setenv("SGC_MAX_LAUNCH_TILES", "57")
+    batch = sg.ReadBatch.from_seqs(seqs)
+    got = gpu_assign(library, permuter, batch, sg.Offset.Forward(5), pad=64)
+    assert got[4].launches_total == -(-(50_021 // 32) // 57) + 1
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2:4] == want[2:4]
+    c = sg.Counter(library, permuter, sg.Offset.Forward(5))  # production mode, host path
+    c.submit(batch)
+    assert np.array_equal(c.finish()[0], want[1])
+
+
+def test_reduce_counts_of_read_shards_on_one_device():
+    """sgc_reduce_counts: three read shards of one sample, three counters, summed into shard 1"""
+    rng = np.random.default_rng(12)
+    guides = make_library(rng, 600, 20)
+    seqs = make_reads(rng, guides, 9000, 75, 5)
+    library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+    permuter = sg.Permuter.new(library)
+    want = oracle_count(guides, seqs, True, sg.Offset.Forward(5))
+    shards = []
+    for part in (seqs[:2000], seqs[2000:2001], seqs[2001:]):
+        c = sg.Counter(library, permuter, sg.Offset.Forward(5))
+        c.submit(sg.ReadBatch.from_seqs(part))
+        shards.append(c)
+    sg.reduce_counts(shards, root=1)
+    counts, total, matched = shards[1].finish()
+    assert np.array_equal(counts, want[1]) and (total, matched) == (want[2], want[3])
+    with pytest.raises(sg.SgcError):
+        sg.reduce_counts([shards[0], shards[0]])
+
+
+def test_reduce_counts_across_devices_with_nccl():
+    """read shards on every device of the box, one ncclReduce of u64[n_guides + 2] to device 0"""
+    import torch
+
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two devices")
+    rng = np.random.default_rng(13)
+    guides = make_library(rng, 2000, 20)
+    seqs = make_reads(rng, guides, 40_000, 75, 5)
+    want = oracle_count(guides, seqs, True, sg.Offset.Forward(5))
+    cuts = np.linspace(0, len(seqs), 2 * n_dev + 1).astype(int)  # two shards per device: fold + NCCL
+    shards, keep = [], []
+    for i in range(2 * n_dev):
+        dev = i % n_dev
+        library = sg.Library(guides, [b"g%d" % j for j in range(len(guides))], device=dev)
+        permuter = sg.Permuter.new(library)
+        c = sg.Counter(library, permuter, sg.Offset.Forward(5))
+        c.submit(sg.ReadBatch.from_seqs(seqs[cuts[i]:cuts[i + 1]]))
+        shards.append(c)
+        keep.append((library, permuter))
+    for root in (0, 2 * n_dev - 1):
+        sg.reduce_counts(shards, root=root)
+        counts, total, matched = shards[root].finish()
+        assert np.array_equal(counts, want[1]) and (total, matched) == (want[2], want[3])
+        if root == 0:  # count everything again for the second root
+            for i, c in enumerate(shards):
+                c.reset()
+                c.submit(sg.ReadBatch.from_seqs(seqs[cuts[i]:cuts[i + 1]]))
+
+
+# ---- offset detector: ties ---------------------------------------------------------------------
+
+def test_offset_tie_goes_to_reverse_and_near_ties_follow_the_oracle():
+    """assign_offset (offsetter.rs:143-149) answers Forward only if min_f < min_r: an exact tie is
+    Reverse.  Palindromic reads give a positional histogram that equals its own mirror image, so
+    every forward window has a reversed twin with the same MSE bit for bit."""
+    rng = np.random.default_rng(99)
+    guides = make_library(rng, 300, 12)
+    library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+    olib, lib_recs = oracle_library(guides)
+    half = ACGT_BYTES[rng.integers(0, 4, (4000, 20))]
+    # skew the composition by position so the entropy profile is not flat
+    for p in range(20):
+        mask = rng.random(4000) < 0.04 * p
+        half[mask, p] = ord("G")
+    pal = np.concatenate([half, half[:, ::-1]], axis=1)
+    seqs = [r.tobytes() for r in pal]
+    got = sg.entropy_offset(library, sg.ReadBatch.from_seqs(seqs), 5000)
+    want = orc.entropy_offset(lib_recs, orc.Records.from_seqs(seqs), 5000)
+    assert got.reverse and (got.reverse, got.index) == (want.reverse, want.index)
+    # near ties: break the symmetry by a handful of bases at one position inside the winning
+    # window of one direction (a one-count change decides Forward or Reverse; the oracle's answers
+    # on this grid are a mix of both)
+    outcomes = set()
+    for flips in (1, 2, 5, 25):
+        for col in (3, 8, 30, 36):
+            near = pal.copy()
+            rows = rng.choice(np.arange(1, 4000), flips, replace=False)
+            near[rows, col] = np.where(near[rows, col] == ord("G"), ord("C"), ord("G"))
+            seqs = [r.tobytes() for r in near]
+            got = sg.entropy_offset(library, sg.ReadBatch.from_seqs(seqs), 5000)
+            want = orc.entropy_offset(lib_recs, orc.Records.from_seqs(seqs), 5000)
+            assert (got.reverse, got.index) == (want.reverse, want.index), (flips, col)
+            outcomes.add(want.reverse)
+    assert outcomes == {False, True}

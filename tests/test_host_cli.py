@@ -140,3 +140,81 @@ def test_reverse_reads_plain_fasta_and_multi_member_gzip(example_dir, tmp_path):
     head, rows = table(p.stdout)
     assert head == "Guide\tsequence\trev"  # utils.rs:24-28 strips .gz then .fa
     assert all(r.split("\t")[1] == r.split("\t")[2] for r in rows) and len(rows) == 100
+
+
+@pytest.mark.gpu
+def test_gene_map_with_crlf_line_ends(example_dir, tmp_path):
+    """genemap.rs:53-68 reads the map with bstr's for_byte_line, which strips "\\r\\n" as well as
+    "\\n": a gene map saved on Windows must give the same table as the original."""
+    lib = os.path.join(example_dir, "library.fasta.gz")
+    fq = os.path.join(example_dir, "sequence.fastq.gz")
+    g2s = os.path.join(example_dir, "g2s.txt")
+    crlf = tmp_path / "g2s_crlf.txt"
+    crlf.write_bytes(open(g2s, "rb").read().replace(b"\n", b"\r\n"))
+    want = run("-l", lib, "-i", fq, "-g", g2s, "-q", check=True).stdout
+    got = run("-l", lib, "-i", fq, "-g", str(crlf), "-q", check=True).stdout
+    assert got == want and "\r" not in got
+    # the oracle strips it too (oracle.cpp load_genemap): product and oracle agree
+    lib_recs = orc.Records.from_path(lib)
+    olib = orc.Library.from_reader(lib_recs)
+    reads = orc.Records.from_path(fq)
+    oc = orc.Counter.new(reads, olib, orc.Permuter.new(olib), orc.entropy_offset(lib_recs, reads, 5000))
+    text = orc.render_results([oc], ["sequence"], olib, crlf.read_bytes(), include_zero=False)
+    assert table(got) == table(text)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shards", [2, 5])
+def test_one_sample_cut_into_read_shards_gives_the_same_table(shards, tmp_path):
+    """--read-shards N: the batches of ONE sample are dealt to N counters and their vectors summed
+    with sgc_reduce_counts (on one device: the fold; across devices: NCCL).  Same table, same
+    totals, and the offset is detected once (offsetter.rs:192-200), not per shard."""
+    from sgcount_b200 import synth
+
+    seed = 0xB2000005
+    arr = synth.make_library(seed, 5000, 20)
+    lib_path = str(tmp_path / "lib.fa")
+    with open(lib_path, "wb") as f:
+        f.write(b"".join(b">lib.%d\n%s\n" % (i, arr[i].tobytes()) for i in range(len(arr))))
+    fq = str(tmp_path / "big.fastq.gz")
+    # 3.5 M reads = 266 MB of sequence lines: five 64 MB batches, so every shard gets work
+    synth.Sample(seed, 0, arr, 75, 11, True).write_fastq(fq, 0, 3_500_000, reads_per_member=400_000)
+    one = run("-l", lib_path, "-i", fq, "-o", str(tmp_path / "one.tsv"), check=True)
+    cut = run("-l", lib_path, "-i", fq, "-o", str(tmp_path / "cut.tsv"), "--read-shards", str(shards), "--timing", check=True)
+    assert open(tmp_path / "one.tsv").read() == open(tmp_path / "cut.tsv").read()
+    assert one.stderr.count("Calculated Offsets: [Reverse(11)]") == 1
+    assert cut.stderr.count("Calculated Offsets: [Reverse(11)]") == 1
+    fin = [l for l in one.stderr.splitlines() if l.startswith("Finished")]
+    assert fin and fin == [l for l in cut.stderr.splitlines() if l.startswith("Finished")]
+    assert '"read_shards_per_sample": %d' % shards in cut.stderr
+
+
+@pytest.mark.gpu
+def test_one_sample_over_every_device_with_nccl(tmp_path):
+    """config 5's partitioning through the product: one sample, --gpus = every device of the box"""
+    import torch
+
+    from sgcount_b200 import synth
+
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two devices")
+    seed = 0xB2000005
+    arr = synth.make_library(seed, 20000, 20)
+    lib_path = str(tmp_path / "lib.fa")
+    with open(lib_path, "wb") as f:
+        f.write(b"".join(b">lib.%d\n%s\n" % (i, arr[i].tobytes()) for i in range(len(arr))))
+    fq = str(tmp_path / "big.fastq.gz")
+    n_reads = 900_000 * n_dev
+    synth.Sample(seed, 0, arr, 75, 3, False).write_fastq(fq, 0, n_reads, reads_per_member=300_000)
+    one = run("-l", lib_path, "-i", fq, "-o", str(tmp_path / "one.tsv"), check=True)
+    many = run("-l", lib_path, "-i", fq, "-o", str(tmp_path / "many.tsv"), "--gpus", str(n_dev), "--timing", check=True)
+    assert open(tmp_path / "one.tsv").read() == open(tmp_path / "many.tsv").read()
+    assert '"read_shards_per_sample": %d' % n_dev in many.stderr
+    assert many.stderr.count("Calculated Offsets: [Forward(3)]") == 1
+    recs = orc.Records.from_path(fq)
+    lib_recs = orc.Records.from_path(lib_path)
+    olib = orc.Library.from_reader(lib_recs)
+    oc = orc.Counter.new(recs, olib, orc.Permuter.new(olib), orc.Offset.Forward(3), None, True, n_threads=os.cpu_count() or 4)
+    text = orc.render_results([oc], ["big"], olib, None, include_zero=False)
+    assert table(open(tmp_path / "many.tsv").read()) == table(text)

@@ -26,18 +26,27 @@ for frac in [float(x) for x in (sys.argv[1:] or ["0", "0.01", "0.1", "0.3", "0.9
         mask = torch.rand(N, device="cuda") < frac
         rows[mask] = hot
         del mask
-    counter = sg.Counter(library, permuter, sg.Offset.Forward(5))
-    for _ in range(2):
+    ref = None
+    for plan, replicas in (("auto", 0), ("off", 1), ("16 replicas", 16)):
+        counter = sg.Counter(library, permuter, sg.Offset.Forward(5))
+        counter.set_replicas(replicas)
+        t0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0[0].record()
+        counter.submit_device(d.data_ptr(), N * 76, N, 76, 75)  # the first launch carries the plan
+        t0[1].record()
         counter.submit_device(d.data_ptr(), N * 76, N, 76, 75)
-    torch.cuda.synchronize()
-    counter.reset()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(5):
-        counter.submit_device(d.data_ptr(), N * 76, N, 76, 75)
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 5
-    counts, total, matched = counter.finish()
-    print(f"hot fraction {frac:.2f}: {ms:.3f} ms  {N / ms / 1e6:.2f} Greads/s  frac={N * 76 / ms / 1e6 / 6547.2:.3f} "
-          f"max count share={counts.max() / max(total, 1):.3f}", flush=True)
+        torch.cuda.synchronize()
+        counter.reset()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            counter.submit_device(d.data_ptr(), N * 76, N, 76, 75)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        counts, total, matched = counter.finish()
+        li = counter.launch_info()
+        ref = counts if ref is None else ref
+        print(f"hot fraction {frac:.2f} plan={plan:<11} replicas={li.replicas} hot={li.hot_guides}: {ms:.3f} ms  "
+              f"{N / ms / 1e6:.2f} Greads/s  frac={N * 76 / ms / 1e6 / 6547.2:.3f}  first launch {t0[0].elapsed_time(t0[1]):.3f} ms  "
+              f"max count share={counts.max() / max(total, 1):.3f} same={bool((counts == ref).all())}", flush=True)

@@ -5,7 +5,14 @@ import itertools
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+# the switches below exist only in the tuning build of the C ABI (make -C sgcount_b200/csrc tuning)
+if not os.environ.get("SGC_CUDA_LIB"):
+    import subprocess
+
+    subprocess.run(["make", "-C", os.path.join(ROOT, "sgcount_b200", "csrc"), "tuning"], check=True, capture_output=True)
+    os.environ["SGC_CUDA_LIB"] = os.path.join(ROOT, "sgcount_b200", "lib", "libsgcount_cuda_tuning.so")
 import torch
 
 import sgcount_b200 as sg
