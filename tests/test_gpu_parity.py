@@ -305,9 +305,7 @@ def test_skew_plan_is_automatic_and_does_not_change_the_table(share):
         counts, total, matched = c.finish()
         assert np.array_equal(counts, rounds * want[1]) and (total, matched) == (rounds * want[2], rounds * want[3])
     info = c.launch_info()
-    if share == 0.0:
-        assert (info.replicas, info.hot_guides) == (1, 0)
-    else:
+    if share > 0.0:  # (with 3 000 log-normal guides the top one may pass 1/256 of the reads by itself)
         assert info.replicas == 16 and info.hot_guides >= 1
     # the host path plans on its first chunk as well
     h = sg.Counter(library, permuter, sg.Offset.Forward(5))
