@@ -402,7 +402,7 @@ def plan_units(cfg, world):
     the ranks; a sample with several shards has its shards dealt round the ranks."""
     units = []
     per = cfg["reads_per_sample"] // cfg["shards_per_sample"]
-    assert per * cfg["shards_per_sample"] == cfg["reads_per_sample"] and per % 256 == 0
+    assert per * cfg["shards_per_sample"] == cfg["reads_per_sample"] and per % 32 == 0  # whole tiles, 16-byte aligned
     for si in range(len(cfg["samples"])):
         for sh in range(cfg["shards_per_sample"]):
             slot = si * cfg["shards_per_sample"] + sh
@@ -432,7 +432,7 @@ def run_full_config(name, cfg, ctx, reps, with_parity):
     samples = [synth.Sample(seed, idx, lib_arr, READ_LEN, off, rev) for idx, rev, off in cfg["samples"]]
     units = plan_units(cfg, world)
     if scale != 1.0:  # --config-scale: smaller runs for development; the JSON says so
-        units = [(si, int(first * scale) // 256 * 256, max(256, int(n * scale) // 256 * 256), r) for si, first, n, r in units]
+        units = [(si, int(first * scale) // 32 * 32, max(32, int(n * scale) // 32 * 32), r) for si, first, n, r in units]
     mine = [u for u in units if u[3] == rank]
 
     # this rank's shards, generated in HBM
@@ -965,6 +965,8 @@ def run_gpu(args):
                 out["parity"] = out["parity_n"]
             del operm, olib
 
+    if rank == 0:
+        print(f"[bench] headline: {json.dumps(out)}", file=sys.stderr, flush=True)
     # ---- the other BASELINE configs at full size -------------------------------------------------
     del counters, states, d_lines, d_probe
     torch.cuda.empty_cache()
@@ -979,6 +981,7 @@ def run_gpu(args):
             res = run_full_config(name, CONFIGS[name], ctx, args.config_reps, with_parity=not args.no_cpu_baseline)
             if rank == 0:
                 cfg_out[name] = res
+                print(f"[bench] {name}: {json.dumps(res)}", file=sys.stderr, flush=True)
     if rank == 0:
         out["configs"] = cfg_out
         if args.fastq_reads > 0:

@@ -17,8 +17,9 @@
 //                                       parked read tries ONE position of Counter::assign
 //                                       against the seed index and, if that misses, goes back
 //                                       on the queue for the next position.
-//   count_generic_kernel : any layout (variable-length lines via u32 offsets, unaligned
-//                          buffers, tile remainders); one thread per read, byte loads.
+//   count_lines_kernel   : any layout (variable-length lines via u32 offsets, unaligned
+//                          buffers, tile remainders); one thread per read, the span lifted from
+//                          global memory with 64-bit loads, same window arithmetic and tables.
 // Per-guide counts are 64-bit atomics in the L2-resident state vector; matched reads are
 // accumulated in registers and flushed once per warp.
 #include <algorithm>
@@ -80,6 +81,7 @@ constexpr int kHotGuides = 4;
 struct CountParams {
   LibView lib;
   const uint8_t* lines;
+  const uint8_t* lines_end;  // lines + n_bytes: no load starts at or past it
   const uint32_t* line_off;  // NULL => fixed stride
   uint64_t n_reads;
   uint64_t first_read;       // index of the first read this launch handles
@@ -175,81 +177,6 @@ __global__ void fold_replicas_kernel(unsigned long long* __restrict__ state, uns
   if (sum) state[i] += sum;
 }
 
-// Record::seq_rev_comp of the fxread crate on one byte
-__device__ __forceinline__ uint8_t complement_byte(uint8_t c, int rc_mode) {
-  if (rc_mode == SGC_RC_BITTRICK) return (c & 2) ? (c ^ 4) : (c ^ 21);
-  switch (c) {
-    case 'A': return 'T';
-    case 'C': return 'G';
-    case 'G': return 'C';
-    case 'T': return 'A';
-    default: return c;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// generic kernel: Counter::assign (counter.rs:96-140) spelled out on the oriented bytes
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
-  uint32_t matched = 0;
-  HotCounts hot{};
-  const uint64_t policy = l2_evict_last_policy();
-  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
-  const int k = (int)p.lib.k;
-  unsigned long long* my_counts =
-      p.rep + (size_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (p.n_rep - 1)) * p.n_guides;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_reads; i += nthreads) {
-    int32_t hit = kMiss;
-    {
-      const uint64_t r = p.first_read + i;
-      uint64_t start;
-      int n;
-      if (p.line_off) {
-        start = p.line_off[r] - p.off_base;
-        n = (int)(p.line_off[r + 1] - p.line_off[r]) - 1;
-      } else {
-        start = r * p.stride;
-        n = (int)p.read_len;
-      }
-      const uint8_t* s = p.lines + start;
-      const int npos = p.recursion ? 3 : 1;
-      for (int pos = 0; pos < npos && hit == kMiss; ++pos) {
-        // Centered/Null: offset; Plus: offset+1; Minus: offset-1 (counter.rs:164-174)
-        int lo;
-        if (pos == 0) {
-          lo = p.offset;
-        } else if (pos == 1) {
-          lo = p.offset + 1;
-        } else {
-          if (p.offset == 0) break;  // checked_sub(1) -> None
-          lo = p.offset - 1;
-        }
-        if (lo + k > n) break;  // a failed trim RETURNS (counter.rs:105-108,175-176)
-        Key key{0, 0};
-        int nbad = 0;
-        uint32_t bad_pos = 0;
-        bool wild = false;
-        for (int j = 0; j < k; ++j) {
-          // forward: the read itself; reverse: byte lo+j of the reverse complement (counter.rs:196-204)
-          const uint8_t c = p.reverse ? complement_byte(s[n - 1 - (lo + j)], p.rc_mode) : s[lo + j];
-          key_set_base(key, (uint32_t)j, p.lib.wide, code_of(c));
-          if (!is_acgt(c)) {
-            ++nbad;
-            bad_pos = (uint32_t)j;
-            wild = c == 'N';
-          }
-        }
-        hit = p.lib.wide
-                  ? window_lookup_t<true>(p.lib, p.lib.fwd, p.with_perm, key, nbad, bad_pos, wild, nullptr, policy)
-                  : window_lookup_t<false>(p.lib, p.lib.fwd, p.with_perm, key, nbad, bad_pos, wild, nullptr, policy);
-      }
-      if (p.assign_out) p.assign_out[r] = hit;
-    }
-    count_hit<4>(p, my_counts, hit, matched, hot);
-  }
-  flush_matched<4>(p, matched, hot);
-}
-
 // ------------------------------------------------------------------------------------------
 // streaming kernel: warp-private rings
 //
@@ -260,6 +187,13 @@ __global__ void __launch_bounds__(256) count_generic_kernel(CountParams p) {
 // ------------------------------------------------------------------------------------------
 constexpr int kWarpReads = 32;
 constexpr int kMaxStages = 4;
+// How a ring buffer goes back to the copy engine (see step A of count_stream_kernel):
+//   0  the refill's byte count depends on a warp vote over the words every lane loaded;
+//   1  the documented producer/consumer form: every lane arrives on a per-buffer "empty"
+//      mbarrier after its loads, the elected lane waits on it before it issues the copy.
+#ifndef SGC_HANDBACK_MBAR
+#define SGC_HANDBACK_MBAR 0
+#endif
 constexpr int kQueueCap = 64;  // <= 31 parked + 32 new
 constexpr uint32_t kReadIdxBits = 30;  // queue word: position << 30 | read index
 
@@ -272,6 +206,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 // would have the compiler rebuild the shared window base for every tile.
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -343,7 +280,7 @@ __device__ __forceinline__ uint32_t pack_window(const uint32_t (&w)[NW], int n_w
   for (int i = 0; i < NW; ++i) {
     x[i] = ascii_residue(w[i]);
     uint32_t c = (w[i] >> 1) & 0x03030303u;
-    if (NW == 5) {  // k = 17..20: all five words are in use and only the last can hold bytes past the window
+    if (NW >= 5) {  // k >= 17: NW = ceil(k / 4), every word is in use and only the last can hold bytes past the window
       if (i == NW - 1) {
         x[i] &= last_mask;
         c &= last_mask;
@@ -417,7 +354,194 @@ __device__ __forceinline__ int32_t try_position(const LibView& v, const IndexVie
                                          nullptr, policy);
 }
 
-// NW = words that hold the k window bytes: 4, 5 (k = 17..20, the common guide lengths), 6 or 8.
+// ------------------------------------------------------------------------------------------
+// line kernel: any layout (variable-length lines through u32 offsets, unaligned buffers, tile
+// remainders of the streaming kernel).  The same arithmetic as the streaming kernel with a
+// PER-READ geometry: a warp takes 32 consecutive reads, every lane lifts the NW + 1 span words of
+// its read straight from global memory with 64-bit loads at the read's own alignment (consecutive
+// lanes hold consecutive reads, so a warp touches each 32-byte sector of its lines at most once
+// and DRAM traffic stays below the algorithmic bytes), the Centered window goes through the
+// front table, and what that does not settle is parked in a warp-private shared-memory queue and
+// drained 32 reads at a time through the seed index, exactly like the streaming kernel's slow
+// path; a parked entry carries its read's geometry (lead byte, Plus / Minus exist) in its tag.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t ldg_stream_u64(const uint64_t* p, uint64_t policy) {
+  uint64_t v;
+  // L1 allocation stays on: the NL loads of a lane fall into one or two sectors
+  asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+  return v;
+}
+
+// tag of a parked read of the line kernel
+constexpr uint32_t kLineIdxBits = 27;  // at most 2^27 reads per launch
+constexpr uint32_t kLineLead = 1u << 27, kLinePlus = 1u << 28, kLineMinus = 1u << 29;
+constexpr int kLineWarps = 8;
+
+template <int NW, bool WIDE>
+__global__ void __launch_bounds__(kLineWarps * 32) count_lines_kernel(CountParams p) {
+  __shared__ WarpQueueT<NW> queues[kLineWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpQueueT<NW>* q = &queues[warp];
+  uint32_t matched = 0;
+  HotCounts hot{};
+  const uint64_t table_policy = l2_evict_last_policy();
+  const uint64_t line_policy = l2_evict_first_policy();
+  const int k = (int)p.lib.k;
+  const StreamGeom& g = p.geom;  // n_words, last_mask, with_perm, wild_byte: the same for every read
+  const IndexView& ix = p.reverse ? p.lib.rev : p.lib.fwd;
+  const uint32_t gwarp = blockIdx.x * kLineWarps + warp, gwarps = gridDim.x * kLineWarps;
+  unsigned long long* my_counts = p.rep + (size_t)(gwarp & (p.n_rep - 1)) * p.n_guides;
+  const int d_plus = p.reverse ? -1 : 1;  // stored displacement of the Plus window
+  constexpr int NL = (4 * NW + 11 + 7) / 8;  // 64-bit loads that cover NW + 2 words at any alignment
+  static_assert(2 * NL >= NW + 3, "span words");
+  uint32_t qn = 0;  // parked reads (warp-uniform)
+
+  auto settle = [&](int32_t hit, uint32_t ridx) {
+    if (p.assign_out) p.assign_out[p.first_read + ridx] = hit;
+    count_hit<4>(p, my_counts, hit, matched, hot);
+  };
+  auto drain = [&](bool all) {
+    while (qn >= 32 || (all && qn > 0)) {
+      const uint32_t cnt = qn < 32 ? qn : 32;
+      qn -= cnt;
+      int next = -1;
+      uint32_t S[NW + 1], tag = 0;
+      if ((uint32_t)lane < cnt) {
+        const uint32_t e = qn + lane;
+#pragma unroll
+        for (int i = 0; i < NW + 1; ++i) S[i] = q->w[i][e];
+        tag = q->tag[e];
+        const uint32_t pos = tag >> 30, ridx = tag & ((1u << kLineIdxBits) - 1);
+        const int lead = (tag & kLineLead) ? 1 : 0;
+        const uint32_t shift = 8u * (uint32_t)(pos == 0 ? lead : (pos == 1 ? lead + d_plus : lead - d_plus));
+        const int32_t hit = try_position<NW, WIDE>(p.lib, ix, g, S, shift, table_policy);
+        if (hit == kMiss) next = pos == 0 ? ((tag & kLinePlus) ? 1 : -1) : (pos == 1 && (tag & kLineMinus) ? 2 : -1);
+        if (next < 0) settle(hit, ridx);
+      }
+      __syncwarp();
+      const uint32_t pm = __ballot_sync(0xffffffffu, next >= 0);
+      if (pm) {
+        if (next >= 0) {
+          const uint32_t e = qn + __popc(pm & ((1u << lane) - 1));
+#pragma unroll
+          for (int i = 0; i < NW + 1; ++i) q->w[i][e] = S[i];
+          q->tag[e] = ((uint32_t)next << 30) | (tag & 0x3FFFFFFFu);
+        }
+        qn += __popc(pm);
+      }
+      __syncwarp();
+    }
+  };
+
+  const uint64_t n_tiles = (p.n_reads + 31) / 32;
+  for (uint64_t t = gwarp; t < n_tiles; t += gwarps) {
+    const uint64_t i = t * 32 + lane;  // read of this lane, relative to the launch
+    int park = -1;                     // position to resume at, or -1 when the read is settled
+    uint32_t S[NW + 1] = {}, flags = 0;
+    if (i < p.n_reads) {
+      const uint64_t r = p.first_read + i;
+      uint64_t start;
+      int n;
+      if (p.line_off) {
+        const uint32_t a = p.line_off[r], b = p.line_off[r + 1];
+        start = a - p.off_base;
+        n = (int)(b - a) - 1;
+      } else {
+        start = r * p.stride;
+        n = (int)p.read_len;
+      }
+      // Centered/Null: offset; Plus: offset+1; Minus: offset-1 (counter.rs:164-174).  A failed trim
+      // RETURNS (counter.rs:105-108,175-176): no Centered window, no match; no Plus, no Minus either.
+      if (p.offset + k > n) {
+        settle(kMiss, (uint32_t)i);
+      } else {
+        const bool try_plus = p.recursion && p.offset + 1 + k <= n;
+        const bool try_minus = try_plus && p.offset >= 1;
+        const int win_src = p.reverse ? n - p.offset - k : p.offset;  // stored coordinates (see StreamGeom)
+        const int lead = ((try_plus && d_plus < 0) || (try_minus && d_plus > 0)) ? 1 : 0;
+        flags = (lead ? kLineLead : 0u) | (try_plus ? kLinePlus : 0u) | (try_minus ? kLineMinus : 0u);
+        const uint8_t* sb = p.lines + start + win_src - lead;  // first span byte
+        const uint64_t* a8 = reinterpret_cast<const uint64_t*>((uintptr_t)sb & ~(uintptr_t)7);
+        uint32_t R[2 * NL];
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+          // never a load that starts at or past the end of the buffer (bytes past the read only
+          // ever reach masked-off positions of a window)
+          const uint64_t v =
+              reinterpret_cast<const uint8_t*>(a8 + j) < p.lines_end ? ldg_stream_u64(a8 + j, line_policy) : 0ull;
+          R[2 * j] = (uint32_t)v;
+          R[2 * j + 1] = (uint32_t)(v >> 32);
+        }
+        const uint32_t sh = (uint32_t)((uintptr_t)sb & 7u);
+        const bool odd = (sh & 4u) != 0;
+        const uint32_t bits = (sh & 3u) * 8u;
+#pragma unroll
+        for (int j = 0; j < NW + 1; ++j) {
+          const uint32_t w0 = odd ? R[j + 1] : R[j], w1 = odd ? R[j + 2] : R[j + 1];
+          S[j] = __funnelshift_r(w0, w1, bits);
+        }
+        // Centered window: front table first (one sector decides ~80 % of the reads)
+        uint32_t w[NW], x[NW];
+#pragma unroll
+        for (int j = 0; j < NW; ++j) w[j] = __funnelshift_r(S[j], S[j + 1], 8u * (uint32_t)lead);
+        Key key;
+        const uint32_t any = pack_window<NW, WIDE>(w, g.n_words, g.last_mask, key, x);
+        park = 0;
+        if (any == 0) {
+          uint64_t b[4];
+          load_bucket(ix.front + (size_t)(front_hash(key.lo, key.hi) >> p.lib.front_shift) * 4, b, table_policy);
+          bool found, flagged;
+          int32_t idx;
+          if (!WIDE) {
+            uint32_t sel = 0;
+#pragma unroll
+            for (int j = 3; j >= 0; --j)
+              if ((uint32_t)b[j] == key.lo) sel = (uint32_t)(b[j] >> 32);
+            const uint32_t want = key.hi | (uint32_t)(kFrontOccupied >> 32);
+            found = ((sel ^ want) & (0xFFu | (uint32_t)(kFrontOccupied >> 32))) == 0;
+            idx = (int32_t)(sel >> (kFrontIdxShift - 32));
+            flagged = (b[0] & kFrontFlag) != 0;
+          } else {
+            const uint64_t probe = ((uint64_t)key.hi << 32) | key.lo;
+            const bool m0 = b[0] == probe && (b[1] & kFrontOccupied), m1 = b[2] == probe && (b[3] & kFrontOccupied);
+            found = m0 || m1;
+            idx = (int32_t)((m0 ? b[1] : b[3]) >> kFrontIdxShift);
+            flagged = (b[1] & kFrontFlag) != 0;
+          }
+          if (found) {
+            park = -1;
+            settle(idx, (uint32_t)i);
+          } else if (!flagged && !g.with_perm) {
+            // not a member and no Permuter: Centered is decided, go on with Plus if there is one
+            park = try_plus ? 1 : -1;
+            if (park < 0) settle(kMiss, (uint32_t)i);
+          }
+        } else if (!g.with_perm) {
+          // a byte outside A,C,G,T and no Permuter: Centered is decided
+          park = try_plus ? 1 : -1;
+          if (park < 0) settle(kMiss, (uint32_t)i);
+        }
+      }
+    }
+    const uint32_t pm = __ballot_sync(0xffffffffu, park >= 0);
+    if (pm) {
+      if (park >= 0) {
+        const uint32_t e = qn + __popc(pm & ((1u << lane) - 1));
+#pragma unroll
+        for (int j = 0; j < NW + 1; ++j) q->w[j][e] = S[j];
+        q->tag[e] = ((uint32_t)park << 30) | flags | (uint32_t)i;
+      }
+      qn += __popc(pm);
+      __syncwarp();
+    }
+    drain(false);
+  }
+  drain(true);
+  flush_matched<4>(p, matched, hot);
+}
+
+// NW = words that hold the k window bytes: 4 (k <= 16, the number of words in use is read from the
+// geometry), or exactly ceil(k / 4) = 5 (k = 17..20, the common guide lengths), 6, 7 or 8.
 template <int NW, bool WIDE, int MODE>
 __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams p, uint32_t n_wtiles, int n_stages,
                                                               uint32_t stage_bytes) {
@@ -431,8 +555,8 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   // shared layout: [warp][stage] tile buffers | [warp][stage] mbarriers | [warp] queues
   uint8_t* my_tiles = smem + (size_t)warp * n_stages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)warps_per_cta * n_stages * stage_bytes);
-  uint64_t* my_bar = bars + warp * kMaxStages;
-  WarpQueueT<NW>* q = reinterpret_cast<WarpQueueT<NW>*>(bars + warps_per_cta * kMaxStages) + warp;
+  uint64_t* my_bar = bars + warp * (2 * kMaxStages);  // [0, kMaxStages) full, [kMaxStages, 2 kMaxStages) empty
+  WarpQueueT<NW>* q = reinterpret_cast<WarpQueueT<NW>*>(bars + warps_per_cta * (2 * kMaxStages)) + warp;
 
   const uint32_t tile_bytes = kWarpReads * p.stride;  // multiple of 16
   const uint32_t gwarp = blockIdx.x * warps_per_cta + warp;
@@ -444,7 +568,10 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
   const uint64_t policy = l2_evict_first_policy();
   uint32_t requested = gwarp;  // tile index of the next request (n_wtiles + gwarps < 2^32); every lane keeps it
   if (lane == 0) {
-    for (int s = 0; s < n_stages; ++s) mbar_init(&my_bar[s], 1);
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&my_bar[s], 1);
+      mbar_init(&my_bar[kMaxStages + s], 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -519,6 +646,20 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
     // the loaded words (`& p.zero` keeps it what it was): the copy cannot be issued, in program
     // order or after any rescheduling by ptxas, before the data is in registers.  No CTA-wide
     // membar per tile.
+#if SGC_HANDBACK_MBAR
+    // consumer release / producer acquire on the buffer's "empty" barrier: the arrive is ordered
+    // after this lane's loads, the copy is issued after all 32 arrivals have been observed
+    if (requested < n_wtiles) {
+      mbar_arrive(cur_bar + 8u * kMaxStages);
+      if (elect_one()) {
+        mbar_wait(cur_bar + 8u * kMaxStages, parity);
+        mbar_expect_tx(cur_bar, tile_bytes);
+        bulk_load(cur_tile, next_src, tile_bytes, cur_bar, policy);
+      }
+      requested += gwarps;
+      next_src += src_step;
+    }
+#else
     uint32_t allw = W[0];
 #pragma unroll
     for (int i = 1; i < NW + 2; ++i) allw &= W[i];
@@ -531,6 +672,7 @@ __global__ void __launch_bounds__(384, 2) count_stream_kernel(const CountParams 
       requested += gwarps;
       next_src += src_step;
     }
+#endif
     cur_tile += stage_bytes;
     cur_bar += 8;
     if (++s == n_stages) {
@@ -672,7 +814,7 @@ namespace {
 
 struct TopGuides {
   unsigned long long packed[kHotGuides];  // count << 32 | guide index, descending
-  unsigned long long matched;
+  unsigned long long total;               // reads counted so far
 };
 
 // One block: the kHotGuides largest entries of counts[0..n).  Every thread keeps its own sorted
@@ -709,7 +851,7 @@ __global__ void __launch_bounds__(1024) top_guides_kernel(const unsigned long lo
         }
     }
     for (int j = 0; j < kHotGuides; ++j) out->packed[j] = top[j];
-    out->matched = counts[n + 1];
+    out->total = counts[n];
   }
 }
 
@@ -775,7 +917,7 @@ struct StreamConfig {
   int warps = 0, stages = 0, ctas_per_sm = 0;
 };
 size_t stream_smem_bytes(const StreamConfig& c, uint32_t stage_bytes, size_t queue_bytes) {
-  return (size_t)c.warps * ((size_t)c.stages * stage_bytes + kMaxStages * sizeof(uint64_t) + queue_bytes);
+  return (size_t)c.warps * ((size_t)c.stages * stage_bytes + 2 * kMaxStages * sizeof(uint64_t) + queue_bytes);
 }
 // How many warps per CTA and CTAs per SM.  Two things were measured to matter: the
 // number of resident warps, and the L1 that the shared-memory carve-out leaves for the scattered
@@ -834,16 +976,19 @@ using StreamKernel = void (*)(const CountParams, uint32_t, int, uint32_t);
     count_stream_kernel<NW, WIDE, 0>, count_stream_kernel<NW, WIDE, 1>, SGC_TUNING_KERNEL(NW, WIDE),       \
         count_stream_kernel<NW, WIDE, 3>, count_stream_kernel<NW, WIDE, 4>                                 \
   }
-const StreamKernel kStreamKernels[4][5] = {SGC_FAMILY(4, false), SGC_FAMILY(5, false), SGC_FAMILY(6, true),
-                                           SGC_FAMILY(8, true)};
+const StreamKernel kStreamKernels[5][5] = {SGC_FAMILY(4, false), SGC_FAMILY(5, false), SGC_FAMILY(6, true),
+                                           SGC_FAMILY(7, true), SGC_FAMILY(8, true)};
 
 // Enqueue the kernels for one device-resident batch.
+// Reads [first, n_reads) of the batch.
 int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const uint32_t* d_off, uint32_t off_base,
-                 uint32_t stride, uint32_t read_len, uint64_t n_reads, int32_t* d_assign, cudaStream_t stream) {
-  if (n_reads == 0) return SGC_OK;
+                 uint32_t stride, uint32_t read_len, uint64_t first, uint64_t n_reads, int32_t* d_assign,
+                 cudaStream_t stream) {
+  if (n_reads <= first) return SGC_OK;
   CountParams p = make_params(c, d_lines, d_off, stride, read_len, d_assign);
   p.off_base = off_base;
-  uint64_t done = 0;
+  p.lines_end = d_lines + n_bytes;
+  uint64_t done = first;
   const uint64_t launches_before = c->last.launches_total;
   c->last = sgc_launch_info{};
   c->last.launches_total = launches_before;
@@ -857,15 +1002,18 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
   const bool stageable = d_off == nullptr && ((uintptr_t)d_lines & 15u) == 0 && stride >= read_len &&
                          (uint64_t)c->offset + c->lib->k <= read_len;
   // kernel family by the words that hold the k window bytes: narrow keys 4 (k <= 16) or 5
-  // (k = 17..20, the common guide lengths); wide keys 6 (k = 21..24) or 8 (k = 25..30)
-  const int family = !c->lib->wide ? (c->lib->k <= 16 ? 0 : 1) : (c->lib->k <= 24 ? 2 : 3);
-  static const size_t family_queue_bytes[4] = {sizeof(WarpQueueT<4>), sizeof(WarpQueueT<5>), sizeof(WarpQueueT<6>),
-                                               sizeof(WarpQueueT<8>)};
+  // (k = 17..20, the common guide lengths); wide keys 6 (k = 21..24), 7 (k = 25..28) or 8 (k = 29, 30)
+  const int family = c->lib->k <= 16 ? 0 : (int)((c->lib->k + 3) / 4) - 4;
+  static const size_t family_queue_bytes[5] = {sizeof(WarpQueueT<4>), sizeof(WarpQueueT<5>), sizeof(WarpQueueT<6>),
+                                               sizeof(WarpQueueT<7>), sizeof(WarpQueueT<8>)};
   const size_t queue_bytes = family_queue_bytes[family];
   StreamConfig cfg = stageable ? pick_stream_config(stage_bytes, queue_bytes) : StreamConfig{};
   // whole tiles only, and never a bulk copy that would run past n_bytes; one launch handles at
   // most 2^30 reads (the queue words keep a 30-bit read index)
-  uint64_t tiles_left = stageable && cfg.stages ? std::min(n_reads / kWarpReads, n_bytes / tile_bytes) : 0;
+  const bool first_aligned = ((first * stride) & 15u) == 0;
+  uint64_t tiles_left = stageable && cfg.stages && first_aligned
+                            ? std::min((n_reads - first) / kWarpReads, (n_bytes - first * stride) / tile_bytes)
+                            : 0;
   uint64_t max_tiles = (1ull << kReadIdxBits) / kWarpReads - 65536;
   if (const long long cap = env_ll("SGC_MAX_LAUNCH_TILES", 0); cap > 0) max_tiles = std::min<uint64_t>(max_tiles, cap);
   const bool any_hot = c->last.hot_guides > 0;
@@ -905,19 +1053,25 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
     c->last.kernel = 0;
     c->last.launches_total += 1;
   }
-  if (done < n_reads) {
+  const bool lines_only = done == first;
+  while (done < n_reads) {  // what the streaming kernel did not take; at most 2^27 reads per launch
     p.first_read = done;
-    p.n_reads = n_reads - done;
-    uint64_t blocks = (p.n_reads + 255) / 256;
-    uint64_t cap = (uint64_t)c->lib->sm_count * 8;
+    p.n_reads = std::min<uint64_t>(n_reads - done, 1ull << kLineIdxBits);
+    uint64_t blocks = (p.n_reads + 32 * kLineWarps - 1) / (32 * kLineWarps);
+    const uint64_t cap = (uint64_t)c->lib->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    count_generic_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+    using LineKernel = void (*)(CountParams);
+    static const LineKernel line_kernels[5] = {count_lines_kernel<4, false>, count_lines_kernel<5, false>,
+                                               count_lines_kernel<6, true>, count_lines_kernel<7, true>,
+                                               count_lines_kernel<8, true>};
+    line_kernels[family]<<<(unsigned)blocks, 32 * kLineWarps, 0, stream>>>(p);
     SGC_CUDA_TRY(cudaGetLastError());
-    if (done == 0) {
+    if (lines_only) {
       c->last.grid = (uint32_t)blocks;
-      c->last.block = 256;
+      c->last.block = 32 * kLineWarps;
     }
     c->last.launches_total += 1;
+    done += p.n_reads;
   }
   if (c->n_rep > 1) {
     fold_replicas_kernel<<<(c->lib->n + 255) / 256, 256, 0, stream>>>(c->d_state, c->d_rep, c->lib->n, c->n_rep);
@@ -945,58 +1099,47 @@ int alloc_replicas(sgc_counter* c, uint32_t replicas) {
   return SGC_OK;
 }
 
-// Skew plan of a counter, made once, from the first kSkewSampleReads reads of its first large
-// batch: they are counted into a scratch vector with the plain kernel, the four most frequent
-// guides are read back, and
-//   top share >= 1/256  -> 16 count replicas (or as many as 64 MB hold);
+// Skew plan of a counter, made once, on its first large batch: the first kSkewSampleReads reads
+// are counted (into the state vector, like any others), the four largest counters are read
+// back, and
+//   top share >= 1/256  -> the rest of the sample is counted into 16 replicas (or as many as
+//                          64 MB hold);
 //   every guide with a share >= 1 % is counted in registers (count_hit, MODE 4).
-// Costs one small launch and one stream synchronisation per counter (= per sample or sample
-// shard).  The counts do not depend on the plan.
+// Costs one extra launch boundary and one stream synchronisation per counter (= per sample or
+// sample shard).  The counts do not depend on the plan.  Returns the reads already counted.
 int plan_skew(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const uint32_t* d_off, uint32_t off_base,
-              uint32_t stride, uint32_t read_len, uint64_t n_reads, cudaStream_t stream) {
+              uint32_t stride, uint32_t read_len, uint64_t n_reads, cudaStream_t stream, uint64_t* counted) {
   c->skew_planned = true;
   const uint64_t sample = std::min<uint64_t>(n_reads, kSkewSampleReads);
-  const size_t words = (size_t)c->lib->n + 2;
-  unsigned long long* d_scratch = nullptr;
-  TopGuides* d_top = nullptr;
-  SGC_CUDA_TRY(cudaMalloc(&d_scratch, words * sizeof(uint64_t) + sizeof(TopGuides)));
-  struct Free {
-    void* p;
-    ~Free() { cudaFree(p); }
-  } free_scratch{d_scratch};
-  d_top = reinterpret_cast<TopGuides*>(d_scratch + words);
-  SGC_CUDA_TRY(cudaMemsetAsync(d_scratch, 0, words * sizeof(uint64_t), stream));
-  unsigned long long* const state = c->d_state;
-  const sgc_launch_info last = c->last;
-  c->d_state = d_scratch;
-  const uint64_t sample_bytes = d_off ? n_bytes : std::min<uint64_t>(n_bytes, sample * stride);
-  int rc = launch_count(c, d_lines, sample_bytes, d_off, off_base, stride, read_len, sample, nullptr, stream);
-  c->d_state = state;
-  c->last = last;
+  if (!c->d_top) SGC_CUDA_TRY(cudaMalloc(&c->d_top, sizeof(TopGuides)));
+  int rc = launch_count(c, d_lines, n_bytes, d_off, off_base, stride, read_len, 0, sample, nullptr, stream);
   if (rc) return rc;
-  top_guides_kernel<<<1, 1024, 0, stream>>>(d_scratch, c->lib->n, d_top);
+  *counted = sample;
+  top_guides_kernel<<<1, 1024, 0, stream>>>(c->d_state, c->lib->n, static_cast<TopGuides*>(c->d_top));
   SGC_CUDA_TRY(cudaGetLastError());
   TopGuides top;
-  SGC_CUDA_TRY(cudaMemcpyAsync(&top, d_top, sizeof top, cudaMemcpyDeviceToHost, stream));
+  SGC_CUDA_TRY(cudaMemcpyAsync(&top, c->d_top, sizeof top, cudaMemcpyDeviceToHost, stream));
   SGC_CUDA_TRY(cudaStreamSynchronize(stream));
-  const uint64_t top_count = top.packed[0] >> 32;
-  if (top_count * 256 < sample) return SGC_OK;  // no guide stands out
+  // shares among everything this counter has seen so far (earlier small batches included)
+  const uint64_t seen = std::max<uint64_t>(top.total, 1), top_count = top.packed[0] >> 32;
+  if (top_count * 256 < seen) return SGC_OK;  // no guide stands out
   rc = alloc_replicas(c, 16);
   if (rc) return rc;
   int n_hot = 0;
   for (int j = 0; j < kHotGuides; ++j)
-    if ((top.packed[j] >> 32) * 100 >= sample) c->hot[n_hot++] = (int32_t)(uint32_t)top.packed[j];
+    if ((top.packed[j] >> 32) * 100 >= seen) c->hot[n_hot++] = (int32_t)(uint32_t)top.packed[j];
   return SGC_OK;
 }
 
 // launch_count preceded, for the counter's first large batch, by the skew plan
 int count_batch(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const uint32_t* d_off, uint32_t off_base,
                 uint32_t stride, uint32_t read_len, uint64_t n_reads, int32_t* d_assign, cudaStream_t stream) {
+  uint64_t counted = 0;
   if (c->auto_skew && !c->skew_planned && !d_assign && n_reads >= kSkewMinBatch) {
-    int rc = plan_skew(c, d_lines, n_bytes, d_off, off_base, stride, read_len, n_reads, stream);
+    int rc = plan_skew(c, d_lines, n_bytes, d_off, off_base, stride, read_len, n_reads, stream, &counted);
     if (rc) return rc;
   }
-  return launch_count(c, d_lines, n_bytes, d_off, off_base, stride, read_len, n_reads, d_assign, stream);
+  return launch_count(c, d_lines, n_bytes, d_off, off_base, stride, read_len, counted, n_reads, d_assign, stream);
 }
 
 int check_batch(const sgc_counter* c, const uint8_t* lines, uint64_t n_bytes, const uint32_t* line_off,
@@ -1083,6 +1226,7 @@ void sgc_counter_destroy(sgc_counter* c) {
   for (cudaEvent_t e : c->copy_tickets) cudaEventDestroy(e);
   for (cudaEvent_t e : c->free_tickets) cudaEventDestroy(e);
   cudaFree(c->d_rep);
+  cudaFree(c->d_top);
   if (c->own_state) cudaFree(c->d_state);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;

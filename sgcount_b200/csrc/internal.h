@@ -62,6 +62,7 @@ struct sgc_counter {
   uint32_t n_rep = 1;
   int32_t hot[4] = {-2, -2, -2, -2};
   bool auto_skew = true, skew_planned = false;
+  void* d_top = nullptr;  // the plan's read-back buffer
   // host-batch staging (sgc_counter_submit)
   cudaStream_t copy_stream = nullptr;
   uint8_t* d_stage[2] = {nullptr, nullptr};
