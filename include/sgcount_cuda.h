@@ -137,6 +137,18 @@ int sgc_counter_create(const sgc_library*, int is_reverse, uint32_t offset, int 
                        int rc_mode, void* stream, uint64_t* d_state, sgc_counter** out);
 void sgc_counter_destroy(sgc_counter*);
 
+/* Span records: all the counting ever looks at of a fixed-length read is the guide window and
+ * one byte either side of it (counter.rs:164-174: offset, offset + 1, offset - 1).  A host that
+ * knows the Offset before it frames the records (it does: offsetter.rs runs first) can cut that
+ * span out of every read and send 24 bytes per read instead of 76.  For reads of `read_len`
+ * bytes this returns where the span starts in the STORED read and how long it is, and the Offset
+ * index that makes a counter treat the span records as (short) reads with exactly the same
+ * outcome: same orientation, `span_offset`, same position_recursion; submit them with
+ * read_len = span_len and any stride >= span_len.  Fails with SGC_ERR_INVALID_ARG when the
+ * Centered window does not fit the read (offset + k > read_len: every read is unmatched anyway). */
+int sgc_span_geometry(uint32_t k, uint32_t read_len, int is_reverse, uint32_t offset, int position_recursion,
+                      uint32_t* span_start, uint32_t* span_len, uint32_t* span_offset);
+
 /* Count a batch held in HOST memory (pinned memory makes the copies asynchronous).  The
  * batch is cut into chunks that are copied and counted on alternating buffers so copy and
  * kernel overlap; returns after the last chunk has been enqueued.  The host buffers must

@@ -211,6 +211,31 @@ class Permuter:
         return self._handle.info()
 
 
+def span_geometry(k: int, read_len: int, offset: Offset, position_recursion: bool = True):
+    """sgc_span_geometry: (start, length) of the span of a `read_len`-byte read — the guide window
+    and the byte either side that Counter::assign may look at (counter.rs:164-174) — and the Offset
+    under which a counter treats span records as reads with the same outcome."""
+    start, length, idx = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    check(_cabi.load().sgc_span_geometry(k, read_len, int(offset.reverse), offset.index, int(position_recursion),
+                                         C.byref(start), C.byref(length), C.byref(idx)))
+    return start.value, length.value, Offset(offset.reverse, idx.value)
+
+
+def span_batch(reader: ReadBatch, k: int, offset: Offset, position_recursion: bool = True, out: Optional[np.ndarray] = None):
+    """Fixed-length reads cut down to span records of stride round_up(length, 8): what a host that
+    frames its own records sends instead of whole lines.  Returns (ReadBatch of spans, Offset)."""
+    assert reader.line_off is None, "span records need fixed-length reads"
+    start, length, span_offset = span_geometry(k, reader.read_len, offset, position_recursion)
+    stride = (length + 7) & ~7
+    n = reader.n_reads
+    rows = reader.lines[:n * reader.stride].reshape(n, reader.stride)
+    if out is None:
+        out = np.zeros(n * stride, dtype=np.uint8)
+    spans = out[:n * stride].reshape(n, stride)
+    spans[:, :length] = rows[:, start:start + length]
+    return ReadBatch(out[:n * stride], n, None, stride, length), span_offset
+
+
 def reduce_counts(shards: Sequence["Counter"], root: int = 0) -> None:
     """Sum of the read shards' count vectors into shards[root] (sgc_reduce_counts: NCCL across
     devices, a fold kernel within one) — count.rs:136's collect for a sample cut into shards."""

@@ -1161,6 +1161,21 @@ int check_batch(const sgc_counter* c, const uint8_t* lines, uint64_t n_bytes, co
 
 extern "C" {
 
+int sgc_span_geometry(uint32_t k, uint32_t read_len, int is_reverse, uint32_t offset, int position_recursion,
+                      uint32_t* span_start, uint32_t* span_len, uint32_t* span_offset) {
+  if (!span_start || !span_len || !span_offset) return set_error(SGC_ERR_INVALID_ARG, "NULL argument");
+  if (k == 0 || (uint64_t)offset + k > read_len)
+    return set_error(SGC_ERR_INVALID_ARG, "the Centered window does not fit the read");
+  // the same three facts the kernels derive (make_geom): does Plus exist, does Minus exist, and
+  // which of them lies before the Centered window in the stored read
+  const StreamGeom g = make_geom(k, read_len, (int)offset, true, is_reverse != 0, position_recursion != 0, SGC_RC_BITTRICK);
+  const uint32_t before = is_reverse ? g.try_plus : g.try_minus, after = is_reverse ? g.try_minus : g.try_plus;
+  *span_start = (uint32_t)g.win_src - before;
+  *span_len = before + k + after;
+  *span_offset = is_reverse ? after : before;  // Offset index of the span records
+  return SGC_OK;
+}
+
 int sgc_counter_create(const sgc_library* lib, int is_reverse, uint32_t offset, int position_recursion, int rc_mode,
                        void* stream, uint64_t* d_state, sgc_counter** out) {
   if (!lib || !out) return set_error(SGC_ERR_INVALID_ARG, "NULL argument");

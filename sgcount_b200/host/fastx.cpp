@@ -8,6 +8,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -76,7 +77,8 @@ class PlainSource : public ByteSource {
 class GzSource : public ByteSource {
  public:
   // frame_records: the workers also frame the records of their member (SeqBlockReader)
-  GzSource(const std::string& path, unsigned threads, bool frame_records = false) {
+  GzSource(const std::string& path, unsigned threads, bool frame_records = false, const SpanSpec* spans = nullptr)
+      : spans_(spans) {
     fd_ = open(path.c_str(), O_RDONLY);
     if (fd_ < 0) throw FastxError("cannot open " + path);
     struct stat st;
@@ -320,7 +322,15 @@ class GzSource : public ByteSource {
           framer.st.lines_per_record = frame_lpr_;
           block.lines.reserve(out.size() / 2);
           try {
-            framer.feed(out.data(), out.size(), block);
+            // span records while every read of the sample has had the first one's length
+            framer.spans = spans_ && !spans_abandoned_.load(std::memory_order_relaxed) ? spans_ : nullptr;
+            if (!framer.feed(out.data(), out.size(), block)) {
+              spans_abandoned_.store(true, std::memory_order_relaxed);
+              framer = SeqParser();
+              framer.st.lines_per_record = frame_lpr_;
+              block.clear();
+              framer.feed(out.data(), out.size(), block);
+            }
             framed = true;
           } catch (const std::exception&) {  // the consumer frames these bytes itself and reports
           }
@@ -389,6 +399,8 @@ class GzSource : public ByteSource {
   size_t next_job_ = 0, consumer_at_ = 0, window_ = 2;
   bool stop_ = false, sequential_ = false;
   int frame_lpr_ = 0;  // lines per record the workers frame with; 0 = they do not
+  const SpanSpec* spans_ = nullptr;
+  std::atomic<bool> spans_abandoned_{false};  // a read of another length was seen: whole lines from here on
   const bool use_fast_inflate_ = []() {
     const char* v = getenv("SGC_INFLATE");  // "zlib": every member through zlib (A/B and tests)
     return !(v && !strcmp(v, "zlib"));
@@ -446,10 +458,11 @@ void SeqBlock::push(const char* seq, size_t l) {
   lines.insert(lines.end(), seq, seq + l);
   lines.push_back('\n');
   len.push_back((uint32_t)l);
+  if (n == 0) stride = (uint32_t)l + 1;
   ++n;
 }
 
-void SeqParser::line(const char* p, size_t len, SeqBlock& out) {
+bool SeqParser::line(const char* p, size_t len, SeqBlock& out) {
   if (st.lines_per_record == 0) {
     if (len == 0) throw FastxError("empty first line: not FASTA/FASTQ");
     if (p[0] == '>')
@@ -459,21 +472,37 @@ void SeqParser::line(const char* p, size_t len, SeqBlock& out) {
     else
       throw FastxError("first byte is neither '>' nor '@'");
   }
-  if (st.phase == 1) out.push(p, len);
+  if (st.phase == 1) {
+    if (spans) {
+      if (len != spans->read_len) return false;
+      if (out.n == 0) {
+        out.spans = true;
+        out.first_len = spans->len;
+        out.stride = spans->stride;
+      }
+      const size_t at = out.lines.size();
+      out.lines.resize(at + spans->stride);  // BigAlloc default-initialises: the pad bytes are never looked at
+      memcpy(out.lines.data() + at, p + spans->start, spans->len);
+      ++out.n;
+    } else {
+      out.push(p, len);
+    }
+  }
   if (++st.phase == st.lines_per_record) st.phase = 0;
+  return true;
 }
 
-void SeqParser::feed(const char* data, size_t len, SeqBlock& out) {
+bool SeqParser::feed(const char* data, size_t len, SeqBlock& out) {
   const char* p = data;
   const char* const end = data + len;
   if (!st.carry.empty()) {  // finish the line the previous chunk left open
     const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
     if (!nl) {
       st.carry.append(p, end);
-      return;
+      return true;
     }
     st.carry.append(p, nl);
-    line(st.carry.data(), st.carry.size(), out);
+    if (!line(st.carry.data(), st.carry.size(), out)) return false;
     st.carry.clear();
     p = nl + 1;
   }
@@ -481,11 +510,12 @@ void SeqParser::feed(const char* data, size_t len, SeqBlock& out) {
     const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
     if (!nl) {
       st.carry.assign(p, end);
-      return;
+      return true;
     }
-    line(p, (size_t)(nl - p), out);
+    if (!line(p, (size_t)(nl - p), out)) return false;
     p = nl + 1;
   }
+  return true;
 }
 
 void SeqParser::finish(SeqBlock& out) {
@@ -504,11 +534,14 @@ struct SeqBlockReader::Impl {
   Bytes raw;                  // gzip: the member / chunk being framed
   std::vector<char> raw_plain;
   bool eof = false;
+  SpanSpec spans;  // what the inflate threads frame with (they hold a pointer to it)
 };
 
-SeqBlockReader::SeqBlockReader(const std::string& path, unsigned inflate_threads) : impl_(new Impl()) {
+SeqBlockReader::SeqBlockReader(const std::string& path, unsigned inflate_threads, const SpanSpec* spans)
+    : impl_(new Impl()) {
+  if (spans) impl_->spans = *spans;
   if (ends_with(path, ".gz"))
-    impl_->gz.reset(new GzSource(path, inflate_threads, /*frame_records=*/true));
+    impl_->gz.reset(new GzSource(path, inflate_threads, /*frame_records=*/true, spans ? &impl_->spans : nullptr));
   else
     impl_->plain.reset(new PlainSource(path));
 }

@@ -88,20 +88,33 @@ template <typename T>
 void BigAlloc<T>::deallocate(T* p, size_t n) { big_free_bytes(p, n * sizeof(T)); }
 using Bytes = std::vector<char, BigAlloc<char>>;
 
+// Span framing (include/sgcount_cuda.h sgc_span_geometry): when every read of a sample has the
+// length of its first one, the inflate threads keep only bytes [start, start + len) of every
+// sequence, in records of `stride` bytes — all the count kernels ever look at, a third of the
+// bytes to copy into pinned memory and over PCIe.
+struct SpanSpec {
+  uint32_t read_len = 0;  // the sample's read length (that of its first record)
+  uint32_t start = 0, len = 0, stride = 0;
+};
+
 // Sequence lines of a run of whole records, packed the way the count kernels take them: every
-// sequence followed by '\n'.
+// sequence followed by '\n' — or, in span mode, fixed-stride span records.
 struct SeqBlock {
   Bytes lines;
-  std::vector<uint32_t> len;  // length of every sequence (without the '\n')
+  std::vector<uint32_t> len;  // length of every sequence (without the '\n'); empty in span mode
   uint64_t n = 0;
   bool uniform = true;  // every sequence is as long as the first
   uint32_t first_len = 0;
+  bool spans = false;   // records are spans: `first_len` = span length, `stride` = record size
+  uint32_t stride = 0;  // bytes per record when uniform (first_len + 1 for whole lines)
   void clear() {
     lines.clear();
     len.clear();
     n = 0;
     uniform = true;
     first_len = 0;
+    spans = false;
+    stride = 0;
   }
   void push(const char* seq, size_t l);
 };
@@ -117,12 +130,15 @@ class SeqParser {
     bool clean() const { return phase == 0 && carry.empty(); }
   };
   State st;
-  void feed(const char* data, size_t len, SeqBlock& out);
+  // span framing of uniform-length reads; feed() returns false at the first sequence of another
+  // length (the block is then incomplete: frame the bytes again without a spec)
+  const SpanSpec* spans = nullptr;
+  bool feed(const char* data, size_t len, SeqBlock& out);
   // end of input: a last line without '\n' counts; throws FastxError on a truncated record
   void finish(SeqBlock& out);
 
  private:
-  void line(const char* p, size_t len, SeqBlock& out);
+  bool line(const char* p, size_t len, SeqBlock& out);
 };
 
 // The hot ingest path of count_sample (count.rs:15-45 hands `Counter::new` a record iterator;
@@ -132,7 +148,9 @@ class SeqParser {
 // framing state and re-frames the member's bytes itself when it does not hold.
 class SeqBlockReader {
  public:
-  explicit SeqBlockReader(const std::string& path, unsigned inflate_threads = 1);
+  // spans: frame span records instead of whole lines wherever a gzip member's reads all have
+  // spans->read_len bytes (blocks say which they hold); nullptr = whole lines only
+  explicit SeqBlockReader(const std::string& path, unsigned inflate_threads = 1, const SpanSpec* spans = nullptr);
   ~SeqBlockReader();
   // Next block (possibly of zero records); false at the end of the input.
   bool next(SeqBlock& out);

@@ -50,6 +50,39 @@ int main(int argc, char** argv) {
       printf("%llu %llu\n", n, bytes);
       return 0;
     }
+    if (argc > 4 && !strcmp(argv[3], "spans")) {  // span framing: fastx_dump <path> <threads> spans read_len,start,len,stride
+      sgh::SpanSpec spec;
+      if (sscanf(argv[4], "%u,%u,%u,%u", &spec.read_len, &spec.start, &spec.len, &spec.stride) != 4) return 2;
+      sgh::SeqBlockReader br(argv[1], (unsigned)atoi(argv[2]), &spec);
+      sgh::SeqBlock b;
+      // hash of what a counter would look at: the span of every read of read_len bytes (whether it
+      // came as a span record or inside a whole line), the whole sequence of any other read
+      unsigned long long n = 0, n_span = 0, h = 1469598103934665603ull;
+      auto mix = [&](const char* p, size_t l, unsigned mark) {
+        for (size_t j = 0; j < l; ++j) h = (h ^ (unsigned char)p[j]) * 1099511628211ull;
+        h = (h ^ mark) * 1099511628211ull;
+      };
+      while (br.next(b)) {
+        if (b.spans) {
+          if (b.first_len != spec.len || b.stride != spec.stride || b.lines.size() != b.n * spec.stride || !b.uniform) return 3;
+          for (unsigned long long i = 0; i < b.n; ++i) mix(b.lines.data() + i * spec.stride, spec.len, 0xFEu);
+          n_span += b.n;
+        } else {
+          size_t at = 0;
+          for (unsigned long long i = 0; i < b.n; ++i) {
+            const size_t l = b.len[i];
+            if (l == spec.read_len)
+              mix(b.lines.data() + at + spec.start, spec.len, 0xFEu);
+            else
+              mix(b.lines.data() + at, l, 0xFFu);
+            at += l + 1;
+          }
+        }
+        n += b.n;
+      }
+      printf("%llu %llx %llu\n", n, h, n_span);
+      return 0;
+    }
     if (argc > 3 && !strcmp(argv[3], "blocks")) {  // the packed-sequence-line path of count_sample
       sgh::SeqBlockReader br(argv[1], (unsigned)atoi(argv[2]));
       sgh::SeqBlock b;

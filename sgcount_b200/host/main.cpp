@@ -62,6 +62,7 @@ struct Args {
   unsigned read_shards = 0;     // counters per sample; 0 = gpus / samples (at least 1)
   unsigned ingest_threads = 0;  // inflate threads per sample; 0 = hardware threads / concurrent samples
   bool timing = false;
+  bool whole_lines = false;  // never frame span records
   int rc_mode = SGC_RC_BITTRICK;
 };
 
@@ -86,6 +87,7 @@ const char* kUsage =
     "      --device <D>                       First device to use [default: 0]\n"
     "      --ingest-threads <N>               Threads inflating the gzip members of one sample [default: cores / samples in flight]\n"
     "      --rc-keep-n                        Reverse complement keeps N (default: the fxread bit trick, N -> J)\n"
+    "      --whole-lines                      Copy whole sequence lines to the device (default: for fixed-length reads, only the guide window and one byte either side)\n"
     "      --timing                           Print a JSON line with the phase times to stderr\n"
     "  -h, --help                             Print help\n";
 
@@ -129,6 +131,7 @@ Args parse_args(int argc, char** argv) {
     else if (f == "--ingest-threads") a.ingest_threads = (unsigned)parse_uint(f, value());
     else if (f == "--rc-keep-n") a.rc_mode = SGC_RC_KEEP_N;
     else if (f == "--timing") a.timing = true;
+    else if (f == "--whole-lines") a.whole_lines = true;
     else if (f == "-h" || f == "--help") { fputs(kUsage, stdout); exit(0); }
     else fail("unexpected argument '%s' found", f.c_str());
   }
@@ -232,6 +235,7 @@ struct Batch {
   std::vector<uint32_t> off;  // n + 1 line starts; kept only once the batch is not uniform
   bool uniform = true;        // every read as long as the first
   size_t first_len = 0;
+  size_t stride = 0;          // bytes per record while uniform (first_len + 1, or the span stride)
   uint64_t n = 0;
 
   void reset() {
@@ -243,7 +247,10 @@ struct Batch {
   bool fits(size_t bytes) const { return used + bytes <= cap && used + bytes < (1ull << 32); }
   bool push(const char* seq, size_t len) {
     if (!fits(len + 1)) return false;
-    if (n == 0) first_len = len;
+    if (n == 0) {
+      first_len = len;
+      stride = len + 1;
+    }
     if (uniform && len != first_len) {  // from here on the kernels need the line starts
       uniform = false;
       off.resize(n + 1);
@@ -260,8 +267,8 @@ struct Batch {
   // block.  Returns false when the batch is full before the block is used up.
   bool append(const sgh::SeqBlock& blk, uint64_t& rec, size_t& byte) {
     while (rec < blk.n) {
-      if (uniform && blk.uniform && (n == 0 || first_len == blk.first_len)) {
-        const size_t stride = (size_t)blk.first_len + 1;
+      if (uniform && blk.uniform && (n == 0 || (first_len == blk.first_len && stride == blk.stride))) {
+        stride = blk.stride;
         size_t room = cap - used;
         if (used + room >= (1ull << 32)) room = (1ull << 32) - 1 - used;
         const uint64_t fit = std::min<uint64_t>(blk.n - rec, room / stride);
@@ -286,7 +293,7 @@ struct Batch {
 void submit(sgc_counter* c, const Batch& b) {
   if (b.n == 0) return;
   if (b.uniform)  // fixed stride selects the streaming kernel
-    check(sgc_counter_submit(c, b.lines, b.used, nullptr, (uint32_t)b.first_len + 1, (uint32_t)b.first_len, b.n));
+    check(sgc_counter_submit(c, b.lines, b.used, nullptr, (uint32_t)b.stride, (uint32_t)b.first_len, b.n));
   else
     check(sgc_counter_submit(c, b.lines, b.used, b.off.data(), 0, 0, b.n));
 }
@@ -338,93 +345,125 @@ struct SampleResult {
   // where the counting thread spent its time (--timing): waiting for the inflate threads,
   // copying sequence lines into pinned memory, in sgc_counter_submit / sync / finish
   double wait_s = 0, copy_s = 0, submit_s = 0;
-  unsigned shards = 1;  // counters (devices) the sample's reads were spread over
+  unsigned shards = 1;  // devices the sample's reads were spread over
+  uint64_t span_reads = 0, line_reads = 0;  // reads that travelled as span records / whole lines
 };
 
 // count_sample (count.rs:15-45).  The inflate threads hand over blocks of sequence lines in file
 // order; this thread packs them into pinned batches and submits them.  With several devices the
 // batches of the ONE sample go round the devices (read shards, each its own counter, stream and
-// pair of pinned buffers) and the shard vectors are summed into the first device's at the end
+// pair of pinned buffers) and the shard vectors are summed into the first one's at the end
 // (sgc_reduce_counts: one NCCL reduce of n_guides + 2 words) — the reference never splits a
 // sample; its per-sample Counters are simply collected (count.rs:136).
-SampleResult count_sample(const std::vector<const sgc_library*>& libs, uint32_t n_guides, const std::string& path,
-                          OffsetValue offset, bool recursion, int rc_mode, unsigned ingest_threads) {
-  struct Lane {
+//
+// When the sample's reads all have the length of its first record (`read_len`, known from the
+// head the offset detector read), the inflate threads frame SPAN records — the guide window and
+// one byte either side, all Counter::assign ever looks at — and those go to a second counter per
+// device whose Offset addresses the window inside the span (sgc_span_geometry).  A member that
+// holds a read of another length comes as whole lines and goes to the ordinary counter.
+SampleResult count_sample(const std::vector<const sgc_library*>& libs, uint32_t n_guides, uint32_t k,
+                          const std::string& path, OffsetValue offset, uint32_t read_len, bool recursion, int rc_mode,
+                          unsigned ingest_threads, bool use_spans) {
+  struct Channel {  // one counter and its pair of pinned buffers
     sgc_counter* c = nullptr;
     Batch b[2];
     int cur = 0;
     bool used = false;
   };
+  struct Lane {
+    Channel ch[2];  // [0] whole lines, [1] span records
+  };
   struct Guard {
     std::vector<Lane> lanes;
     ~Guard() {
-      for (auto& l : lanes) {
-        sgc_counter_destroy(l.c);
-        for (auto& x : l.b)
-          if (x.lines) sgc_host_free(x.lines);
-      }
+      for (auto& l : lanes)
+        for (auto& ch : l.ch) {
+          sgc_counter_destroy(ch.c);
+          for (auto& x : ch.b)
+            if (x.lines) sgc_host_free(x.lines);
+        }
     }
   } g;
   g.lanes.resize(libs.size());
-  for (size_t d = 0; d < libs.size(); ++d)
-    check(sgc_counter_create(libs[d], offset.reverse, offset.index, recursion, rc_mode, nullptr, nullptr, &g.lanes[d].c));
-  // blocks of packed sequence lines, framed by the inflate threads (fastx.h); they start
-  // inflating while the pinned buffers are being allocated
-  sgh::SeqBlockReader reader(path, ingest_threads);
+  sgh::SpanSpec spec;
+  uint32_t span_offset = 0;
+  if (use_spans && sgc_span_geometry(k, read_len, offset.reverse, offset.index, recursion, &spec.start, &spec.len,
+                                     &span_offset) == SGC_OK) {
+    spec.read_len = read_len;
+    spec.stride = (spec.len + 7u) & ~7u;
+    use_spans = spec.stride < read_len + 1;  // only if it sends fewer bytes
+  } else {
+    use_spans = false;
+  }
+  // blocks of packed sequence lines or span records, framed by the inflate threads (fastx.h);
+  // they start inflating while the pinned buffers are being allocated
+  sgh::SeqBlockReader reader(path, ingest_threads, use_spans ? &spec : nullptr);
   const size_t cap = 64u << 20;
-  auto ready = [&](Lane& l) {  // the pinned buffers of a lane, on first use
-    if (l.b[0].lines) return;
-    for (auto& b : l.b) {
+  auto ready = [&](size_t d, int kind) -> Channel& {  // counter and pinned buffers on first use
+    Channel& ch = g.lanes[d].ch[kind];
+    if (ch.c) return ch;
+    check(sgc_counter_create(libs[d], offset.reverse, kind ? span_offset : offset.index, recursion, rc_mode, nullptr,
+                             nullptr, &ch.c));
+    for (auto& b : ch.b) {
       void* p = nullptr;
       check(sgc_host_alloc(&p, cap));
       b.lines = static_cast<uint8_t*>(p);
       b.cap = cap;
       b.reset();
     }
+    return ch;
   };
   sgh::SeqBlock blk;
   size_t d = 0;
   SampleResult r;
   using Clock = std::chrono::steady_clock;
   auto since = [](Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); };
-  ready(g.lanes[0]);
+  ready(0, use_spans ? 1 : 0);
   for (;;) {
     auto t0 = Clock::now();
     const bool more = reader.next(blk);
     r.wait_s += since(t0);
     if (!more) break;
+    const int kind = blk.spans ? 1 : 0;
+    (blk.spans ? r.span_reads : r.line_reads) += blk.n;
     uint64_t rec = 0;
     size_t byte = 0;
     for (;;) {
-      Lane& l = g.lanes[d];
+      Channel& ch = ready(d, kind);
       t0 = Clock::now();
-      const bool done = l.b[l.cur].append(blk, rec, byte);
+      const bool done = ch.b[ch.cur].append(blk, rec, byte);
       r.copy_s += since(t0);
       if (done) break;
-      if (l.b[l.cur].n == 0) fail("a sequence line longer than %zu bytes", cap);
+      if (ch.b[ch.cur].n == 0) fail("a sequence line longer than %zu bytes", cap);
       t0 = Clock::now();
-      submit(l.c, l.b[l.cur]);
-      l.used = true;
-      l.cur ^= 1;
+      submit(ch.c, ch.b[ch.cur]);
+      ch.used = true;
+      ch.cur ^= 1;
       // the buffer about to be refilled was handed over one submit ago: its copy must have
       // finished, the copy just queued (and every kernel) may still be running
-      check(sgc_counter_wait_copies(l.c, 1));
-      l.b[l.cur].reset();
+      check(sgc_counter_wait_copies(ch.c, 1));
+      ch.b[ch.cur].reset();
       d = (d + 1) % g.lanes.size();  // the next batch goes to the next device
-      ready(g.lanes[d]);
       r.submit_s += since(t0);
     }
   }
   auto t0 = Clock::now();
-  for (auto& l : g.lanes)
-    if (l.b[0].lines && l.b[l.cur].n) {
-      submit(l.c, l.b[l.cur]);
-      l.used = true;
-    }
   std::vector<sgc_counter*> shards;
-  for (auto& l : g.lanes)
-    if (l.used || &l == &g.lanes[0]) shards.push_back(l.c);
-  r.shards = (unsigned)shards.size();
+  unsigned devices_used = 0;
+  for (auto& l : g.lanes) {
+    bool any = false;
+    for (auto& ch : l.ch) {
+      if (!ch.c) continue;
+      if (ch.b[ch.cur].n) {
+        submit(ch.c, ch.b[ch.cur]);
+        ch.used = true;
+      }
+      if (ch.used || shards.empty()) shards.push_back(ch.c);
+      any |= ch.used;
+    }
+    devices_used += any;
+  }
+  r.shards = std::max(devices_used, 1u);
   if (shards.size() > 1) check(sgc_reduce_counts(shards.data(), (int)shards.size(), 0));
   r.counts.resize(n_guides);
   check(sgc_counter_finish(shards[0], r.counts.data(), &r.total, &r.matched));
@@ -508,6 +547,8 @@ int main(int argc, char** argv) {
     std::atomic<size_t> next{0};
     std::mutex err_mu;
     std::string first_error;
+    std::vector<uint32_t> first_len(n_samples);
+    for (size_t i = 0; i < n_samples; ++i) first_len[i] = (uint32_t)heads[i].first_len;
     heads.clear();
     const unsigned workers = (unsigned)std::min<size_t>(std::max(args.threads, (unsigned)gpus), n_samples);
     // fewer samples than devices: every sample is cut into read shards over `per_sample` devices
@@ -522,8 +563,8 @@ int main(int argc, char** argv) {
         try {
           std::vector<const sgc_library*> sample_libs;
           for (size_t j = 0; j < per_sample; ++j) sample_libs.push_back(libs[(s * per_sample + j) % gpus]);
-          results[s] = count_sample(sample_libs, hlib.n, args.input_paths[s], offsets[s], !args.no_position_recursion,
-                                    args.rc_mode, ingest_threads);
+          results[s] = count_sample(sample_libs, hlib.n, hlib.k, args.input_paths[s], offsets[s], first_len[s],
+                                    !args.no_position_recursion, args.rc_mode, ingest_threads, !args.whole_lines);
           if (!args.quiet) {
             const SampleResult& r = results[s];
             fprintf(stderr, "Finished: %s; Fraction mapped: %.3f [%llu / %llu]\n", names[s].c_str(),
@@ -547,15 +588,18 @@ int main(int argc, char** argv) {
       unsigned long long reads = 0;
       double wait_s = 0, copy_s = 0, submit_s = 0;
       unsigned max_shards = 1;
+      unsigned long long span_reads = 0;
       for (const auto& r : results) {
         reads += r.total, wait_s += r.wait_s, copy_s += r.copy_s, submit_s += r.submit_s;
+        span_reads += r.span_reads;
         max_shards = std::max(max_shards, r.shards);
       }
       fprintf(stderr, "{\"count_s\": %.6f, \"reads\": %llu, \"samples\": %zu, \"sample_workers\": %u, "
-              "\"ingest_threads\": %u, \"gpus\": %d, \"read_shards_per_sample\": %u, \"wait_inflate_s\": %.6f, "
+              "\"ingest_threads\": %u, \"gpus\": %d, \"read_shards_per_sample\": %u, \"span_reads\": %llu, \"wait_inflate_s\": %.6f, "
               "\"copy_to_pinned_s\": %.6f, \"submit_sync_s\": %.6f, \"read_inputs_s\": %.3f, "
               "\"device_tables_s\": %.3f, \"offsets_s\": %.3f}\n",
-              count_s, reads, n_samples, workers, ingest_threads, gpus, max_shards, wait_s, copy_s, submit_s, t_inputs,
+              count_s, reads, n_samples, workers, ingest_threads, gpus, max_shards, span_reads, wait_s, copy_s, submit_s,
+              t_inputs,
               t_tables - t_inputs, t_offsets - t_tables);
     }
 

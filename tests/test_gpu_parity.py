@@ -425,3 +425,37 @@ def test_offset_tie_goes_to_reverse_and_near_ties_follow_the_oracle():
             assert (got.reverse, got.index) == (want.reverse, want.index), (flips, col)
             outcomes.add(want.reverse)
     assert outcomes == {False, True}
+
+
+# ---- span records --------------------------------------------------------------------------------
+
+def test_span_records_count_like_whole_reads():
+    """sgc_span_geometry: the guide window and one byte either side are all Counter::assign looks at
+    (counter.rs:164-174).  For every geometry — windows flush with either end of the read, offset
+    0, both orientations, recursion on and off, narrow and wide keys — span records counted under
+    the span Offset give the per-read assignment of the whole reads, which is the oracle's."""
+    rng = np.random.default_rng(4242)
+    cases = [(20, 75, 5, False, True), (20, 75, 0, False, True), (20, 75, 55, False, True), (20, 75, 54, True, True),
+             (20, 75, 0, True, True), (20, 75, 55, True, True), (20, 75, 7, True, False), (20, 20, 0, False, True),
+             (16, 50, 3, False, True), (24, 60, 11, True, True), (30, 75, 44, False, True), (28, 75, 45, True, True)]
+    for k, read_len, offset, reverse, recursion in cases:
+        guides = make_library(rng, 300, k, plant=0.05)
+        wild = b"J" if reverse else b"N"
+        seqs = make_reads(rng, guides, 3000, read_len, offset, reverse, False, wild=wild)
+        library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+        permuter = sg.Permuter.new(library)
+        off = sg.Offset(reverse, offset)
+        batch = sg.ReadBatch.from_seqs(seqs)
+        want = oracle_count(guides, seqs, True, off, recursion)
+        spans, span_off = sg.span_batch(batch, k, off, recursion)
+        assert spans.stride % 8 == 0 and spans.read_len <= k + 2 and span_off.reverse == reverse
+        got = gpu_assign(library, permuter, spans, span_off, recursion, pad=64)
+        label = (k, read_len, offset, reverse, recursion, spans.read_len, span_off)
+        assert np.array_equal(got[0], want[0]), label
+        assert np.array_equal(got[1], want[1]) and got[2:4] == want[2:4], label
+        assert got[4].kernel == 0, label  # the streaming kernel
+        c = sg.Counter(library, permuter, span_off, recursion)  # production mode, host path
+        c.submit(spans)
+        assert np.array_equal(c.finish()[0], want[1]), label
+    with pytest.raises(sg.SgcError):
+        sg.span_geometry(20, 24, sg.Offset.Forward(5))  # the Centered window does not fit

@@ -222,3 +222,39 @@ def test_one_sample_over_every_device_with_nccl(tmp_path):
     oc = orc.Counter.new(recs, olib, orc.Permuter.new(olib), orc.Offset.Forward(3), None, True, n_threads=os.cpu_count() or 4)
     text = orc.render_results([oc], ["big"], olib, None, include_zero=False)
     assert table(open(tmp_path / "many.tsv").read()) == table(text)
+
+
+@pytest.mark.gpu
+def test_span_records_and_whole_lines_give_the_same_table(tmp_path):
+    """fixed-length reads travel as span records by default; --whole-lines sends the lines.  A
+    sample with one read of another length falls back member by member.  Same table each way."""
+    from sgcount_b200 import synth
+
+    seed = 0xB2000006
+    arr = synth.make_library(seed, 3000, 20)
+    lib_path = str(tmp_path / "lib.fa")
+    with open(lib_path, "wb") as f:
+        f.write(b"".join(b">lib.%d\n%s\n" % (i, arr[i].tobytes()) for i in range(len(arr))))
+    for rev, off in ((False, 0), (True, 17)):
+        fq = str(tmp_path / f"s{int(rev)}.fastq.gz")
+        synth.Sample(seed, int(rev), arr, 75, off, rev).write_fastq(fq, 0, 300_000, reads_per_member=40_000)
+        a = run("-l", lib_path, "-i", fq, "--timing", check=True)
+        b = run("-l", lib_path, "-i", fq, "--timing", "--whole-lines", check=True)
+        assert a.stdout == b.stdout and len(a.stdout.splitlines()) > 1000
+        assert '"span_reads": 300000' in a.stderr and '"span_reads": 0' in b.stderr
+        # one shorter read in the last member: that member comes as whole lines
+        text = gzip.open(fq, "rb").read().rstrip(b"\n").split(b"\n")
+        text[-3] = text[-3][:60]
+        text[-1] = text[-1][:60]
+        odd = str(tmp_path / f"odd{int(rev)}.fastq.gz")
+        members = [text[i:i + 160_000] for i in range(0, len(text), 160_000)]
+        with open(odd, "wb") as f:
+            for m in members:
+                f.write(gzip.compress(b"\n".join(m) + b"\n", 1))
+        c = run("-l", lib_path, "-i", odd, "-a", str(off), *(["-r"] if rev else []), "--timing", check=True)
+        d = run("-l", lib_path, "-i", odd, "-a", str(off), *(["-r"] if rev else []), "--timing", "--whole-lines", check=True)
+        assert c.stdout == d.stdout
+        import re
+
+        n_span = int(re.search(r'"span_reads": (\d+)', c.stderr).group(1))
+        assert 0 < n_span < 300_000

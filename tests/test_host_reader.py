@@ -139,3 +139,53 @@ def test_blocks_edge_cases(tmp_path):
     assert "truncated" in dump(tmp_path / "trunc.fq.gz", 4, "blocks")[2]
     (tmp_path / "cut.fq.gz").write_bytes(blob[:len(blob) // 3])
     assert dump(tmp_path / "cut.fq.gz", 4, "blocks")[0] == 1
+
+
+def span_fnv(records, read_len, start, length):
+    h = 1469598103934665603
+    for _, seq in records:
+        part, mark = (seq[start:start + length], 0xFE) if len(seq) == read_len else (seq, 0xFF)
+        for c in part:
+            h = ((h ^ c) * 1099511628211) & (2**64 - 1)
+        h = ((h ^ mark) * 1099511628211) & (2**64 - 1)
+    return f"{len(records)} {h:x}"
+
+
+def test_span_framing(tmp_path):
+    """Span records (fastx.h SpanSpec): bytes [start, start + len) of every read, fixed stride, framed
+    by the inflate threads while every read has the sample's read length; a member holding a read
+    of another length comes as whole lines, and so does everything framed by the consumer itself
+    (plain files, single members, members cut inside a record).  What a counter looks at is the
+    same either way."""
+    rng = random.Random(5)
+    recs = [(b"r%d extra" % i, bytes(rng.choice(b"ACGTN") for _ in range(75))) for i in range(40000)]
+    text = b"".join(b"@" + i + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n" for i, s in recs)
+    starts = [m.start() for m in __import__("re").finditer(rb"^@r\d+ extra$", text, flags=__import__("re").M)]
+    bounds = sorted(rng.sample(starts[1:], 7))
+    aligned = [text[a:b] for a, b in zip([0] + bounds, bounds + [len(text)])]
+    spec = "75,4,22,24"
+    want = span_fnv(recs, 75, 4, 22)
+    (tmp_path / "aligned.fq.gz").write_bytes(b"".join(gzip.compress(m, 1) for m in aligned))
+    for threads in (2, 16):
+        rc, out, err = dump(tmp_path / "aligned.fq.gz", threads, "spans", spec)
+        assert rc == 0 and out == want + " 40000", (threads, out, err)  # every record travelled as a span
+    # framed by the consumer: whole lines, same content
+    (tmp_path / "plain.fq").write_bytes(text)
+    (tmp_path / "single.fq.gz").write_bytes(gzip.compress(text, 1))
+    for name in ("plain.fq", "single.fq.gz"):
+        rc, out, err = dump(tmp_path / name, 4, "spans", spec)
+        assert rc == 0 and out == want + " 0", (name, out, err)
+    # one read of another length in the middle of member 3: that member (at least) falls back
+    odd = list(recs)
+    k = sum(m.count(b"\n@r") + (1 if m.startswith(b"@r") else 0) for m in aligned[:3]) + 5
+    odd[k] = (odd[k][0], odd[k][1][:40])
+    text2 = b"".join(b"@" + i + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n" for i, s in odd)
+    starts2 = [m.start() for m in __import__("re").finditer(rb"^@r\d+ extra$", text2, flags=__import__("re").M)]
+    idx = [starts.index(b) for b in bounds]
+    aligned2 = [text2[a:b] for a, b in zip([0] + [starts2[i] for i in idx], [starts2[i] for i in idx] + [len(text2)])]
+    (tmp_path / "odd.fq.gz").write_bytes(b"".join(gzip.compress(m, 1) for m in aligned2))
+    for threads in (2, 16):
+        rc, out, err = dump(tmp_path / "odd.fq.gz", threads, "spans", spec)
+        n, h, n_span = out.split()
+        assert rc == 0 and f"{n} {h}" == span_fnv(odd, 75, 4, 22), (threads, out, err)
+        assert int(n_span) <= 40000 - len([1 for _ in aligned2[3].split(b"\n+\n")]) + 1
