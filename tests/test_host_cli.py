@@ -180,13 +180,15 @@ def test_one_sample_cut_into_read_shards_gives_the_same_table(shards, tmp_path):
     # 3.5 M reads = 266 MB of sequence lines: five 64 MB batches, so every shard gets work
     synth.Sample(seed, 0, arr, 75, 11, True).write_fastq(fq, 0, 3_500_000, reads_per_member=400_000)
     one = run("-l", lib_path, "-i", fq, "-o", str(tmp_path / "one.tsv"), check=True)
-    cut = run("-l", lib_path, "-i", fq, "-o", str(tmp_path / "cut.tsv"), "--read-shards", str(shards), "--timing", check=True)
+    cut = run("-l", lib_path, "-i", fq, "-o", str(tmp_path / "cut.tsv"), "--read-shards", str(shards), "--timing",
+              "--whole-lines", check=True)
     assert open(tmp_path / "one.tsv").read() == open(tmp_path / "cut.tsv").read()
     assert one.stderr.count("Calculated Offsets: [Reverse(11)]") == 1
     assert cut.stderr.count("Calculated Offsets: [Reverse(11)]") == 1
     fin = [l for l in one.stderr.splitlines() if l.startswith("Finished")]
     assert fin and fin == [l for l in cut.stderr.splitlines() if l.startswith("Finished")]
-    # 266 MB of sequence lines are four 64 MB batches: at most four counters get work
+    # 266 MB of whole sequence lines are four 64 MB batches: at most four counters get work (as span
+    # records, the default and what `one` used, the same reads are 84 MB)
     import re
 
     used = int(re.search(r'"read_shards_per_sample": (\d+)', cut.stderr).group(1))
