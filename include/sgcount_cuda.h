@@ -36,8 +36,8 @@ extern "C" {
 #define SGC_ERR_INVALID_ARG 1
 #define SGC_ERR_CUDA 2
 #define SGC_ERR_DUPLICATE_SEQUENCE 3 /* panic "Unexpected duplicate sequence in library", library.rs:92 */
-#define SGC_ERR_NON_ACGT_LIBRARY 4   /* library byte outside A,C,G,T: not representable 2-bit (documented deviation) */
-#define SGC_ERR_K_UNSUPPORTED 5      /* guide length outside 1..30 */
+#define SGC_ERR_NON_ACGT_LIBRARY 4   /* not returned since ABI 2: such libraries take the byte-keyed index (below) */
+#define SGC_ERR_K_UNSUPPORTED 5      /* guide length outside 1..SGC_MAX_K */
 #define SGC_ERR_READ_TOO_SHORT 6     /* Err "Sequences in reference library are larger...", offsetter.rs:154-156 */
 #define SGC_ERR_NAN_ENTROPY 7        /* panic "Unexpected minmax error in entropy", offsetter.rs:123-141 */
 #define SGC_ERR_EMPTY_READER 8       /* panic "empty reader", offsetter.rs:38 */
@@ -46,7 +46,8 @@ extern "C" {
 #define SGC_ERR_NCCL 11              /* libnccl.so.2 could not be loaded, or an NCCL call failed (sgc_reduce_counts) */
 
 #define SGC_MAX_GUIDES 4194302u
-#define SGC_MAX_K 30u
+#define SGC_MAX_K 1024u    /* guides of up to SGC_MAX_K_PACKED bases over A,C,G,T use the 2-bit tables */
+#define SGC_MAX_K_PACKED 30u
 
 /* how Record::seq_rev_comp (fxread, used at counter.rs:203) maps non-ACGT bytes; see DESIGN.md */
 #define SGC_RC_BITTRICK 0 /* c&2 ? c^4 : c^21 — 'N' becomes 'J' and 'J' becomes 'N' (default) */
@@ -72,8 +73,13 @@ int sgc_host_free(void* ptr);
  * consumes without counting (offsetter.rs:57,190-191).
  * with_permutations: 0 = --exact (count.rs:103-107 passes None), 1 = build the
  * unambiguous one-mismatch variants.
- * Errors: SGC_ERR_DUPLICATE_SEQUENCE, SGC_ERR_NON_ACGT_LIBRARY, SGC_ERR_K_UNSUPPORTED,
- * SGC_ERR_TOO_MANY_GUIDES, SGC_ERR_EMPTY_READER (n == 0; library.rs:74 unwraps).
+ * The reference keeps sequences as opaque byte strings of any length (library.rs:65-99).  Guides
+ * of up to 30 bases over A,C,G,T — every real sgRNA library — are packed 2-bit into the L2-resident
+ * tables the fast kernels use; a library with any other byte (an N, lower case) or with longer
+ * sequences is indexed by its bytes instead (sgc_library_info.opaque = 1): same results, a
+ * simple one-thread-per-read kernel, none of the roofline claims.
+ * Errors: SGC_ERR_DUPLICATE_SEQUENCE, SGC_ERR_K_UNSUPPORTED, SGC_ERR_TOO_MANY_GUIDES,
+ * SGC_ERR_EMPTY_READER (n == 0; library.rs:74 unwraps).
  */
 int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, int with_permutations,
                        sgc_library** out);
@@ -90,6 +96,7 @@ typedef struct sgc_library_info {
   uint64_t table_bytes;  /* seed directories + postings + both front tables              */
   double build_ms;       /* device time of the build kernels                             */
   uint64_t front_left_out; /* members (x2 orientations) resolved through the seed index only */
+  int32_t opaque;          /* 1: byte-keyed index (a byte outside A,C,G,T, or k > 30) */
 } sgc_library_info;
 int sgc_library_get_info(const sgc_library*, sgc_library_info* out);
 
@@ -198,11 +205,14 @@ int sgc_counter_state(sgc_counter*, uint64_t** d_state, uint64_t* n_words);
  * are folded on that device first.  Asynchronous: sgc_counter_finish(shards[root]) waits for it.
  * Every counter must come from a library of the same guides.  Errors: SGC_ERR_NCCL. */
 int sgc_reduce_counts(sgc_counter* const* shards, int n_shards, int root);
+/* Optional: create the communicators for counters on these devices ahead of time (loading NCCL and
+ * ncclCommInitAll take seconds; the CLI does this on a side thread while it builds its tables). */
+int sgc_reduce_prepare(const int* devices, int n_devices);
 
 /* Statistics of the last sgc_counter_submit_device call, for benchmarking. */
 typedef struct sgc_launch_info {
   uint32_t grid, block, smem_bytes;
-  uint32_t kernel; /* 0 = streaming fixed-stride kernel, 1 = generic kernel */
+  uint32_t kernel; /* 0 = streaming fixed-stride kernel, 1 = line kernel (any layout), 2 = byte-keyed (opaque library) */
   uint64_t launches_total;
   uint32_t replicas;   /* copies of the count vector in use (1 = none) */
   uint32_t hot_guides; /* guides counted in registers */

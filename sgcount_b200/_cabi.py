@@ -48,6 +48,7 @@ class LibraryInfo(C.Structure):
         ("table_bytes", C.c_uint64),
         ("build_ms", C.c_double),
         ("front_left_out", C.c_uint64),
+        ("opaque", C.c_int32),
     ]
 
 
@@ -86,6 +87,7 @@ SIGNATURES = {
     "sgc_counter_sync": (_int, [_vp]),
     "sgc_counter_wait_copies": (_int, [_vp, _u32]),
     "sgc_reduce_counts": (_int, [C.POINTER(_vp), _int, _int]),
+    "sgc_reduce_prepare": (_int, [C.POINTER(_int), _int]),
     "sgc_counter_reset": (_int, [_vp]),
     "sgc_counter_finish": (_int, [_vp, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "sgc_counter_state": (_int, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),

@@ -985,6 +985,14 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
                  uint32_t stride, uint32_t read_len, uint64_t first, uint64_t n_reads, int32_t* d_assign,
                  cudaStream_t stream) {
   if (n_reads <= first) return SGC_OK;
+  if (c->lib->opaque) {  // byte-keyed library (opaque.cu): one simple kernel, whatever the layout
+    c->last.kernel = 2;
+    c->last.block = 256;
+    c->last.replicas = 1;
+    c->last.hot_guides = 0;
+    c->last.launches_total += 1;
+    return opaque_count(c, d_lines, d_off, off_base, stride, read_len, first, n_reads, d_assign, stream, &c->last.grid);
+  }
   CountParams p = make_params(c, d_lines, d_off, stride, read_len, d_assign);
   p.off_base = off_base;
   p.lines_end = d_lines + n_bytes;
@@ -1135,7 +1143,7 @@ int plan_skew(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const ui
 int count_batch(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const uint32_t* d_off, uint32_t off_base,
                 uint32_t stride, uint32_t read_len, uint64_t n_reads, int32_t* d_assign, cudaStream_t stream) {
   uint64_t counted = 0;
-  if (c->auto_skew && !c->skew_planned && !d_assign && n_reads >= kSkewMinBatch) {
+  if (c->auto_skew && !c->skew_planned && !d_assign && n_reads >= kSkewMinBatch && !c->lib->opaque) {
     int rc = plan_skew(c, d_lines, n_bytes, d_off, off_base, stride, read_len, n_reads, stream, &counted);
     if (rc) return rc;
   }

@@ -43,9 +43,25 @@ int position_counts_device(const uint8_t* d_lines, const uint32_t* d_line_off, u
                            uint32_t read_len, uint64_t n_reads, uint32_t size, uint32_t* d_hist /* size*4, zeroed */,
                            cudaStream_t stream);
 
+// exclusive prefix sum of cnt[0..n) into start[0..n) on the default stream (library.cu);
+// tile_sums: scratch of (n + 2047) / 2048 + 1 words
+int exclusive_scan_u32(const uint32_t* d_cnt, uint32_t n, uint32_t* d_start, uint32_t* d_tile_sums);
+
 }  // namespace sgc
 
 struct sgc_library;
+struct sgc_counter;
+
+namespace sgc {
+// opaque.cu: libraries with a byte outside A,C,G,T or guides longer than kMaxK, kept as bytes
+constexpr uint32_t kMaxKOpaque = 1024;
+int opaque_build(sgc_library* lib, const uint8_t* d_seqs, uint64_t* n_variants, uint64_t* n_ambiguous, uint32_t* dup_guide);
+void opaque_destroy(sgc_library* lib);
+int opaque_lookup_tokens(const sgc_library* lib, const uint8_t* d_tokens, uint64_t n_tokens, int32_t* d_idx, uint8_t* d_kind);
+int opaque_count(const sgc_counter* c, const uint8_t* d_lines, const uint32_t* d_off, uint32_t off_base, uint32_t stride,
+                 uint32_t read_len, uint64_t first, uint64_t n_reads, int32_t* d_assign, cudaStream_t stream,
+                 uint32_t* grid_out);
+}  // namespace sgc
 
 struct sgc_counter {
   const sgc_library* lib = nullptr;
@@ -91,6 +107,12 @@ struct sgc_library {
   uint32_t dir_shift = 0, front_shift = 0;
   sgc::SeedParts parts{};
   size_t front_bytes = 0;
+  // opaque libraries (opaque.cu): the members' bytes and the two half indexes
+  bool opaque = false;
+  uint8_t* d_oseqs = nullptr;
+  uint32_t* d_ostart[2] = {nullptr, nullptr};
+  uint32_t* d_opost[2] = {nullptr, nullptr};
+  uint32_t oshift = 0;
   uint32_t* d_lib_hist = nullptr;  // k*4 positional counts over guides 1..n-1 (offsetter.rs:190-191)
   int sm_count = 0;
   sgc_library_info info{};

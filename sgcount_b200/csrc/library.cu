@@ -391,16 +391,15 @@ void sgc_library_destroy(sgc_library* lib) {
     cudaFree(lib->ix[o].d_front);
     cudaFree(lib->ix[o].d_keys);
   }
+  opaque_destroy(lib);
   cudaFree(lib->d_lib_hist);
   delete lib;
 }
 
 }  // extern "C"
 
-namespace {
-
-// exclusive prefix sum of cnt[0..n) into start[0..n) on the default stream
-int exclusive_scan(const uint32_t* d_cnt, uint32_t n, uint32_t* d_start, uint32_t* d_tile_sums) {
+namespace sgc {
+int exclusive_scan_u32(const uint32_t* d_cnt, uint32_t n, uint32_t* d_start, uint32_t* d_tile_sums) {
   const uint32_t tiles = (n + kScanTile - 1) / kScanTile;
   scan_tile_sums_kernel<<<tiles, kScanThreads>>>(d_cnt, n, d_tile_sums);
   scan_sums_kernel<<<1, kScanThreads>>>(d_tile_sums, tiles);
@@ -408,6 +407,9 @@ int exclusive_scan(const uint32_t* d_cnt, uint32_t n, uint32_t* d_start, uint32_
   SGC_CUDA_TRY(cudaGetLastError());
   return SGC_OK;
 }
+}  // namespace sgc
+
+namespace {
 
 // temporaries of one build, allocated before the timed region
 struct BuildScratch {
@@ -438,7 +440,7 @@ int build_index(sgc_library* lib, int o, BuildScratch& sc, BuildStatus* d_st) {
   }
   seed_count_kernel<<<blocks_for(n, T), T>>>(ix.d_keys, n, lib->dir_shift, lib->parts, cnt);
   for (int i = 0; i < kSeeds; ++i) {
-    int rc = exclusive_scan(sc.cnt[i].p, entries, sc.start[i].p, sc.sums.p);
+    int rc = exclusive_scan_u32(sc.cnt[i].p, entries, sc.start[i].p, sc.sums.p);
     if (rc) return rc;
     SGC_CUDA_TRY(cudaMemcpyAsync(sc.cur[i].p, sc.start[i].p, (size_t)entries * 4, cudaMemcpyDeviceToDevice, 0));
   }
@@ -480,7 +482,7 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
                        sgc_library** out) {
   if (!seqs || !out) return set_error(SGC_ERR_INVALID_ARG, "seqs/out is NULL");
   if (n == 0) return set_error(SGC_ERR_EMPTY_READER, "empty library (library.rs:74 unwraps on an empty table)");
-  if (k == 0 || k > kMaxK) return set_error(SGC_ERR_K_UNSUPPORTED, "guide length must be 1..30");
+  if (k == 0 || k > kMaxKOpaque) return set_error(SGC_ERR_K_UNSUPPORTED, "guide length must be 1..1024");
   if (n > SGC_MAX_GUIDES) return set_error(SGC_ERR_TOO_MANY_GUIDES, "too many guides");
   int ndev = 0;
   SGC_CUDA_TRY(cudaGetDeviceCount(&ndev));
@@ -493,8 +495,12 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   lib->n = n;
   lib->k = k;
   lib->with_perm = with_permutations != 0;
+  // The 2-bit tables hold A,C,G,T guides of up to 30 bases.  Anything else the reference accepts
+  // (library.rs keeps opaque byte strings) goes through the byte-keyed index of opaque.cu.
+  lib->opaque = k > kMaxK;
+  for (size_t i = 0, total = (size_t)n * k; i < total && !lib->opaque; ++i) lib->opaque = !is_acgt(seqs[i]);
   lib->wide = k > kNarrowMaxK;
-  lib->parts = make_seed_parts(k, lib->wide);
+  if (!lib->opaque) lib->parts = make_seed_parts(k, lib->wide);
   struct Cleanup {
     sgc_library* l;
     ~Cleanup() {
@@ -521,9 +527,9 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   BuildScratch scratch;
   SGC_CUDA_TRY(d_seqs.alloc((size_t)n * k));
   SGC_CUDA_TRY(d_st.alloc(1));
-  int rc = scratch.alloc((uint32_t)dir_entries);
+  int rc = lib->opaque ? SGC_OK : scratch.alloc((uint32_t)dir_entries);
   if (rc) return rc;
-  for (int o = 0; o < 2; ++o) {
+  for (int o = 0; o < 2 && !lib->opaque; ++o) {
     sgc_library::Index& ix = lib->ix[o];
     SGC_CUDA_TRY(cudaMalloc(&ix.d_keys, (size_t)n * sizeof(uint64_t)));
     for (int i = 0; i < kSeeds; ++i) {
@@ -551,9 +557,15 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   SGC_CUDA_TRY(cudaEventCreate(&events.b));
   const cudaEvent_t e0 = events.a, e1 = events.b;
   SGC_CUDA_TRY(cudaEventRecord(e0, 0));
-  pack_library_kernel<<<blocks_for(n, 256), 256>>>(d_seqs.p, n, k, lib->wide, lib->ix[0].d_keys, lib->ix[1].d_keys,
-                                                   d_st.p);
-  rc = lib->wide ? build_tables<true>(lib, scratch, d_st.p) : build_tables<false>(lib, scratch, d_st.p);
+  uint64_t o_variants = 0, o_ambiguous = 0;
+  uint32_t o_dup = 0xFFFFFFFFu;
+  if (lib->opaque) {
+    rc = opaque_build(lib, d_seqs.p, &o_variants, &o_ambiguous, &o_dup);
+  } else {
+    pack_library_kernel<<<blocks_for(n, 256), 256>>>(d_seqs.p, n, k, lib->wide, lib->ix[0].d_keys, lib->ix[1].d_keys,
+                                                     d_st.p);
+    rc = lib->wide ? build_tables<true>(lib, scratch, d_st.p) : build_tables<false>(lib, scratch, d_st.p);
+  }
   if (rc) return rc;
   // library positional histogram for the offset detector: records 1..n-1 (offsetter.rs:57,190-191)
   SGC_CUDA_TRY(cudaMemsetAsync(lib->d_lib_hist, 0, (size_t)k * 4 * sizeof(uint32_t), 0));
@@ -569,6 +581,11 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
 
   BuildStatus st;
   SGC_CUDA_TRY(cudaMemcpy(&st, d_st.p, sizeof st, cudaMemcpyDeviceToHost));
+  if (lib->opaque) {
+    st.dup_guide = o_dup;
+    st.n_variants = o_variants;
+    st.n_ambiguous = o_ambiguous;
+  }
   if (st.bad_guide != 0xFFFFFFFFu) {
     char buf[160];
     snprintf(buf, sizeof buf, "library sequence %u holds a byte outside A,C,G,T", st.bad_guide);
@@ -584,9 +601,12 @@ int sgc_library_create(int device, const uint8_t* seqs, uint32_t n, uint32_t k, 
   lib->info.device = device;
   lib->info.n_variants = st.n_variants;
   lib->info.n_ambiguous = st.n_ambiguous;
-  lib->info.n_slots = ((size_t)1 << log_buckets) * (lib->wide ? 2 : 4);
-  // what one counter touches: the directories, postings and front table of its orientation
-  lib->info.table_bytes = kSeeds * (dir_entries * (lib->wide ? 16 : 8) + post_words * 8) + lib->front_bytes;
+  lib->info.opaque = lib->opaque;
+  if (!lib->opaque) {
+    lib->info.n_slots = ((size_t)1 << log_buckets) * (lib->wide ? 2 : 4);
+    // what one counter touches: the directories, postings and front table of its orientation
+    lib->info.table_bytes = kSeeds * (dir_entries * (lib->wide ? 16 : 8) + post_words * 8) + lib->front_bytes;
+  }
   lib->info.build_ms = ms;
   lib->info.front_left_out = st.front_left_out;
   cleanup.l = nullptr;
@@ -611,9 +631,14 @@ int sgc_library_lookup(const sgc_library* lib, const uint8_t* tokens, uint64_t n
   SGC_CUDA_TRY(d_idx.alloc(n_tokens));
   if (kind_out) SGC_CUDA_TRY(d_kind.alloc(n_tokens));
   SGC_CUDA_TRY(cudaMemcpy(d_tok.p, tokens, n_tokens * lib->k, cudaMemcpyHostToDevice));
-  lookup_tokens_kernel<<<blocks_for(n_tokens, 256), 256>>>(lib->view(), lib->with_perm, d_tok.p, n_tokens, d_idx.p,
-                                                            d_kind.p);
-  SGC_CUDA_TRY(cudaGetLastError());
+  if (lib->opaque) {
+    int rc = opaque_lookup_tokens(lib, d_tok.p, n_tokens, d_idx.p, d_kind.p);
+    if (rc) return rc;
+  } else {
+    lookup_tokens_kernel<<<blocks_for(n_tokens, 256), 256>>>(lib->view(), lib->with_perm, d_tok.p, n_tokens, d_idx.p,
+                                                              d_kind.p);
+    SGC_CUDA_TRY(cudaGetLastError());
+  }
   SGC_CUDA_TRY(cudaMemcpy(idx_out, d_idx.p, n_tokens * sizeof(int32_t), cudaMemcpyDeviceToHost));
   if (kind_out) SGC_CUDA_TRY(cudaMemcpy(kind_out, d_kind.p, n_tokens, cudaMemcpyDeviceToHost));
   return SGC_OK;

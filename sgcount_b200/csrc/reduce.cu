@@ -12,6 +12,7 @@
 // carries an NCCL (PyTorch) the same copy is shared instead of a second one being mapped.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -71,13 +72,32 @@ int nccl_error(const char* what, int rc) {
 }
 
 // communicators of one device set, in the order of the (sorted) device list; kept for the life
-// of the process (ncclCommInitAll takes tens of milliseconds)
+// of the process (loading NCCL and ncclCommInitAll take seconds: sgc_reduce_prepare)
 struct CommSet {
   std::vector<int> devices;
   std::vector<ncclComm_t> comms;
 };
 std::mutex g_comm_mu;
 std::map<std::vector<int>, CommSet> g_comms;
+
+// the communicators of a (sorted, duplicate-free) device list, created on first use; call with
+// g_comm_mu held
+int comms_for(const std::vector<int>& devices, CommSet** out) {
+  Nccl& n = nccl();
+  if (!n.error.empty()) return set_error(SGC_ERR_NCCL, n.error);
+  CommSet& cs = g_comms[devices];
+  if (cs.comms.empty()) {
+    cs.devices = devices;
+    cs.comms.resize(devices.size());
+    const int rc = n.CommInitAll(cs.comms.data(), (int)devices.size(), devices.data());
+    if (rc != kNcclSuccess) {
+      g_comms.erase(devices);
+      return nccl_error("ncclCommInitAll", rc);
+    }
+  }
+  *out = &cs;
+  return SGC_OK;
+}
 
 __global__ void add_state_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src,
                                  size_t n) {
@@ -124,25 +144,18 @@ extern "C" int sgc_reduce_counts(sgc_counter* const* shards, int n_shards, int r
   if (leader.size() == 1) return SGC_OK;
 
   // 2. one rank per device
-  Nccl& n = nccl();
-  if (!n.error.empty()) return set_error(SGC_ERR_NCCL, n.error);
   std::vector<int> devices;
   for (auto& kv : leader) devices.push_back(kv.first);  // sorted by the map
   std::lock_guard<std::mutex> lk(g_comm_mu);  // communicators are shared: one reduce at a time per process
-  CommSet& cs = g_comms[devices];
-  if (cs.comms.empty()) {
-    cs.devices = devices;
-    cs.comms.resize(devices.size());
-    const int rc = n.CommInitAll(cs.comms.data(), (int)devices.size(), devices.data());
-    if (rc != kNcclSuccess) {
-      g_comms.erase(devices);
-      return nccl_error("ncclCommInitAll", rc);
-    }
-  }
+  CommSet* csp = nullptr;
+  int rc = comms_for(devices, &csp);
+  if (rc) return rc;
+  CommSet& cs = *csp;
+  Nccl& n = nccl();
   int root_rank = 0;
   for (size_t r = 0; r < devices.size(); ++r)
     if (devices[r] == shards[root]->lib->device) root_rank = (int)r;
-  int rc = n.GroupStart();
+  rc = n.GroupStart();
   if (rc != kNcclSuccess) return nccl_error("ncclGroupStart", rc);
   for (size_t r = 0; r < devices.size(); ++r) {
     sgc_counter* l = leader[devices[r]];
@@ -156,4 +169,17 @@ extern "C" int sgc_reduce_counts(sgc_counter* const* shards, int n_shards, int r
   rc = n.GroupEnd();
   if (rc != kNcclSuccess) return nccl_error("ncclGroupEnd", rc);
   return SGC_OK;
+}
+
+// Creates the NCCL communicators sgc_reduce_counts will need for counters on these devices
+// (ncclCommInitAll takes seconds: a host starts this on a side thread while it builds its tables).
+extern "C" int sgc_reduce_prepare(const int* devices, int n_devices) {
+  if (!devices || n_devices < 1) return set_error(SGC_ERR_INVALID_ARG, "bad device list");
+  std::vector<int> sorted(devices, devices + n_devices);
+  std::sort(sorted.begin(), sorted.end());
+  sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+  if (sorted.size() < 2) return SGC_OK;
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  CommSet* cs = nullptr;
+  return comms_for(sorted, &cs);
 }

@@ -7,9 +7,8 @@
 //           [-x] [-s N] [-t N] [-q] [-z]   [--gpus N] [--device D] [--rc-keep-n]
 //
 // Differences from the reference, all documented in DESIGN.md: rows are written in library-file
-// order (the reference iterates a randomly seeded HashMap); a library byte outside A,C,G,T is an
-// error; `-t` sets the number of samples processed concurrently (one host pipeline and one CUDA
-// stream per counter each), `--gpus` spreads the samples over devices and, when there are fewer
+// order (the reference iterates a randomly seeded HashMap); `-t` sets the number of samples
+// processed concurrently (one host pipeline and one CUDA stream per counter each), `--gpus` spreads the samples over devices and, when there are fewer
 // samples than devices, cuts every sample into read shards over gpus / samples devices whose
 // count vectors are summed with sgc_reduce_counts (NCCL).
 #include <atomic>
@@ -516,6 +515,26 @@ int main(int argc, char** argv) {
     if (ndev == 0) fail("no CUDA device: this build has no CPU fallback");
     if (args.device >= ndev) fail("no such device: %d", args.device);
     const int gpus = std::min(args.gpus, ndev - args.device);
+    // fewer samples than devices: every sample is cut into read shards over `per_sample` devices,
+    // summed with NCCL at the end; its communicators are created on a side thread meanwhile
+    const size_t per_sample =
+        args.read_shards ? args.read_shards : (n_samples < (size_t)gpus ? (size_t)gpus / n_samples : 1);
+    std::thread nccl_warmup;
+    struct JoinGuard {
+      std::thread& t;
+      ~JoinGuard() {
+        if (t.joinable()) t.join();
+      }
+    } nccl_join{nccl_warmup};
+    if (per_sample > 1 && gpus > 1) {
+      nccl_warmup = std::thread([&] {
+        for (size_t s = 0; s < n_samples; ++s) {  // one communicator set per distinct device group
+          std::vector<int> devs;
+          for (size_t j = 0; j < per_sample; ++j) devs.push_back(args.device + (int)((s * per_sample + j) % gpus));
+          sgc_reduce_prepare(devs.data(), (int)devs.size());  // a failure is reported by sgc_reduce_counts itself
+        }
+      });
+    }
     // one table per device; -x builds no Permuter (count.rs:103-107)
     std::vector<sgc_library*> libs(gpus, nullptr);
     struct LibGuard {
@@ -551,9 +570,6 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < n_samples; ++i) first_len[i] = (uint32_t)heads[i].first_len;
     heads.clear();
     const unsigned workers = (unsigned)std::min<size_t>(std::max(args.threads, (unsigned)gpus), n_samples);
-    // fewer samples than devices: every sample is cut into read shards over `per_sample` devices
-    const size_t per_sample =
-        args.read_shards ? args.read_shards : (n_samples < (size_t)gpus ? (size_t)gpus / n_samples : 1);
     const unsigned ingest_threads =
         args.ingest_threads ? args.ingest_threads : std::max(1u, std::thread::hardware_concurrency() / workers);
     auto work = [&]() {

@@ -459,3 +459,85 @@ def test_span_records_count_like_whole_reads():
         assert np.array_equal(c.finish()[0], want[1]), label
     with pytest.raises(sg.SgcError):
         sg.span_geometry(20, 24, sg.Offset.Forward(5))  # the Centered window does not fit
+
+
+# ---- libraries the 2-bit tables cannot hold -----------------------------------------------------
+
+def _opaque_library(rng, n, k, kind):
+    """kind 'long': A,C,G,T guides of k > 30 bases; 'bytes': a tenth of the guides carry an N or a
+    lower-case base (library.rs keeps sequences as opaque byte strings)"""
+    guides = make_library(rng, n, k, plant=0.05)
+    if kind == "bytes":
+        out, seen = [], set()
+        for g in guides:
+            if rng.random() < 0.1:
+                b = bytearray(g)
+                b[int(rng.integers(k))] = int(rng.choice(list(b"Nnacgt")))
+                g = bytes(b)
+            if g not in seen:
+                seen.add(g)
+                out.append(g)
+        guides = out
+    return guides
+
+
+@pytest.mark.parametrize("kind,k", [("bytes", 20), ("bytes", 12), ("long", 31), ("long", 50), ("bytes", 40)])
+def test_opaque_libraries_match_the_oracle(kind, k):
+    """A library byte outside A,C,G,T or a guide longer than 30 bases takes the byte-keyed index
+    (opaque.cu).  Per-read assignment, counts and the Permuter's observable lookups equal the
+    oracle's in both orientations, both rc modes, fixed and variable length, recursion on and off."""
+    rng = np.random.default_rng(1000 + k)
+    guides = _opaque_library(rng, 400, k, kind)
+    library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+    permuter = sg.Permuter.new(library)
+    assert permuter.info().opaque == 1
+    olib, _ = oracle_library(guides)
+    operm = orc.Permuter.new(olib)
+    # composed lookup on members, their lexicon variants and noise
+    tokens = []
+    for g in guides[:60]:
+        tokens.append(g)
+        for _ in range(4):
+            b = bytearray(g)
+            b[int(rng.integers(k))] = int(rng.choice(list(b"ACGTNx")))
+            tokens.append(bytes(b))
+    idx, kinds = permuter.lookup(tokens)
+    for t, i, kd in zip(tokens, idx, kinds):
+        want = olib.contains_index(t)
+        if want >= 0:
+            assert (i, kd) == (want, 1), t
+        else:
+            want = operm.contains_index(t)
+            assert (i, kd) == ((want, 2) if want >= 0 else (-1, 0)), t
+    for case in range(6):
+        read_len = int(rng.integers(k + 1, k + 50))
+        offset = int(rng.integers(0, read_len - k + 1))
+        reverse, variable = bool(case & 1), bool(case & 2)
+        recursion, with_perm = case != 4, case != 5
+        rc_mode = _cabi.RC_KEEP_N if case >= 3 else _cabi.RC_BITTRICK
+        seqs = make_reads(rng, guides, 2000, read_len, offset, reverse, variable)
+        off = sg.Offset(reverse, offset)
+        got = gpu_assign(library, permuter if with_perm else None, sg.ReadBatch.from_seqs(seqs), off, recursion, rc_mode)
+        want = oracle_count(guides, seqs, with_perm, off, recursion, rc_mode)
+        label = (kind, k, case, read_len, offset, reverse, variable)
+        assert np.array_equal(got[0], want[0]), label
+        assert np.array_equal(got[1], want[1]) and got[2:4] == want[2:4], label
+        assert got[4].kernel == 2, label
+        c = sg.Counter(library, permuter if with_perm else None, off, recursion, rc_mode)
+        c.submit(sg.ReadBatch.from_seqs(seqs))
+        c.submit(sg.ReadBatch.from_seqs(seqs))
+        assert np.array_equal(c.finish()[0], 2 * want[1]), label
+    # the offset detector works on bytes and does not care how the library is indexed
+    seqs = make_reads(rng, guides, 3000, k + 30, 7)
+    got = sg.entropy_offset(library, sg.ReadBatch.from_seqs(seqs), 5000)
+    want = orc.entropy_offset(oracle_library(guides)[1], orc.Records.from_seqs(seqs), 5000)
+    assert (got.reverse, got.index) == (want.reverse, want.index)
+
+
+def test_opaque_library_duplicates_and_limits():
+    with pytest.raises(sg.SgcError) as e:
+        sg.Library([b"ACGTNACGTA", b"TTGTNACGTA", b"ACGTNACGTA"], [b"a", b"b", b"c"])
+    assert e.value.code == _cabi.ERR_DUPLICATE_SEQUENCE and "ACGTNACGTA" in str(e.value)
+    with pytest.raises(sg.SgcError) as e:
+        sg.Library([b"A" * 1025], [b"a"])
+    assert e.value.code == _cabi.ERR_K_UNSUPPORTED

@@ -149,10 +149,17 @@ def test_library():
         sg.Library.from_reader(sg.ReadBatch.from_seqs([b"ACTG", b"ACT"]))
 
 
-def test_library_rejects_what_two_bits_cannot_hold():
-    with pytest.raises(sg.SgcError) as e:
-        sg.Library.from_reader(batch(b"ACTG", b"ACNG"))
-    assert e.value.code == _cabi.ERR_NON_ACGT_LIBRARY
-    with pytest.raises(sg.SgcError) as e:
-        sg.Library.from_reader(batch(b"A" * 31))
-    assert e.value.code == _cabi.ERR_K_UNSUPPORTED
+def test_library_accepts_what_two_bits_cannot_hold():
+    """library.rs:65-99 keeps opaque byte strings of any length: an N in a guide, or 31 bases, is a
+    legal library (byte-keyed index, opaque.cu), and behaves like any other"""
+    library = sg.Library.from_reader(batch(b"ACTG", b"ACNG"))
+    assert library.contains(b"ACNG") == b"seq.1" and library.contains(b"ACTG") == b"seq.0"
+    assert library.contains(b"ACAG") is None
+    permuter = sg.Permuter.new(library)
+    assert permuter.contains(b"ACAG") is None          # parents ACTG and ACNG: the Permuter's null set
+    assert permuter.contains(b"CCNG") == b"ACNG"
+    assert permuter.contains(b"ACNN") == b"ACNG"       # N is in the lexicon (permutes.rs:3)
+    assert permuter.contains(b"ACNg") is None          # g is not
+    long = sg.Library.from_reader(batch(b"A" * 31, b"C" * 31))
+    assert long.contains(b"A" * 31) == b"seq.0" and long._exact.info().opaque == 1
+    assert sg.Permuter.new(long).contains(b"A" * 30 + b"G") == b"A" * 31
