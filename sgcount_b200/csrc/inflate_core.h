@@ -1,0 +1,346 @@
+// inflate_core.h — one gzip member (RFC 1952 framing, RFC 1951 DEFLATE), decoded by ONE sequential
+// context: a thread of the device kernel in gzip.cu, or the host (the same source compiles with
+// g++ for tests/test_device_inflate_core.py, which checks it against zlib on every block kind).
+//
+// Written from the RFCs for this use: many small members (BGZF blocks, the blocked gzip that
+// sequencers and bgzip write) decoded side by side, one thread each, so the state per stream must
+// be small.  Huffman codes are kept in canonical form — count of codes per length + symbols in code
+// order, 640 bytes for the literal/length alphabet — and decoded through an 8-bit look-ahead table
+// (covers every code of up to 8 bits: the bases and quality characters of a FASTQ) with the
+// bit-serial canonical walk behind it for longer codes.  The tables live wherever the `Tables`
+// policy puts them: plain arrays on the host, bank-interleaved shared memory on the device.
+#pragma once
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define SGC_HD __host__ __device__ __forceinline__
+#else
+#define SGC_HD inline
+#endif
+
+namespace sgc {
+namespace inflate {
+
+enum Status : int {
+  kOk = 0,
+  kBadHeader = 1,      // not a gzip member (magic, method, reserved flags)
+  kTruncated = 2,      // input ended inside the member
+  kBadBlock = 3,       // reserved block type, stored-length check, bad code lengths
+  kBadCode = 4,        // a bit pattern that is no code, or an invalid length / distance symbol
+  kBadDistance = 5,    // a match reaching before the start of the member's output
+  kOutputFull = 6,     // more output than the caller's capacity
+};
+
+constexpr int kMaxBits = 15;
+constexpr int kLitLenSyms = 288, kDistSyms = 32, kFastBits = 8, kDistFastBits = 6;
+
+// Plain-array tables (host, and the reference point for the device layout).
+struct PlainTables {
+  uint16_t lcount[kMaxBits + 1], lsym[kLitLenSyms];
+  uint16_t dcount[kMaxBits + 1], dsym[kDistSyms];
+  uint16_t lfast[1 << kFastBits];  // (symbol << 4) | code length, 0 = longer than kFastBits
+  uint16_t dfast[1 << kDistFastBits];
+  SGC_HD uint16_t get_lcount(int i) const { return lcount[i]; }
+  SGC_HD void set_lcount(int i, uint16_t v) { lcount[i] = v; }
+  SGC_HD uint16_t get_lsym(int i) const { return lsym[i]; }
+  SGC_HD void set_lsym(int i, uint16_t v) { lsym[i] = v; }
+  SGC_HD uint16_t get_dcount(int i) const { return dcount[i]; }
+  SGC_HD void set_dcount(int i, uint16_t v) { dcount[i] = v; }
+  SGC_HD uint16_t get_dsym(int i) const { return dsym[i]; }
+  SGC_HD void set_dsym(int i, uint16_t v) { dsym[i] = v; }
+  SGC_HD uint16_t get_lfast(int i) const { return lfast[i]; }
+  SGC_HD void set_lfast(int i, uint16_t v) { lfast[i] = v; }
+  SGC_HD uint16_t get_dfast(int i) const { return dfast[i]; }
+  SGC_HD void set_dfast(int i, uint16_t v) { dfast[i] = v; }
+};
+
+// LSB-first bit reader over a byte range; reads past the end deliver zeros and set `overrun`.
+struct BitReader {
+  const uint8_t* in;
+  size_t len, pos;
+  uint64_t buf;
+  int cnt;
+  bool overrun;
+  SGC_HD void init(const uint8_t* p, size_t n, size_t at) {
+    in = p;
+    len = n;
+    pos = at;
+    buf = 0;
+    cnt = 0;
+    overrun = false;
+  }
+  SGC_HD void refill() {  // at least 56 valid bits afterwards
+    while (cnt <= 56) {
+      uint64_t b = 0;
+      if (pos < len)
+        b = in[pos];
+      else if (pos >= len + 8)
+        overrun = true;  // more than the slack a decoder may look ahead
+      ++pos;
+      buf |= b << cnt;
+      cnt += 8;
+    }
+  }
+  SGC_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
+  SGC_HD void drop(int n) {
+    buf >>= n;
+    cnt -= n;
+  }
+  SGC_HD uint32_t take(int n) {  // n <= 32, after a refill
+    const uint32_t v = peek(n);
+    drop(n);
+    return v;
+  }
+  // bytes of input consumed so far, counting whole bytes still in the buffer as unread
+  SGC_HD size_t consumed() const { return pos - (size_t)(cnt >> 3); }
+  SGC_HD void align_to_byte() { drop(cnt & 7); }
+};
+
+// Canonical code of one alphabet from its code lengths: counts per length and symbols in code
+// order.  Returns false for an over-subscribed set, or an incomplete one that is not the single
+// code RFC 1951 allows for a one-symbol distance alphabet.
+template <typename SetCount, typename SetSym>
+SGC_HD bool build_canonical(const uint8_t* lengths, int n, SetCount set_count, SetSym set_sym, uint16_t* count_out,
+                            bool must_be_complete = false) {
+  uint16_t count[kMaxBits + 1];
+  for (int i = 0; i <= kMaxBits; ++i) count[i] = 0;
+  for (int i = 0; i < n; ++i) ++count[lengths[i]];
+  int left = 1;  // codes still available at the current length
+  for (int l = 1; l <= kMaxBits; ++l) {
+    left <<= 1;
+    left -= count[l];
+    if (left < 0) return false;  // over-subscribed
+  }
+  uint16_t offs[kMaxBits + 1];
+  offs[1] = 0;
+  for (int l = 1; l < kMaxBits; ++l) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
+  for (int i = 0; i < n; ++i)
+    if (lengths[i]) set_sym(offs[lengths[i]]++, (uint16_t)i);
+  for (int l = 0; l <= kMaxBits; ++l) {
+    set_count(l, count[l]);
+    count_out[l] = count[l];
+  }
+  // incomplete: legal only for a literal/length or distance alphabet whose codes all have length 1
+  // (a lone distance code — or none: a block of literals only), as zlib decides it
+  if (left == 0) return true;
+  if (must_be_complete) return false;
+  for (int l = 2; l <= kMaxBits; ++l)
+    if (count[l]) return false;
+  return true;
+}
+
+// Bit-serial canonical decode: the code is read most significant bit first; at each length the
+// codes are consecutive, so "code - first < count" decides membership (RFC 1951 3.2.2).
+template <typename GetCount, typename GetSym>
+SGC_HD int decode_slow(BitReader& br, GetCount get_count, GetSym get_sym) {
+  int code = 0, first = 0, index = 0;
+  uint64_t bits = br.buf;
+  for (int l = 1; l <= kMaxBits; ++l) {
+    code |= (int)(bits & 1);
+    bits >>= 1;
+    const int cnt = get_count(l);
+    if (code - first < cnt) {
+      br.drop(l);
+      return get_sym(index + (code - first));
+    }
+    index += cnt;
+    first = (first + cnt) << 1;
+    code <<= 1;
+  }
+  return -1;
+}
+
+// RFC 1951 3.2.5 as arithmetic (no tables to place in device memory): base value and number of
+// extra bits of length symbol c (257 + c) and of distance symbol d.
+SGC_HD uint32_t len_extra_bits(int c) { return c < 8 || c == 28 ? 0u : (uint32_t)(c >> 2) - 1u; }
+SGC_HD uint32_t len_base(int c) { return c < 8 ? (uint32_t)c + 3u : (c == 28 ? 258u : ((4u | ((uint32_t)c & 3u)) << len_extra_bits(c)) + 3u); }
+SGC_HD uint32_t dist_extra_bits(int d) { return d < 4 ? 0u : (uint32_t)(d >> 1) - 1u; }
+SGC_HD uint32_t dist_base(int d) { return d < 4 ? (uint32_t)d + 1u : ((2u | ((uint32_t)d & 1u)) << dist_extra_bits(d)) + 1u; }
+// order in which the code-length code's own lengths are sent (RFC 1951 3.2.7)
+SGC_HD int cl_order(int i) { return "\x10\x11\x12\x00\x08\x07\x09\x06\x0a\x05\x0b\x04\x0c\x03\x0d\x02\x0e\x01\x0f"[i]; }
+
+template <typename GetSym, typename SetFast>
+SGC_HD void fill_lookahead(const uint16_t* count, int bits, GetSym get_sym, SetFast set_fast) {
+  for (int i = 0; i < (1 << bits); ++i) set_fast(i, 0);
+  int code = 0, index = 0;
+  for (int l = 1; l <= bits; ++l) {
+    for (int j = 0; j < count[l]; ++j, ++code, ++index) {
+      // the code's bits arrive most significant first: reverse them into stream order
+      uint32_t r = 0;
+      for (int b = 0; b < l; ++b) r |= ((uint32_t)(code >> b) & 1u) << (l - 1 - b);
+      const uint16_t entry = (uint16_t)((get_sym(index) << 4) | l);
+      for (uint32_t i = r; i < (1u << bits); i += 1u << l) set_fast((int)i, entry);
+    }
+    code <<= 1;
+  }
+}
+
+// Tables of one block from the two length arrays; also fills the look-ahead tables.
+template <typename Tables>
+SGC_HD bool install_codes(Tables& t, const uint8_t* ll, int nl, const uint8_t* dl, int nd) {
+  uint16_t lc[kMaxBits + 1], dc[kMaxBits + 1];
+  if (!build_canonical(ll, nl, [&](int i, uint16_t v) { t.set_lcount(i, v); }, [&](int i, uint16_t v) { t.set_lsym(i, v); }, lc))
+    return false;
+  if (!build_canonical(dl, nd, [&](int i, uint16_t v) { t.set_dcount(i, v); }, [&](int i, uint16_t v) { t.set_dsym(i, v); }, dc))
+    return false;
+  if (lc[0] == nl) return false;  // no literal/length code at all: not even end-of-block
+  // look-ahead tables: walk the codes of up to `bits` bits in canonical order
+  fill_lookahead(lc, kFastBits, [&](int i) { return t.get_lsym(i); }, [&](int i, uint16_t v) { t.set_lfast(i, v); });
+  fill_lookahead(dc, kDistFastBits, [&](int i) { return t.get_dsym(i); }, [&](int i, uint16_t v) { t.set_dfast(i, v); });
+  return true;
+}
+
+// One gzip member at in[0 .. in_len).  On kOk: *consumed = bytes of the member including its
+// 8-byte trailer, *produced = bytes written to out, *crc32 / *isize = the trailer's fields.
+template <typename Tables>
+SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, Tables& t, size_t* consumed,
+                         size_t* produced, uint32_t* crc32, uint32_t* isize) {
+  // ---- RFC 1952 header
+  if (in_len < 18) return in_len < 4 || (in[0] == 0x1f && in[1] == 0x8b) ? kTruncated : kBadHeader;
+  if (in[0] != 0x1f || in[1] != 0x8b || in[2] != 8 || (in[3] & 0xE0)) return kBadHeader;
+  const uint8_t flg = in[3];
+  size_t pos = 10;
+  if (flg & 4) {  // FEXTRA (BGZF keeps its block size here)
+    if (pos + 2 > in_len) return kTruncated;
+    pos += 2 + ((size_t)in[pos] | ((size_t)in[pos + 1] << 8));
+  }
+  for (int field = 0; field < 2; ++field)  // FNAME, FCOMMENT: zero-terminated
+    if (flg & (field ? 16 : 8)) {
+      while (pos < in_len && in[pos]) ++pos;
+      ++pos;
+    }
+  if (flg & 2) pos += 2;  // FHCRC
+  if (pos >= in_len) return kTruncated;
+
+  // ---- RFC 1951 blocks
+  BitReader br;
+  br.init(in, in_len, pos);
+  size_t op = 0;
+  for (;;) {
+    br.refill();
+    const uint32_t last = br.take(1), type = br.take(2);
+    if (type == 0) {  // stored
+      br.align_to_byte();
+      br.refill();
+      const uint32_t n = br.take(16), nn = br.take(16);
+      if ((n ^ nn) != 0xFFFFu) return br.overrun ? kTruncated : kBadBlock;
+      size_t at = br.consumed();  // the buffer holds whole bytes only
+      if (at + n > in_len) return kTruncated;
+      if (op + n > out_cap) return kOutputFull;
+      for (uint32_t i = 0; i < n; ++i) out[op + i] = in[at + i];
+      op += n;
+      br.init(in, in_len, at + n);
+    } else if (type == 3) {
+      return br.overrun ? kTruncated : kBadBlock;
+    } else {
+      uint8_t lengths[kLitLenSyms + kDistSyms];
+      int nl, nd;
+      if (type == 1) {  // fixed code
+        nl = 288;
+        nd = 32;  // 30 and 31 complete the 5-bit code and are errors if they occur
+        for (int i = 0; i < 144; ++i) lengths[i] = 8;
+        for (int i = 144; i < 256; ++i) lengths[i] = 9;
+        for (int i = 256; i < 280; ++i) lengths[i] = 7;
+        for (int i = 280; i < 288; ++i) lengths[i] = 8;
+        for (int i = 0; i < 32; ++i) lengths[288 + i] = 5;
+      } else {  // dynamic code: the code-length code first
+        nl = (int)br.take(5) + 257;
+        nd = (int)br.take(5) + 1;
+        const int nc = (int)br.take(4) + 4;
+        if (nl > 286 || nd > 30) return br.overrun ? kTruncated : kBadBlock;
+        uint8_t cl[19];
+        for (int i = 0; i < 19; ++i) cl[i] = 0;
+        for (int i = 0; i < nc; ++i) {
+          br.refill();
+          cl[cl_order(i)] = (uint8_t)br.take(3);
+        }
+        // the code-length alphabet is tiny: its canonical form lives in registers / local arrays
+        uint16_t ccount[kMaxBits + 1], csym[19], dummy[kMaxBits + 1];
+        if (!build_canonical(cl, 19, [&](int i, uint16_t v) { ccount[i] = v; }, [&](int i, uint16_t v) { csym[i] = v; }, dummy, true))
+          return kBadBlock;
+        int i = 0;
+        while (i < nl + nd) {
+          br.refill();
+          const int s = decode_slow(br, [&](int l) { return (int)ccount[l]; }, [&](int k) { return (int)csym[k]; });
+          if (s < 0) return br.overrun ? kTruncated : kBadCode;
+          if (s < 16) {
+            lengths[i++] = (uint8_t)s;
+          } else {
+            uint8_t prev = 0;
+            int rep;
+            if (s == 16) {
+              if (i == 0) return kBadBlock;
+              prev = lengths[i - 1];
+              rep = 3 + (int)br.take(2);
+            } else if (s == 17) {
+              rep = 3 + (int)br.take(3);
+            } else {
+              rep = 11 + (int)br.take(7);
+            }
+            if (i + rep > nl + nd) return kBadBlock;
+            while (rep--) lengths[i++] = prev;
+          }
+        }
+        if (lengths[256] == 0) return kBadBlock;  // no end-of-block code
+        // the decoder below wants the distance lengths at a fixed place
+        if (nl != 288)
+          for (int j = nd - 1; j >= 0; --j) lengths[288 + j] = lengths[nl + j];
+      }
+      if (!install_codes(t, lengths, nl, lengths + 288, nd)) return kBadBlock;
+      // ---- symbols
+      for (;;) {
+        br.refill();
+        int sym;
+        const uint16_t e = t.get_lfast((int)br.peek(kFastBits));
+        if (e) {
+          br.drop(e & 15);
+          sym = e >> 4;
+        } else {
+          sym = decode_slow(br, [&](int l) { return (int)t.get_lcount(l); }, [&](int k) { return (int)t.get_lsym(k); });
+          if (sym < 0) return br.overrun ? kTruncated : kBadCode;
+        }
+        if (sym < 256) {
+          if (op >= out_cap) return kOutputFull;
+          out[op++] = (uint8_t)sym;
+          continue;
+        }
+        if (sym == 256) break;
+        sym -= 257;
+        if (sym >= 29) return kBadCode;
+        const uint32_t length = len_base(sym) + br.take((int)len_extra_bits(sym));
+        br.refill();
+        int ds;
+        const uint16_t de = t.get_dfast((int)br.peek(kDistFastBits));
+        if (de) {
+          br.drop(de & 15);
+          ds = de >> 4;
+        } else {
+          ds = decode_slow(br, [&](int l) { return (int)t.get_dcount(l); }, [&](int k) { return (int)t.get_dsym(k); });
+          if (ds < 0) return br.overrun ? kTruncated : kBadCode;
+        }
+        if (ds >= 30) return kBadCode;
+        const uint32_t dist = dist_base(ds) + br.take((int)dist_extra_bits(ds));
+        if (dist > op) return kBadDistance;
+        if (op + length > out_cap) return kOutputFull;
+        for (uint32_t i = 0; i < length; ++i) out[op + i] = out[op + i - dist];  // byte by byte: overlap is the point
+        op += length;
+      }
+      if (br.overrun) return kTruncated;
+    }
+    if (last) break;
+  }
+  // ---- trailer
+  br.align_to_byte();
+  size_t at = br.consumed();
+  if (at + 8 > in_len) return kTruncated;
+  *crc32 = (uint32_t)in[at] | ((uint32_t)in[at + 1] << 8) | ((uint32_t)in[at + 2] << 16) | ((uint32_t)in[at + 3] << 24);
+  *isize = (uint32_t)in[at + 4] | ((uint32_t)in[at + 5] << 8) | ((uint32_t)in[at + 6] << 16) | ((uint32_t)in[at + 7] << 24);
+  *consumed = at + 8;
+  *produced = op;
+  return kOk;
+}
+
+}  // namespace inflate
+}  // namespace sgc

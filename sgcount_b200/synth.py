@@ -27,6 +27,7 @@ def _load():
         L.sgs_sample_fill_host.argtypes = [vp, u64, u64, vp, C.c_int]
         L.sgs_sample_fill_device.argtypes = [vp, C.c_int, u64, u64, vp, vp]
         L.sgs_sample_write_fastq.argtypes = [vp, u64, u64, C.c_char_p, u64, C.c_int, C.c_int]
+        L.sgs_sample_write_fastq_bgzf.argtypes = [vp, u64, u64, C.c_char_p, C.c_int, C.c_int, u32]
         _lib = L
     return _lib
 
@@ -81,3 +82,9 @@ class Sample:
                     n_threads: int = 0) -> None:
         _check(_load().sgs_sample_write_fastq(self._h, first, n_reads, path.encode(), reads_per_member, gz_level,
                                               n_threads or (os.cpu_count() or 1)))
+
+    def write_fastq_bgzf(self, path: str, first: int, n_reads: int, gz_level: int = 1, n_threads: int = 0,
+                         block_bytes: int = 65280) -> None:
+        """BGZF (bgzip's blocked gzip): <= 64 KB members with the 'BC' extra field, cut anywhere"""
+        _check(_load().sgs_sample_write_fastq_bgzf(self._h, first, n_reads, path.encode(), gz_level,
+                                                   n_threads or (os.cpu_count() or 1), block_bytes))

@@ -367,4 +367,109 @@ int sgs_sample_write_fastq(const sgs_sample* s, uint64_t first_read, uint64_t n_
   return 0;
 }
 
+// BGZF: the blocked gzip that bgzip and sequencers write — members of at most 64 KB whose extra field
+// ('B','C', block size - 1) lets a reader walk the blocks without inflating them.  Like bgzip, blocks
+// are cut every `block_bytes` of text wherever that falls, not at record boundaries.
+int sgs_sample_write_fastq_bgzf(const sgs_sample* s, uint64_t first_read, uint64_t n_reads, const char* path, int gz_level,
+                                int n_threads, uint32_t block_bytes) {
+  if (!s || !path) return fail("NULL argument");
+  if (n_threads < 1) n_threads = 1;
+  if (block_bytes == 0 || block_bytes > 65280) block_bytes = 65280;
+  if (gz_level < 1) gz_level = 1;
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(std::string("cannot create ") + path);
+  const SampleView v = s->host_view();
+  const uint32_t L = s->read_len;
+  const uint64_t seg_reads = 32768;  // a thread's unit of work
+  const uint64_t n_segs = (n_reads + seg_reads - 1) / seg_reads;
+  std::string carry;  // text of a segment's tail that did not fill a block: prepended to the next segment
+  for (uint64_t g0 = 0; g0 < n_segs; g0 += n_threads) {
+    const uint64_t g1 = std::min<uint64_t>(n_segs, g0 + n_threads);
+    std::vector<std::string> texts(g1 - g0), blobs(g1 - g0);
+    std::vector<int> status(g1 - g0, 0);
+    {
+      std::vector<std::thread> pool;
+      for (uint64_t g = g0; g < g1; ++g)
+        pool.emplace_back([&, g]() {
+          const uint64_t lo = g * seg_reads, hi = std::min(n_reads, lo + seg_reads);
+          std::string& text = texts[g - g0];
+          text.reserve((hi - lo) * (2 * L + 24));
+          std::vector<uint8_t> line(L + 1);
+          const std::string qual(L, 'I');
+          char hdr[32];
+          for (uint64_t i = lo; i < hi; ++i) {
+            make_read(v, first_read + i, line.data());
+            int hn = snprintf(hdr, sizeof hdr, "@r%llu\n", (unsigned long long)(first_read + i));
+            text.append(hdr, hn);
+            text.append((const char*)line.data(), L + 1);
+            text.append("+\n");
+            text.append(qual);
+            text.push_back('\n');
+          }
+        });
+      for (auto& th : pool) th.join();
+    }
+    // block boundaries run through the whole file: segment g starts with what g - 1 left over
+    std::vector<size_t> head(g1 - g0, 0);
+    for (uint64_t g = g0; g < g1; ++g) {
+      std::string& text = texts[g - g0];
+      text.insert(0, carry);
+      const bool last = g + 1 == n_segs;
+      const size_t whole = last ? text.size() : text.size() / block_bytes * block_bytes;
+      carry.assign(text, whole, std::string::npos);
+      text.resize(whole);
+    }
+    {
+      std::vector<std::thread> pool;
+      for (uint64_t g = g0; g < g1; ++g)
+        pool.emplace_back([&, g]() {
+          const std::string& text = texts[g - g0];
+          std::string& outb = blobs[g - g0];
+          std::vector<unsigned char> cbuf(block_bytes + 1024);
+          for (size_t at = 0; at < text.size(); at += block_bytes) {
+            const size_t n = std::min<size_t>(block_bytes, text.size() - at);
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (deflateInit2(&zs, gz_level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
+              status[g - g0] = 1;
+              return;
+            }
+            zs.next_in = (Bytef*)text.data() + at;
+            zs.avail_in = (uInt)n;
+            zs.next_out = cbuf.data();
+            zs.avail_out = (uInt)cbuf.size();
+            const int rc = deflate(&zs, Z_FINISH);
+            const size_t clen = zs.total_out;
+            deflateEnd(&zs);
+            if (rc != Z_STREAM_END || clen + 26 > 65536) {
+              status[g - g0] = 1;
+              return;
+            }
+            const uint32_t bsize = (uint32_t)(18 + clen + 8 - 1), crc = (uint32_t)crc32(0L, (const Bytef*)text.data() + at, (uInt)n);
+            const unsigned char hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0,
+                                           (unsigned char)(bsize & 0xff), (unsigned char)(bsize >> 8)};
+            outb.append((const char*)hdr, 18);
+            outb.append((const char*)cbuf.data(), clen);
+            const uint32_t tail[2] = {crc, (uint32_t)n};
+            outb.append((const char*)tail, 8);
+          }
+        });
+      for (auto& th : pool) th.join();
+    }
+    for (size_t i = 0; i < blobs.size(); ++i)
+      if (status[i] || fwrite(blobs[i].data(), 1, blobs[i].size(), f) != blobs[i].size()) {
+        fclose(f);
+        return fail("bgzf/write failed");
+      }
+  }
+  // the empty end-of-file block of the BGZF specification
+  static const unsigned char eof_block[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (fwrite(eof_block, 1, 28, f) != 28) {
+    fclose(f);
+    return fail("bgzf/write failed");
+  }
+  fclose(f);
+  return 0;
+}
+
 }  // extern "C"

@@ -48,6 +48,11 @@ int sgs_sample_fill_device(sgs_sample*, int device, uint64_t first_read, uint64_
 int sgs_sample_write_fastq(const sgs_sample*, uint64_t first_read, uint64_t n_reads, const char* path,
                            uint64_t reads_per_member, int gz_level, int n_threads);
 
+/* The same records as BGZF (bgzip's blocked gzip: members of <= 64 KB with the 'BC' block-size extra
+ * field, cut every block_bytes of text wherever that falls, and the empty end-of-file block). */
+int sgs_sample_write_fastq_bgzf(const sgs_sample*, uint64_t first_read, uint64_t n_reads, const char* path, int gz_level,
+                                int n_threads, uint32_t block_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,3 +46,26 @@ for gpus in sorted({1, torch.cuda.device_count()}):
           f"rows {tables[gpus].count(10) - 1}", flush=True)
 assert len(set(tables.values())) == 1, "tables differ between GPU counts"
 print("tables identical; offsets as planted:", want)
+
+# Config 5 in small: ONE sample (the first file grown to `one_reads` reads) on 1 GPU and cut into
+# read shards over all visible GPUs (sgc_reduce_counts sums the shard vectors with NCCL): identical
+# tables, the offset detected once.  Whole lines and span records both.
+one_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 8 * n_reads
+big = os.path.join(tmp, "big.fastq.gz")
+synth.Sample(seed, 100, arr, 75, 9, False).write_fastq(big, 0, one_reads, reads_per_member=1 << 20, gz_level=1)
+single = {}
+for gpus in sorted({1, torch.cuda.device_count()}):
+    for extra in ([], ["--whole-lines"]):
+        out = os.path.join(tmp, f"big{gpus}{len(extra)}.tsv")
+        p = subprocess.run([exe, "-l", lib, "-i", big, "-o", out, "--gpus", str(gpus), "--timing", *extra],
+                           capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        assert p.stderr.count("Calculated Offsets: [Forward(9)]") == 1, p.stderr
+        t = json.loads([l for l in p.stderr.splitlines() if l.startswith("{")][-1])
+        single[(gpus, len(extra))] = open(out, "rb").read()
+        print(f"one sample, gpus={gpus} {'whole lines' if extra else 'span records'}: count_s {t['count_s']:.3f}  "
+              f"{t['reads'] / t['count_s'] / 1e6:.1f} M reads/s  shards {t['read_shards_per_sample']}  "
+              f"wait_inflate {t['wait_inflate_s']:.3f} copy {t['copy_to_pinned_s']:.3f} submit {t['submit_sync_s']:.3f} "
+              f"tables {t['device_tables_s']:.2f} s", flush=True)
+assert len(set(single.values())) == 1, "single-sample tables differ between GPU counts / framings"
+print("single sample: tables identical on 1 and", torch.cuda.device_count(), "GPUs, offset detected once")
