@@ -43,6 +43,8 @@ extern "C" {
 #define SGC_ERR_EMPTY_READER 8       /* panic "empty reader", offsetter.rs:38 */
 #define SGC_ERR_TOO_MANY_GUIDES 9    /* more than SGC_MAX_GUIDES library sequences */
 #define SGC_ERR_BATCH_TOO_LARGE 10   /* a variable-length batch must stay below 4 GiB (u32 line offsets) */
+#define SGC_ERR_GZIP 12              /* a gzip block did not inflate on the device (sgc_fastq_stream_*) */
+#define SGC_ERR_FASTQ_FORMAT 13      /* not fixed-length 4-line FASTQ (sgc_fastq_stream_*): count it through the host path */
 #define SGC_ERR_NCCL 11              /* libnccl.so.2 could not be loaded, or an NCCL call failed (sgc_reduce_counts) */
 
 #define SGC_MAX_GUIDES 4194302u
@@ -208,6 +210,31 @@ int sgc_reduce_counts(sgc_counter* const* shards, int n_shards, int root);
 /* Optional: create the communicators for counters on these devices ahead of time (loading NCCL and
  * ncclCommInitAll take seconds; the CLI does this on a side thread while it builds its tables). */
 int sgc_reduce_prepare(const int* devices, int n_devices);
+
+/* ---- FASTQ straight from BGZF blocks -----------------------------------------------------------
+ * The reference reads a sample through fxread::initialize_reader (count.rs:24): gzip inflate and
+ * line splitting on the host.  For blocked gzip (BGZF: bgzip, sequencer output — independent
+ * members of at most 64 KB that carry their size in a 'BC' extra field) the whole ingest runs on
+ * the device instead: one thread inflates each block, the text is framed into records by a
+ * newline scan, the guide-window span of every sequence line is cut out and counted, and the only
+ * bytes that cross PCIe are the compressed ones.
+ *
+ * counter: created with the SPAN offset of sgc_span_geometry for reads of read_len bytes; the
+ * stream counts into it (same device, same CUDA stream).  Only fixed-length 4-line FASTQ is framed
+ * here; anything else fails with SGC_ERR_FASTQ_FORMAT (a corrupt block: SGC_ERR_GZIP) and the
+ * caller resets the counter and counts the sample through sgc_counter_submit instead.
+ * submit: n_blocks consecutive blocks, in file order, continuing where the previous call stopped;
+ * gz + block_begin[i] .. gz + block_begin[i + 1] is block i (host memory), block_isize[i] its
+ * ISIZE field.  One call is one wave: it should carry thousands of blocks (one device thread
+ * each) and must inflate to less than 2 GiB.  Blocks may end anywhere in a record.
+ * finish: end of the input; *n_records = records counted. */
+typedef struct sgc_fastq_stream sgc_fastq_stream;
+int sgc_fastq_stream_create(sgc_counter* counter, uint32_t read_len, uint32_t span_start, uint32_t span_len,
+                            sgc_fastq_stream** out);
+void sgc_fastq_stream_destroy(sgc_fastq_stream*);
+int sgc_fastq_stream_submit(sgc_fastq_stream*, const uint8_t* gz, const uint64_t* block_begin,
+                            const uint32_t* block_isize, uint32_t n_blocks);
+int sgc_fastq_stream_finish(sgc_fastq_stream*, uint64_t* n_records);
 
 /* Statistics of the last sgc_counter_submit_device call, for benchmarking. */
 typedef struct sgc_launch_info {

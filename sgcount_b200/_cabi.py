@@ -25,6 +25,8 @@ ERR_EMPTY_READER = 8
 ERR_TOO_MANY_GUIDES = 9
 ERR_BATCH_TOO_LARGE = 10
 ERR_NCCL = 11
+ERR_GZIP = 12
+ERR_FASTQ_FORMAT = 13
 
 RC_BITTRICK = 0
 RC_KEEP_N = 1
@@ -91,6 +93,10 @@ SIGNATURES = {
     "sgc_counter_reset": (_int, [_vp]),
     "sgc_counter_finish": (_int, [_vp, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "sgc_counter_state": (_int, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),
+    "sgc_fastq_stream_create": (_int, [_vp, _u32, _u32, _u32, C.POINTER(_vp)]),
+    "sgc_fastq_stream_destroy": (None, [_vp]),
+    "sgc_fastq_stream_submit": (_int, [_vp, _vp, _vp, _vp, _u32]),
+    "sgc_fastq_stream_finish": (_int, [_vp, C.POINTER(_u64)]),
     "sgc_counter_launch_info": (_int, [_vp, C.POINTER(LaunchInfo)]),
 }
 

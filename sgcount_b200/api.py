@@ -360,3 +360,58 @@ class Counter:
 
     def fraction_mapped(self) -> float:
         return self.matched_reads() / self.total_reads()
+
+
+def bgzf_blocks(blob: bytes):
+    """(begin offsets [n + 1], ISIZE [n]) of the blocks of a BGZF file (the 'BC' extra subfield
+    holds the block size - 1), or None when the bytes are not BGZF."""
+    begin, isize, pos, n = [], [], 0, len(blob)
+    while pos < n:
+        if n - pos < 28 or blob[pos:pos + 4] != b"\x1f\x8b\x08\x04":
+            return None
+        xlen = int.from_bytes(blob[pos + 10:pos + 12], "little")
+        extra, bsize, at = blob[pos + 12:pos + 12 + xlen], None, 0
+        while at + 4 <= len(extra):
+            slen = int.from_bytes(extra[at + 2:at + 4], "little")
+            if extra[at:at + 2] == b"BC" and slen == 2:
+                bsize = int.from_bytes(extra[at + 4:at + 6], "little") + 1
+            at += 4 + slen
+        if bsize is None or pos + bsize > n:
+            return None
+        begin.append(pos)
+        isize.append(int.from_bytes(blob[pos + bsize - 4:pos + bsize], "little"))
+        pos += bsize
+    begin.append(pos)
+    return np.array(begin, dtype=np.uint64), np.array(isize, dtype=np.uint32)
+
+
+class FastqStream:
+    """sgc_fastq_stream: BGZF blocks of a fixed-length FASTQ inflated, framed and counted on the
+    device.  `counter` must have been created with the span Offset of span_geometry()."""
+
+    def __init__(self, counter: Counter, read_len: int, span_start: int, span_len: int):
+        self._counter = counter
+        self._ptr = C.c_void_p()
+        check(_cabi.load().sgc_fastq_stream_create(counter._ptr, read_len, span_start, span_len, C.byref(self._ptr)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ptr", None):
+                _cabi.load().sgc_fastq_stream_destroy(self._ptr)
+                self._ptr = None
+        except Exception:  # interpreter shutdown
+            pass
+
+    def submit(self, blob: np.ndarray, begin: np.ndarray, isize: np.ndarray) -> None:
+        """one wave: blocks begin[i]..begin[i+1] of `blob` (uint8), consecutive, in file order"""
+        begin = np.ascontiguousarray(begin, dtype=np.uint64)
+        isize = np.ascontiguousarray(isize, dtype=np.uint32)
+        assert len(begin) == len(isize) + 1
+        check(_cabi.load().sgc_fastq_stream_submit(self._ptr, blob.ctypes.data, begin.ctypes.data, isize.ctypes.data, len(isize)))
+        self._counter._result = None
+
+    def finish(self) -> int:
+        n = C.c_uint64()
+        check(_cabi.load().sgc_fastq_stream_finish(self._ptr, C.byref(n)))
+        self._counter._result = None
+        return int(n.value)

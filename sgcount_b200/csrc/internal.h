@@ -43,9 +43,10 @@ int position_counts_device(const uint8_t* d_lines, const uint32_t* d_line_off, u
                            uint32_t read_len, uint64_t n_reads, uint32_t size, uint32_t* d_hist /* size*4, zeroed */,
                            cudaStream_t stream);
 
-// exclusive prefix sum of cnt[0..n) into start[0..n) on the default stream (library.cu);
+// exclusive prefix sum of cnt[0..n) into start[0..n) (library.cu);
 // tile_sums: scratch of (n + 2047) / 2048 + 1 words
-int exclusive_scan_u32(const uint32_t* d_cnt, uint32_t n, uint32_t* d_start, uint32_t* d_tile_sums);
+int exclusive_scan_u32(const uint32_t* d_cnt, uint32_t n, uint32_t* d_start, uint32_t* d_tile_sums,
+                       cudaStream_t stream = nullptr);
 
 }  // namespace sgc
 

@@ -399,11 +399,11 @@ void sgc_library_destroy(sgc_library* lib) {
 }  // extern "C"
 
 namespace sgc {
-int exclusive_scan_u32(const uint32_t* d_cnt, uint32_t n, uint32_t* d_start, uint32_t* d_tile_sums) {
+int exclusive_scan_u32(const uint32_t* d_cnt, uint32_t n, uint32_t* d_start, uint32_t* d_tile_sums, cudaStream_t stream) {
   const uint32_t tiles = (n + kScanTile - 1) / kScanTile;
-  scan_tile_sums_kernel<<<tiles, kScanThreads>>>(d_cnt, n, d_tile_sums);
-  scan_sums_kernel<<<1, kScanThreads>>>(d_tile_sums, tiles);
-  scan_tiles_kernel<<<tiles, kScanThreads>>>(d_cnt, n, d_tile_sums, d_start);
+  scan_tile_sums_kernel<<<tiles, kScanThreads, 0, stream>>>(d_cnt, n, d_tile_sums);
+  scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(d_tile_sums, tiles);
+  scan_tiles_kernel<<<tiles, kScanThreads, 0, stream>>>(d_cnt, n, d_tile_sums, d_start);
   SGC_CUDA_TRY(cudaGetLastError());
   return SGC_OK;
 }
