@@ -818,38 +818,40 @@ struct TopGuides {
 };
 
 // One block: the kHotGuides largest entries of counts[0..n).  Every thread keeps its own sorted
-// short list over a strided slice; the lists are merged through shared memory by thread 0
-// (n <= 4 M guides, 1024 threads: the merge walks 4096 candidates once).
+// short list over a strided slice; lane 0 of every warp merges its warp's lists, thread 0 the
+// warps' (two short serial merges instead of one long one).
+__device__ __forceinline__ void top_insert(unsigned long long (&top)[kHotGuides], unsigned long long v) {
+#pragma unroll
+  for (int j = 0; j < kHotGuides; ++j)
+    if (v > top[j]) {
+      const unsigned long long t = top[j];
+      top[j] = v;
+      v = t;
+    }
+}
 __global__ void __launch_bounds__(1024) top_guides_kernel(const unsigned long long* __restrict__ counts, uint32_t n,
                                                          TopGuides* out) {
   __shared__ unsigned long long cand[1024 * kHotGuides];
+  __shared__ unsigned long long warp_top[32 * kHotGuides];
   unsigned long long best[kHotGuides] = {};
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    unsigned long long v = counts[i];
-    if (v == 0) continue;
-    v = (v << 32) | i;
-#pragma unroll
-    for (int j = 0; j < kHotGuides; ++j)
-      if (v > best[j]) {
-        const unsigned long long t = best[j];
-        best[j] = v;
-        v = t;
-      }
+    const unsigned long long v = counts[i];
+    if (v) top_insert(best, (v << 32) | i);
   }
 #pragma unroll
   for (int j = 0; j < kHotGuides; ++j) cand[threadIdx.x * kHotGuides + j] = best[j];
   __syncthreads();
+  const uint32_t warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long top[kHotGuides] = {};
+    for (uint32_t c = 0; c < 32 * kHotGuides; ++c) top_insert(top, cand[warp * 32 * kHotGuides + c]);
+#pragma unroll
+    for (int j = 0; j < kHotGuides; ++j) warp_top[warp * kHotGuides + j] = top[j];
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long top[kHotGuides] = {};
-    for (uint32_t c = 0; c < blockDim.x * kHotGuides; ++c) {
-      unsigned long long v = cand[c];
-      for (int j = 0; j < kHotGuides; ++j)
-        if (v > top[j]) {
-          const unsigned long long t = top[j];
-          top[j] = v;
-          v = t;
-        }
-    }
+    for (uint32_t c = 0; c < n_warps * kHotGuides; ++c) top_insert(top, warp_top[c]);
     for (int j = 0; j < kHotGuides; ++j) out->packed[j] = top[j];
     out->total = counts[n];
   }
@@ -1236,6 +1238,7 @@ void sgc_counter_destroy(sgc_counter* c) {
   if (!c) return;
   DeviceGuard guard(c->lib->device);
   cudaStreamSynchronize(c->stream);
+  for (sgc_fastq_stream* s : std::vector<sgc_fastq_stream*>(c->fastq_streams)) fastq_stream_release(s);
   if (c->copy_stream) {
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamDestroy(c->copy_stream);

@@ -224,7 +224,8 @@ int grow(T** p, size_t* cap, size_t need) {
 using namespace sgc;
 
 struct sgc_fastq_stream {
-  sgc_counter* counter = nullptr;
+  sgc_counter* counter = nullptr;  // NULL once released (its counter was destroyed first)
+  int device = 0;
   uint32_t read_len = 0, span_start = 0, span_len = 0, span_stride = 0;
   cudaStream_t stream = nullptr;
   StreamState* d_state = nullptr;
@@ -292,6 +293,31 @@ int frame_and_count(sgc_fastq_stream* s, uint32_t n_text, uint64_t first_block) 
 
 }  // namespace
 
+// Frees the device side and detaches the stream from its counter; the handle itself stays valid.
+void sgc::fastq_stream_release(sgc_fastq_stream* s) {
+  if (!s || !s->counter) return;
+  DeviceGuard guard(s->device);
+  cudaStreamSynchronize(s->stream);
+  auto& list = s->counter->fastq_streams;
+  list.erase(std::remove(list.begin(), list.end(), s), list.end());
+  s->counter = nullptr;
+  s->failed = true;  // nothing more can be submitted
+  cudaFree(s->d_state);
+  cudaFree(s->d_gz);
+  cudaFree(s->d_text);
+  cudaFree(s->d_spans);
+  cudaFree(s->d_tail);
+  cudaFree(s->d_begin);
+  cudaFree(s->d_outoff);
+  cudaFree(s->d_counts);
+  cudaFree(s->d_first);
+  cudaFree(s->d_sums);
+  s->d_state = nullptr;
+  s->d_gz = s->d_text = s->d_spans = s->d_tail = nullptr;
+  s->d_begin = s->d_outoff = nullptr;
+  s->d_counts = s->d_first = s->d_sums = nullptr;
+}
+
 extern "C" {
 
 int sgc_fastq_stream_create(sgc_counter* counter, uint32_t read_len, uint32_t span_start, uint32_t span_len,
@@ -302,10 +328,12 @@ int sgc_fastq_stream_create(sgc_counter* counter, uint32_t read_len, uint32_t sp
   DeviceGuard guard(counter->lib->device);
   sgc_fastq_stream* s = new sgc_fastq_stream();
   s->counter = counter;
+  s->device = counter->lib->device;
   s->read_len = read_len;
   s->span_start = span_start;
   s->span_len = span_len;
   s->span_stride = (span_len + 7u) & ~7u;
+  s->device = counter->lib->device;
   s->stream = counter->stream;  // one stream: the count of a wave follows its framing
   struct Cleanup {
     sgc_fastq_stream* s;
@@ -320,6 +348,7 @@ int sgc_fastq_stream_create(sgc_counter* counter, uint32_t read_len, uint32_t sp
   SGC_CUDA_TRY(cudaMemcpyAsync(s->d_state, &st0, sizeof st0, cudaMemcpyHostToDevice, s->stream));
   SGC_CUDA_TRY(cudaStreamSynchronize(s->stream));
   SGC_CUDA_TRY(cudaFuncSetAttribute(inflate_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInflateSmem));
+  counter->fastq_streams.push_back(s);
   cleanup.s = nullptr;
   *out = s;
   return SGC_OK;
@@ -327,27 +356,16 @@ int sgc_fastq_stream_create(sgc_counter* counter, uint32_t read_len, uint32_t sp
 
 void sgc_fastq_stream_destroy(sgc_fastq_stream* s) {
   if (!s) return;
-  DeviceGuard guard(s->counter->lib->device);
-  cudaStreamSynchronize(s->stream);
-  cudaFree(s->d_state);
-  cudaFree(s->d_gz);
-  cudaFree(s->d_text);
-  cudaFree(s->d_spans);
-  cudaFree(s->d_tail);
-  cudaFree(s->d_begin);
-  cudaFree(s->d_outoff);
-  cudaFree(s->d_counts);
-  cudaFree(s->d_first);
-  cudaFree(s->d_sums);
+  sgc::fastq_stream_release(s);
   delete s;
 }
 
 int sgc_fastq_stream_submit(sgc_fastq_stream* s, const uint8_t* gz, const uint64_t* block_begin, const uint32_t* block_isize,
                             uint32_t n_blocks) {
   if (!s || !gz || !block_begin || !block_isize) return set_error(SGC_ERR_INVALID_ARG, "NULL argument");
-  if (s->failed) return set_error(SGC_ERR_INVALID_ARG, "the stream has failed");
+  if (s->failed || !s->counter) return set_error(SGC_ERR_INVALID_ARG, "the stream has failed or its counter is gone");
   if (n_blocks == 0) return SGC_OK;
-  DeviceGuard guard(s->counter->lib->device);
+  DeviceGuard guard(s->device);
   // where every block's text goes: the prefix sum of the ISIZE fields
   s->h_outoff.resize((size_t)n_blocks + 1);
   uint64_t n_text = 0;
@@ -357,7 +375,7 @@ int sgc_fastq_stream_submit(sgc_fastq_stream* s, const uint8_t* gz, const uint64
     n_text += block_isize[i];
   }
   s->h_outoff[n_blocks] = kHeadroom + n_text;
-  if (n_text >= (1ull << 31)) return set_error(SGC_ERR_BATCH_TOO_LARGE, "a wave of blocks must inflate to less than 2 GiB");
+  if (n_text >= (1ull << 32) - 2 * kHeadroom) return set_error(SGC_ERR_BATCH_TOO_LARGE, "a wave of blocks must inflate to less than 4 GiB");
   const uint64_t gz_bytes = block_begin[n_blocks] - block_begin[0];
   int rc = grow(&s->d_gz, &s->gz_cap, (size_t)gz_bytes + 16);
   if (rc == SGC_OK) rc = grow(&s->d_text, &s->text_cap, (size_t)kHeadroom + n_text + 64);
@@ -378,8 +396,8 @@ int sgc_fastq_stream_submit(sgc_fastq_stream* s, const uint8_t* gz, const uint64
 
 int sgc_fastq_stream_finish(sgc_fastq_stream* s, uint64_t* n_records) {
   if (!s) return set_error(SGC_ERR_INVALID_ARG, "stream is NULL");
-  if (s->failed) return set_error(SGC_ERR_INVALID_ARG, "the stream has failed");
-  DeviceGuard guard(s->counter->lib->device);
+  if (s->failed || !s->counter) return set_error(SGC_ERR_INVALID_ARG, "the stream has failed or its counter is gone");
+  DeviceGuard guard(s->device);
   StreamState st;
   SGC_CUDA_TRY(cudaMemcpyAsync(&st, s->d_state, sizeof st, cudaMemcpyDeviceToHost, s->stream));
   SGC_CUDA_TRY(cudaStreamSynchronize(s->stream));

@@ -56,31 +56,51 @@ struct PlainTables {
   SGC_HD void set_dfast(int i, uint16_t v) { dfast[i] = v; }
 };
 
-// LSB-first bit reader over a byte range; reads past the end deliver zeros and set `overrun`.
+// LSB-first bit reader over a byte range, refilled 32 bits at a time with ALIGNED word loads (one
+// load per refill, no byte loop).  The words that hold the first and last byte of the range must be
+// readable, i.e. up to 3 bytes before `in` and 3 bytes after in + len may be touched; bits past
+// the range read as zero, and `overrun` says that the decoder asked for bits beyond it.
 struct BitReader {
-  const uint8_t* in;
-  size_t len, pos;
+  const uint32_t* words;  // in, rounded down to a word
+  size_t len;             // bytes of the range
+  size_t next;            // byte offset (from `in`) of the next word to load; may be negative mod 2^64 at first
+  uint32_t lead;          // in - (const uint8_t*)words
   uint64_t buf;
   int cnt;
   bool overrun;
-  SGC_HD void init(const uint8_t* p, size_t n, size_t at) {
-    in = p;
+  SGC_HD void init(const uint8_t* in, size_t n, size_t at) {
+    const uintptr_t a = (uintptr_t)(in + at);
+    words = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
     len = n;
-    pos = at;
+    lead = (uint32_t)(a & 3u);
+    next = at - lead;  // offset of words[0] relative to `in` (wraps when the word starts before `in`)
     buf = 0;
     cnt = 0;
     overrun = false;
+    // first word: drop the bytes in front of the position
+    uint32_t w = load_word();
+    buf = (uint64_t)(w >> (8 * lead));
+    cnt = 32 - 8 * (int)lead;
   }
-  SGC_HD void refill() {  // at least 56 valid bits afterwards
-    while (cnt <= 56) {
-      uint64_t b = 0;
-      if (pos < len)
-        b = in[pos];
-      else if (pos >= len + 8)
-        overrun = true;  // more than the slack a decoder may look ahead
-      ++pos;
-      buf |= b << cnt;
-      cnt += 8;
+  SGC_HD uint32_t load_word() {
+    // bytes of this word that lie inside [0, len) keep their value, the others read as zero
+    const size_t off = next;  // may be "negative" for the very first word only
+    uint32_t w = 0;
+    if ((ptrdiff_t)off < (ptrdiff_t)len) {
+      w = *words;
+      const ptrdiff_t over = (ptrdiff_t)off + 4 - (ptrdiff_t)len;  // bytes of the word past the range
+      if (over > 0) w &= over >= 4 ? 0u : (0xFFFFFFFFu >> (8 * (int)over));
+    } else if ((ptrdiff_t)off >= (ptrdiff_t)len + 8) {
+      overrun = true;  // more than the slack a decoder may look ahead
+    }
+    ++words;
+    next += 4;
+    return w;
+  }
+  SGC_HD void refill() {  // more than 32 valid bits afterwards
+    if (cnt <= 32) {
+      buf |= (uint64_t)load_word() << cnt;
+      cnt += 32;
     }
   }
   SGC_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
@@ -94,7 +114,7 @@ struct BitReader {
     return v;
   }
   // bytes of input consumed so far, counting whole bytes still in the buffer as unread
-  SGC_HD size_t consumed() const { return pos - (size_t)(cnt >> 3); }
+  SGC_HD size_t consumed() const { return next - (size_t)(cnt >> 3); }
   SGC_HD void align_to_byte() { drop(cnt & 7); }
 };
 
@@ -192,8 +212,74 @@ SGC_HD bool install_codes(Tables& t, const uint8_t* ll, int nl, const uint8_t* d
   return true;
 }
 
+// The code tables of a fixed (type 1) or dynamic (type 2) block, read from the block header.
+template <typename Tables>
+SGC_HD int read_codes(BitReader& br, Tables& t, uint32_t type) {
+  uint8_t lengths[kLitLenSyms + kDistSyms];
+  int nl, nd;
+  if (type == 1) {  // fixed code
+    nl = 288;
+    nd = 32;  // 30 and 31 complete the 5-bit code and are errors if they occur
+    for (int i = 0; i < 144; ++i) lengths[i] = 8;
+    for (int i = 144; i < 256; ++i) lengths[i] = 9;
+    for (int i = 256; i < 280; ++i) lengths[i] = 7;
+    for (int i = 280; i < 288; ++i) lengths[i] = 8;
+    for (int i = 0; i < 32; ++i) lengths[288 + i] = 5;
+  } else {  // dynamic code: the code-length code first
+    br.refill();
+    nl = (int)br.take(5) + 257;
+    nd = (int)br.take(5) + 1;
+    const int nc = (int)br.take(4) + 4;
+    if (nl > 286 || nd > 30) return br.overrun ? kTruncated : kBadBlock;
+    uint8_t cl[19];
+    for (int i = 0; i < 19; ++i) cl[i] = 0;
+    for (int i = 0; i < nc; ++i) {
+      br.refill();
+      cl[cl_order(i)] = (uint8_t)br.take(3);
+    }
+    // the code-length alphabet is tiny: its canonical form lives in registers / local arrays
+    uint16_t ccount[kMaxBits + 1], csym[19], dummy[kMaxBits + 1];
+    if (!build_canonical(cl, 19, [&](int i, uint16_t v) { ccount[i] = v; }, [&](int i, uint16_t v) { csym[i] = v; }, dummy, true))
+      return kBadBlock;
+    int i = 0;
+    while (i < nl + nd) {
+      br.refill();
+      const int s = decode_slow(br, [&](int l) { return (int)ccount[l]; }, [&](int k) { return (int)csym[k]; });
+      if (s < 0) return br.overrun ? kTruncated : kBadCode;
+      if (s < 16) {
+        lengths[i++] = (uint8_t)s;
+      } else {
+        uint8_t prev = 0;
+        int rep;
+        if (s == 16) {
+          if (i == 0) return kBadBlock;
+          prev = lengths[i - 1];
+          rep = 3 + (int)br.take(2);
+        } else if (s == 17) {
+          rep = 3 + (int)br.take(3);
+        } else {
+          rep = 11 + (int)br.take(7);
+        }
+        if (i + rep > nl + nd) return kBadBlock;
+        while (rep--) lengths[i++] = prev;
+      }
+    }
+    if (lengths[256] == 0) return kBadBlock;  // no end-of-block code
+    // the tables below want the distance lengths at a fixed place
+    if (nl != 288)
+      for (int j = nd - 1; j >= 0; --j) lengths[288 + j] = lengths[nl + j];
+  }
+  return install_codes(t, lengths, nl, lengths + 288, nd) ? kOk : kBadBlock;
+}
+
 // One gzip member at in[0 .. in_len).  On kOk: *consumed = bytes of the member including its
 // 8-byte trailer, *produced = bytes written to out, *crc32 / *isize = the trailer's fields.
+//
+// Written as ONE loop over a small state machine — block header, one symbol, eight bytes of a
+// pending match, eight bytes of a stored block — instead of nested loops: the threads of a warp
+// decode different members, and with a single loop head they reconverge every iteration, each
+// doing one step of whatever state it is in, instead of drifting apart for good.  A long match
+// (a quality line is one 75-byte match) is copied in steps, so no lane waits for another's copy.
 template <typename Tables>
 SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, Tables& t, size_t* consumed,
                          size_t* produced, uint32_t* crc32, uint32_t* isize) {
@@ -215,101 +301,48 @@ SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t 
   if (pos >= in_len) return kTruncated;
 
   // ---- RFC 1951 blocks
+  enum { kHeader, kSymbol, kCopy, kStored, kDone };
   BitReader br;
   br.init(in, in_len, pos);
   size_t op = 0;
-  for (;;) {
-    br.refill();
-    const uint32_t last = br.take(1), type = br.take(2);
-    if (type == 0) {  // stored
-      br.align_to_byte();
+  int state = kHeader, rc = kOk;
+  uint32_t last = 0;
+  uint32_t run = 0;      // bytes of the pending match / stored block still to copy
+  uint32_t dist = 0;     // distance of the pending match
+  uint64_t pattern = 0;  // dist < 8: the dist bytes the match repeats, lowest byte first
+  uint32_t phase = 0;    //           and which of them comes next
+  size_t stored_at = 0;  // input position of the stored bytes
+  while (state != kDone) {
+    if (state == kSymbol) {
       br.refill();
-      const uint32_t n = br.take(16), nn = br.take(16);
-      if ((n ^ nn) != 0xFFFFu) return br.overrun ? kTruncated : kBadBlock;
-      size_t at = br.consumed();  // the buffer holds whole bytes only
-      if (at + n > in_len) return kTruncated;
-      if (op + n > out_cap) return kOutputFull;
-      for (uint32_t i = 0; i < n; ++i) out[op + i] = in[at + i];
-      op += n;
-      br.init(in, in_len, at + n);
-    } else if (type == 3) {
-      return br.overrun ? kTruncated : kBadBlock;
-    } else {
-      uint8_t lengths[kLitLenSyms + kDistSyms];
-      int nl, nd;
-      if (type == 1) {  // fixed code
-        nl = 288;
-        nd = 32;  // 30 and 31 complete the 5-bit code and are errors if they occur
-        for (int i = 0; i < 144; ++i) lengths[i] = 8;
-        for (int i = 144; i < 256; ++i) lengths[i] = 9;
-        for (int i = 256; i < 280; ++i) lengths[i] = 7;
-        for (int i = 280; i < 288; ++i) lengths[i] = 8;
-        for (int i = 0; i < 32; ++i) lengths[288 + i] = 5;
-      } else {  // dynamic code: the code-length code first
-        nl = (int)br.take(5) + 257;
-        nd = (int)br.take(5) + 1;
-        const int nc = (int)br.take(4) + 4;
-        if (nl > 286 || nd > 30) return br.overrun ? kTruncated : kBadBlock;
-        uint8_t cl[19];
-        for (int i = 0; i < 19; ++i) cl[i] = 0;
-        for (int i = 0; i < nc; ++i) {
-          br.refill();
-          cl[cl_order(i)] = (uint8_t)br.take(3);
-        }
-        // the code-length alphabet is tiny: its canonical form lives in registers / local arrays
-        uint16_t ccount[kMaxBits + 1], csym[19], dummy[kMaxBits + 1];
-        if (!build_canonical(cl, 19, [&](int i, uint16_t v) { ccount[i] = v; }, [&](int i, uint16_t v) { csym[i] = v; }, dummy, true))
-          return kBadBlock;
-        int i = 0;
-        while (i < nl + nd) {
-          br.refill();
-          const int s = decode_slow(br, [&](int l) { return (int)ccount[l]; }, [&](int k) { return (int)csym[k]; });
-          if (s < 0) return br.overrun ? kTruncated : kBadCode;
-          if (s < 16) {
-            lengths[i++] = (uint8_t)s;
-          } else {
-            uint8_t prev = 0;
-            int rep;
-            if (s == 16) {
-              if (i == 0) return kBadBlock;
-              prev = lengths[i - 1];
-              rep = 3 + (int)br.take(2);
-            } else if (s == 17) {
-              rep = 3 + (int)br.take(3);
-            } else {
-              rep = 11 + (int)br.take(7);
-            }
-            if (i + rep > nl + nd) return kBadBlock;
-            while (rep--) lengths[i++] = prev;
-          }
-        }
-        if (lengths[256] == 0) return kBadBlock;  // no end-of-block code
-        // the decoder below wants the distance lengths at a fixed place
-        if (nl != 288)
-          for (int j = nd - 1; j >= 0; --j) lengths[288 + j] = lengths[nl + j];
+      int sym;
+      const uint16_t e = t.get_lfast((int)br.peek(kFastBits));
+      if (e) {
+        br.drop(e & 15);
+        sym = e >> 4;
+      } else {
+        sym = decode_slow(br, [&](int l) { return (int)t.get_lcount(l); }, [&](int k) { return (int)t.get_lsym(k); });
       }
-      if (!install_codes(t, lengths, nl, lengths + 288, nd)) return kBadBlock;
-      // ---- symbols
-      for (;;) {
-        br.refill();
-        int sym;
-        const uint16_t e = t.get_lfast((int)br.peek(kFastBits));
-        if (e) {
-          br.drop(e & 15);
-          sym = e >> 4;
+      if (sym < 0 || sym > 285) {
+        rc = br.overrun ? kTruncated : kBadCode;
+        state = kDone;
+      } else if (sym < 256) {
+        if (op >= out_cap) {
+          rc = kOutputFull;
+          state = kDone;
         } else {
-          sym = decode_slow(br, [&](int l) { return (int)t.get_lcount(l); }, [&](int k) { return (int)t.get_lsym(k); });
-          if (sym < 0) return br.overrun ? kTruncated : kBadCode;
-        }
-        if (sym < 256) {
-          if (op >= out_cap) return kOutputFull;
           out[op++] = (uint8_t)sym;
-          continue;
         }
-        if (sym == 256) break;
+      } else if (sym == 256) {
+        if (br.overrun) {
+          rc = kTruncated;
+          state = kDone;
+        } else {
+          state = last ? kDone : kHeader;
+        }
+      } else {
         sym -= 257;
-        if (sym >= 29) return kBadCode;
-        const uint32_t length = len_base(sym) + br.take((int)len_extra_bits(sym));
+        run = len_base(sym) + br.take((int)len_extra_bits(sym));
         br.refill();
         int ds;
         const uint16_t de = t.get_dfast((int)br.peek(kDistFastBits));
@@ -318,22 +351,96 @@ SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t 
           ds = de >> 4;
         } else {
           ds = decode_slow(br, [&](int l) { return (int)t.get_dcount(l); }, [&](int k) { return (int)t.get_dsym(k); });
-          if (ds < 0) return br.overrun ? kTruncated : kBadCode;
         }
-        if (ds >= 30) return kBadCode;
-        const uint32_t dist = dist_base(ds) + br.take((int)dist_extra_bits(ds));
-        if (dist > op) return kBadDistance;
-        if (op + length > out_cap) return kOutputFull;
-        for (uint32_t i = 0; i < length; ++i) out[op + i] = out[op + i - dist];  // byte by byte: overlap is the point
-        op += length;
+        if (ds < 0 || ds >= 30) {
+          rc = br.overrun ? kTruncated : kBadCode;
+          state = kDone;
+        } else {
+          dist = dist_base(ds) + br.take((int)dist_extra_bits(ds));
+          if (dist > op) {
+            rc = kBadDistance;
+            state = kDone;
+          } else if (op + run > out_cap) {
+            rc = kOutputFull;
+            state = kDone;
+          } else {
+            if (dist < 8) {  // a short period: keep the repeated bytes in a register
+              pattern = 0;
+              for (uint32_t i = 0; i < dist; ++i) pattern |= (uint64_t)out[op - dist + i] << (8 * i);
+              phase = 0;
+            }
+            state = kCopy;
+          }
+        }
       }
-      if (br.overrun) return kTruncated;
+    } else if (state == kCopy) {
+      const uint32_t n = run < 8 ? run : 8;
+      if (dist >= 8) {
+        uint8_t tmp[8];
+        for (uint32_t i = 0; i < 8; ++i) tmp[i] = i < n ? out[op + i - dist] : 0;  // loads first: they do not overlap the stores
+        for (uint32_t i = 0; i < 8; ++i)
+          if (i < n) out[op + i] = tmp[i];
+      } else {
+        for (uint32_t i = 0; i < 8; ++i)
+          if (i < n) {
+            out[op + i] = (uint8_t)(pattern >> (8 * phase));
+            phase = phase + 1 == dist ? 0 : phase + 1;
+          }
+      }
+      op += n;
+      run -= n;
+      if (run == 0) state = kSymbol;
+    } else if (state == kStored) {
+      const uint32_t n = run < 8 ? run : 8;
+      for (uint32_t i = 0; i < 8; ++i)
+        if (i < n) out[op + i] = in[stored_at + i];
+      op += n;
+      stored_at += n;
+      run -= n;
+      if (run == 0) {
+        br.init(in, in_len, stored_at);
+        state = last ? kDone : kHeader;
+      }
+    } else {  // kHeader
+      br.refill();
+      last = br.take(1);
+      const uint32_t type = br.take(2);
+      if (type == 0) {  // stored
+        br.align_to_byte();
+        br.refill();
+        const uint32_t n = br.take(16);
+        br.refill();
+        const uint32_t nn = br.take(16);
+        stored_at = br.consumed();  // the buffer holds whole bytes only
+        if ((n ^ nn) != 0xFFFFu) {
+          rc = br.overrun ? kTruncated : kBadBlock;
+          state = kDone;
+        } else if (stored_at + n > in_len) {
+          rc = kTruncated;
+          state = kDone;
+        } else if (op + n > out_cap) {
+          rc = kOutputFull;
+          state = kDone;
+        } else if (n == 0) {
+          br.init(in, in_len, stored_at);
+          state = last ? kDone : kHeader;
+        } else {
+          run = n;
+          state = kStored;
+        }
+      } else if (type == 3) {
+        rc = br.overrun ? kTruncated : kBadBlock;
+        state = kDone;
+      } else {
+        rc = read_codes(br, t, type);
+        state = rc == kOk ? kSymbol : kDone;
+      }
     }
-    if (last) break;
   }
+  if (rc != kOk) return rc;
   // ---- trailer
   br.align_to_byte();
-  size_t at = br.consumed();
+  const size_t at = br.consumed();
   if (at + 8 > in_len) return kTruncated;
   *crc32 = (uint32_t)in[at] | ((uint32_t)in[at + 1] << 8) | ((uint32_t)in[at + 2] << 16) | ((uint32_t)in[at + 3] << 24);
   *isize = (uint32_t)in[at + 4] | ((uint32_t)in[at + 5] << 8) | ((uint32_t)in[at + 6] << 16) | ((uint32_t)in[at + 7] << 24);

@@ -90,7 +90,15 @@ struct sgc_counter {
   std::deque<cudaEvent_t> copy_tickets;   // one per sgc_counter_submit call whose copies may still run
   std::vector<cudaEvent_t> free_tickets;
   sgc_launch_info last{};
+  // device-ingest streams that count into this counter (gzip.cu); released with it if still open
+  std::vector<struct sgc_fastq_stream*> fastq_streams;
 };
+
+namespace sgc {
+// gzip.cu: frees the device side of a stream whose counter is going away (the handle stays valid
+// for sgc_fastq_stream_destroy)
+void fastq_stream_release(struct sgc_fastq_stream* s);
+}
 
 struct sgc_library {
   int device = 0;

@@ -167,6 +167,8 @@ class FastxReader {
   bool next(const char*& id, size_t& id_len, const char*& seq, size_t& seq_len);
   // Sequence line only (the hot loop of count_sample): a view into the read buffer.
   bool next_seq(const char*& seq, size_t& seq_len);
+  // '@' records of four lines (known once a record has been read)
+  bool is_fastq() const { return lines_per_record_ == 4; }
 
  private:
   void sniff(const char* line, size_t len);

@@ -15,17 +15,19 @@ int main(int argc, char** argv) {
   unsigned char buf[1 << 16];
   for (size_t got; (got = fread(buf, 1, sizeof buf, f)) > 0;) data.insert(data.end(), buf, buf + got);
   fclose(f);
+  const size_t n_data = data.size();
+  data.resize(n_data + 8);  // the decoder loads aligned words: up to 3 bytes past the end are touched
   const size_t cap = argc > 2 ? (size_t)atoll(argv[2]) : (size_t)1 << 30;
   std::vector<unsigned char> out(cap < ((size_t)64 << 20) ? cap : ((size_t)64 << 20));
   sgc::inflate::PlainTables t;
   size_t pos = 0, members = 0;
   unsigned long long total = 0, h = 1469598103934665603ull;
-  while (pos < data.size()) {
+  while (pos < n_data) {
     size_t used = 0, made = 0;
     uint32_t crc = 0, isize = 0;
     int rc;
     for (;;) {
-      rc = sgc::inflate::gunzip_member(data.data() + pos, data.size() - pos, out.data(), out.size(), t, &used, &made, &crc, &isize);
+      rc = sgc::inflate::gunzip_member(data.data() + pos, n_data - pos, out.data(), out.size(), t, &used, &made, &crc, &isize);
       if (rc != sgc::inflate::kOutputFull || out.size() >= cap) break;
       out.resize(out.size() * 2 < cap ? out.size() * 2 : cap);
     }

@@ -11,7 +11,13 @@
 // processed concurrently (one host pipeline and one CUDA stream per counter each), `--gpus` spreads the samples over devices and, when there are fewer
 // samples than devices, cuts every sample into read shards over gpus / samples devices whose
 // count vectors are summed with sgc_reduce_counts (NCCL).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <atomic>
+#include <condition_variable>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -62,6 +68,7 @@ struct Args {
   unsigned ingest_threads = 0;  // inflate threads per sample; 0 = hardware threads / concurrent samples
   bool timing = false;
   bool whole_lines = false;  // never frame span records
+  bool host_inflate = false; // never inflate on the device
   int rc_mode = SGC_RC_BITTRICK;
 };
 
@@ -87,6 +94,7 @@ const char* kUsage =
     "      --ingest-threads <N>               Threads inflating the gzip members of one sample [default: cores / samples in flight]\n"
     "      --rc-keep-n                        Reverse complement keeps N (default: the fxread bit trick, N -> J)\n"
     "      --whole-lines                      Copy whole sequence lines to the device (default: for fixed-length reads, only the guide window and one byte either side)\n"
+    "      --host-inflate                     Inflate and frame records on the host even for BGZF input (default: BGZF files of fixed-length FASTQ are inflated, framed and counted on the device)\n"
     "      --timing                           Print a JSON line with the phase times to stderr\n"
     "  -h, --help                             Print help\n";
 
@@ -131,6 +139,7 @@ Args parse_args(int argc, char** argv) {
     else if (f == "--rc-keep-n") a.rc_mode = SGC_RC_KEEP_N;
     else if (f == "--timing") a.timing = true;
     else if (f == "--whole-lines") a.whole_lines = true;
+    else if (f == "--host-inflate") a.host_inflate = true;
     else if (f == "-h" || f == "--help") { fputs(kUsage, stdout); exit(0); }
     else fail("unexpected argument '%s' found", f.c_str());
   }
@@ -311,7 +320,9 @@ struct SampleHead {
   std::vector<uint8_t> lines;
   std::vector<uint32_t> off{0};
   size_t first_len = 0;
-  bool any = false;  // the file holds at least one record
+  bool any = false;      // the file holds at least one record
+  bool fastq = false;    // '@' records (4 lines)
+  bool uniform = true;   // every record read so far has first_len bases
 };
 SampleHead read_head(const std::string& path, unsigned long records) {
   SampleHead h;
@@ -323,6 +334,8 @@ SampleHead read_head(const std::string& path, unsigned long records) {
       h.first_len = seq_len;
       h.any = true;
     }
+    h.uniform &= seq_len == h.first_len;
+    h.fastq = reader.is_fastq();
     if (i >= records) break;
     h.lines.insert(h.lines.end(), seq, seq + seq_len);
     h.lines.push_back('\n');
@@ -346,7 +359,173 @@ struct SampleResult {
   double wait_s = 0, copy_s = 0, submit_s = 0;
   unsigned shards = 1;  // devices the sample's reads were spread over
   uint64_t span_reads = 0, line_reads = 0;  // reads that travelled as span records / whole lines
+  bool device_ingest = false;               // inflate and record framing ran on the device (BGZF input)
+  uint64_t device_blocks = 0;
+  std::string host_because;                 // why the device ingest was not used
 };
+
+// ---- device ingest: BGZF blocks inflated, framed and counted on the GPU (sgc_fastq_stream_*) ----
+// A read-only mapping of a file.
+struct MappedFile {
+  const uint8_t* data = nullptr;
+  size_t size = 0;
+  int fd = -1;
+  explicit MappedFile(const std::string& path) {
+    fd = open(path.c_str(), O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) return;
+    size = (size_t)st.st_size;
+    if (size == 0) return;
+    void* p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (p != MAP_FAILED) data = static_cast<const uint8_t*>(p);
+  }
+  ~MappedFile() {
+    if (data) munmap(const_cast<uint8_t*>(data), size);
+    if (fd >= 0) close(fd);
+  }
+};
+
+// BGZF (bgzip, sequencers): every member carries its own size in a 'BC' extra subfield, so the
+// blocks can be walked without inflating anything.  False if the file is not BGZF throughout.
+bool bgzf_index(const uint8_t* d, size_t n, std::vector<uint64_t>& begin, std::vector<uint32_t>& isize) {
+  size_t pos = 0;
+  while (pos < n) {
+    if (n - pos < 28 || d[pos] != 0x1f || d[pos + 1] != 0x8b || d[pos + 2] != 8 || !(d[pos + 3] & 4)) return false;
+    const size_t xlen = d[pos + 10] | ((size_t)d[pos + 11] << 8);
+    if (pos + 12 + xlen > n) return false;
+    size_t bsize = 0;
+    for (size_t at = pos + 12; at + 4 <= pos + 12 + xlen;) {
+      const size_t slen = d[at + 2] | ((size_t)d[at + 3] << 8);
+      if (d[at] == 'B' && d[at + 1] == 'C' && slen == 2 && at + 6 <= pos + 12 + xlen) bsize = (d[at + 4] | ((size_t)d[at + 5] << 8)) + 1;
+      at += 4 + slen;
+    }
+    if (bsize < 28 || pos + bsize > n) return false;
+    begin.push_back(pos);
+    uint32_t sz;
+    memcpy(&sz, d + pos + bsize - 4, 4);
+    isize.push_back(sz);
+    pos += bsize;
+  }
+  begin.push_back(pos);
+  return !isize.empty();
+}
+
+// One sample through the device ingest.  Returns false (after resetting nothing: the caller
+// starts a fresh counter) when the file is not BGZF or the device reports input it does not take —
+// a read of another length, FASTA, a damaged block — so that the host path counts the sample.
+bool count_sample_on_device(const sgc_library* lib, uint32_t n_guides, uint32_t k, const std::string& path, OffsetValue offset,
+                            uint32_t read_len, bool recursion, int rc_mode, SampleResult& r, std::string& why_not) {
+  uint32_t span_start = 0, span_len = 0, span_offset = 0;
+  if (sgc_span_geometry(k, read_len, offset.reverse, offset.index, recursion, &span_start, &span_len, &span_offset) != SGC_OK) {
+    why_not = "the guide window does not fit the reads";
+    return false;
+  }
+  MappedFile file(path);
+  if (!file.data) {
+    why_not = "cannot map the file";
+    return false;
+  }
+  std::vector<uint64_t> begin;
+  std::vector<uint32_t> isize;
+  if (!bgzf_index(file.data, file.size, begin, isize)) {
+    why_not = "not BGZF";
+    return false;
+  }
+  const auto t_start = std::chrono::steady_clock::now();
+  sgc_counter* c = nullptr;
+  sgc_fastq_stream* stream = nullptr;
+  uint8_t* pinned[2] = {nullptr, nullptr};
+  size_t pinned_cap = 0;
+  struct Guard {
+    sgc_counter*& c;
+    sgc_fastq_stream*& s;
+    uint8_t* (&p)[2];
+    ~Guard() {
+      sgc_fastq_stream_destroy(s);
+      sgc_counter_destroy(c);
+      for (auto* x : p)
+        if (x) sgc_host_free(x);
+    }
+  } guard{c, stream, pinned};
+  check(sgc_counter_create(lib, offset.reverse, span_offset, recursion, rc_mode, nullptr, nullptr, &c));
+  check(sgc_fastq_stream_create(c, read_len, span_start, span_len, &stream));
+  // waves of blocks: as many as fit 3 GiB of text (one device thread per block: the more the better)
+  const size_t n_blocks = isize.size();
+  std::vector<std::pair<size_t, size_t>> waves;
+  for (size_t a = 0; a < n_blocks;) {
+    size_t b = a;
+    uint64_t text = 0;
+    while (b < n_blocks && b - a < 49152 && text + isize[b] < (3ull << 30)) text += isize[b++];
+    if (b == a) b = a + 1;
+    waves.emplace_back(a, b);
+    pinned_cap = std::max<size_t>(pinned_cap, begin[b] - begin[a]);
+    a = b;
+  }
+  for (auto& p : pinned) {
+    void* q = nullptr;
+    check(sgc_host_alloc(&q, pinned_cap + 64));
+    p = static_cast<uint8_t*>(q);
+  }
+  // a side thread brings the compressed bytes of the next wave into pinned memory (page cache ->
+  // pinned, in parallel pieces) while the device works on the current one
+  std::mutex mu;
+  std::condition_variable cv;
+  size_t filled = 0, consumed = 0;  // waves copied into / released from the two buffers
+  std::thread reader([&] {
+    for (size_t w = 0; w < waves.size(); ++w) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return w < consumed + 2; });
+      }
+      const size_t a = waves[w].first, b = waves[w].second;
+      copy_lines(pinned[w & 1], reinterpret_cast<const char*>(file.data + begin[a]), begin[b] - begin[a]);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        filled = w + 1;
+      }
+      cv.notify_all();
+    }
+  });
+  std::string error;
+  int status = SGC_OK;
+  std::vector<uint64_t> rebased;
+  for (size_t w = 0; w < waves.size(); ++w) {
+    const size_t a = waves[w].first, b = waves[w].second;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return filled > w; });
+    }
+    if (status == SGC_OK) {
+      rebased.assign(begin.begin() + a, begin.begin() + b + 1);
+      for (auto& x : rebased) x -= begin[a];
+      status = sgc_fastq_stream_submit(stream, pinned[w & 1], rebased.data(), isize.data() + a, (uint32_t)(b - a));
+      if (status != SGC_OK) error = sgc_last_error();
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      consumed = w + 1;
+    }
+    cv.notify_all();
+  }
+  reader.join();
+  uint64_t n_records = 0;
+  if (status == SGC_OK) {
+    status = sgc_fastq_stream_finish(stream, &n_records);
+    if (status != SGC_OK) error = sgc_last_error();
+  }
+  if (status == SGC_ERR_GZIP || status == SGC_ERR_FASTQ_FORMAT) {
+    why_not = error;
+    return false;
+  }
+  if (status != SGC_OK) fail("%s", error.c_str());
+  r.counts.resize(n_guides);
+  check(sgc_counter_finish(c, r.counts.data(), &r.total, &r.matched));
+  r.span_reads = n_records;
+  r.device_ingest = true;
+  r.device_blocks = n_blocks;
+  r.submit_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+  return true;
+}
 
 // count_sample (count.rs:15-45).  The inflate threads hand over blocks of sequence lines in file
 // order; this thread packs them into pinned batches and submits them.  With several devices the
@@ -567,7 +746,11 @@ int main(int argc, char** argv) {
     std::mutex err_mu;
     std::string first_error;
     std::vector<uint32_t> first_len(n_samples);
-    for (size_t i = 0; i < n_samples; ++i) first_len[i] = (uint32_t)heads[i].first_len;
+    std::vector<char> head_uniform(n_samples, 0);  // 4-line FASTQ whose head reads all have one length
+    for (size_t i = 0; i < n_samples; ++i) {
+      first_len[i] = (uint32_t)heads[i].first_len;
+      head_uniform[i] = heads[i].fastq && heads[i].uniform;
+    }
     heads.clear();
     const unsigned workers = (unsigned)std::min<size_t>(std::max(args.threads, (unsigned)gpus), n_samples);
     const unsigned ingest_threads =
@@ -579,8 +762,21 @@ int main(int argc, char** argv) {
         try {
           std::vector<const sgc_library*> sample_libs;
           for (size_t j = 0; j < per_sample; ++j) sample_libs.push_back(libs[(s * per_sample + j) % gpus]);
-          results[s] = count_sample(sample_libs, hlib.n, hlib.k, args.input_paths[s], offsets[s], first_len[s],
-                                    !args.no_position_recursion, args.rc_mode, ingest_threads, !args.whole_lines);
+          // BGZF input of fixed-length FASTQ: the whole ingest on the device (one device per sample);
+          // anything else, or anything the device declines, through the host's inflate threads
+          bool on_device = false;
+          std::string why_not = "switched off";
+          if (!args.host_inflate && !args.whole_lines && head_uniform[s] && per_sample == 1 &&
+              args.input_paths[s].size() > 3 && args.input_paths[s].compare(args.input_paths[s].size() - 3, 3, ".gz") == 0)
+            on_device = count_sample_on_device(sample_libs[0], hlib.n, hlib.k, args.input_paths[s], offsets[s], first_len[s],
+                                               !args.no_position_recursion, args.rc_mode, results[s], why_not);
+          else if (!head_uniform[s])
+            why_not = "reads of several lengths (or FASTA)";
+          if (!on_device) {
+            results[s] = count_sample(sample_libs, hlib.n, hlib.k, args.input_paths[s], offsets[s], first_len[s],
+                                      !args.no_position_recursion, args.rc_mode, ingest_threads, !args.whole_lines);
+            results[s].host_because = why_not;
+          }
           if (!args.quiet) {
             const SampleResult& r = results[s];
             fprintf(stderr, "Finished: %s; Fraction mapped: %.3f [%llu / %llu]\n", names[s].c_str(),
@@ -604,18 +800,24 @@ int main(int argc, char** argv) {
       unsigned long long reads = 0;
       double wait_s = 0, copy_s = 0, submit_s = 0;
       unsigned max_shards = 1;
-      unsigned long long span_reads = 0;
+      unsigned long long span_reads = 0, device_blocks = 0;
+      unsigned device_samples = 0;
+      std::string host_because;
       for (const auto& r : results) {
         reads += r.total, wait_s += r.wait_s, copy_s += r.copy_s, submit_s += r.submit_s;
         span_reads += r.span_reads;
+        device_samples += r.device_ingest;
+        device_blocks += r.device_blocks;
+        if (!r.device_ingest && host_because.empty()) host_because = r.host_because;
         max_shards = std::max(max_shards, r.shards);
       }
       fprintf(stderr, "{\"count_s\": %.6f, \"reads\": %llu, \"samples\": %zu, \"sample_workers\": %u, "
-              "\"ingest_threads\": %u, \"gpus\": %d, \"read_shards_per_sample\": %u, \"span_reads\": %llu, \"wait_inflate_s\": %.6f, "
+              "\"ingest_threads\": %u, \"gpus\": %d, \"read_shards_per_sample\": %u, \"span_reads\": %llu, \"device_ingest_samples\": %u, "
+              "\"device_blocks\": %llu, \"host_ingest_because\": \"%s\", \"wait_inflate_s\": %.6f, "
               "\"copy_to_pinned_s\": %.6f, \"submit_sync_s\": %.6f, \"read_inputs_s\": %.3f, "
               "\"device_tables_s\": %.3f, \"offsets_s\": %.3f}\n",
-              count_s, reads, n_samples, workers, ingest_threads, gpus, max_shards, span_reads, wait_s, copy_s, submit_s,
-              t_inputs,
+              count_s, reads, n_samples, workers, ingest_threads, gpus, max_shards, span_reads, device_samples, device_blocks,
+              host_because.c_str(), wait_s, copy_s, submit_s, t_inputs,
               t_tables - t_inputs, t_offsets - t_tables);
     }
 

@@ -263,3 +263,64 @@ def test_span_records_and_whole_lines_give_the_same_table(tmp_path):
 
         n_span = int(re.search(r'"span_reads": (\d+)', c.stderr).group(1))
         assert 0 < n_span < 300_000
+
+
+@pytest.mark.gpu
+def test_bgzf_samples_are_inflated_framed_and_counted_on_the_device(tmp_path):
+    """BGZF input of fixed-length FASTQ takes the device ingest (sgc_fastq_stream_*); --host-inflate
+    forces the host's inflate threads; a BGZF file the device declines (a read of another length)
+    falls back by itself.  Always the same table, and the oracle's."""
+    import json
+
+    from sgcount_b200 import synth
+
+    seed = 0xB2000007
+    arr = synth.make_library(seed, 4000, 20)
+    lib_path = str(tmp_path / "lib.fa")
+    with open(lib_path, "wb") as f:
+        f.write(b"".join(b">lib.%d\n%s\n" % (i, arr[i].tobytes()) for i in range(len(arr))))
+    paths = []
+    for s, (rev, off) in enumerate([(False, 4), (True, 20)]):
+        p = str(tmp_path / f"s{s}.fastq.gz")
+        synth.Sample(seed, s, arr, 75, off, rev).write_fastq_bgzf(p, 0, 250_000)
+        paths.append(p)
+
+    def timing(proc):
+        return json.loads([l for l in proc.stderr.splitlines() if l.startswith("{")][-1])
+
+    dev = run("-l", lib_path, "-i", *paths, "--timing", check=True)
+    host = run("-l", lib_path, "-i", *paths, "--timing", "--host-inflate", check=True)
+    assert "Calculated Offsets: [Forward(4), Reverse(20)]" in dev.stderr
+    assert dev.stdout == host.stdout and len(dev.stdout.splitlines()) > 1000
+    assert timing(dev)["device_ingest_samples"] == 2 and timing(dev)["device_blocks"] > 1000
+    assert timing(host)["device_ingest_samples"] == 0
+    assert [l for l in dev.stderr.splitlines() if l.startswith("Finished")] == \
+        [l for l in host.stderr.splitlines() if l.startswith("Finished")]
+    # the oracle on the same files
+    lib_recs = orc.Records.from_path(lib_path)
+    olib = orc.Library.from_reader(lib_recs)
+    operm = orc.Permuter.new(olib)
+    counters = [orc.Counter.new(orc.Records.from_path(p), olib, operm, orc.Offset(rev, off), None, True,
+                                n_threads=os.cpu_count() or 4) for p, (rev, off) in zip(paths, [(False, 4), (True, 20)])]
+    text = orc.render_results(counters, ["s0", "s1"], olib, None, include_zero=False)
+    assert table(dev.stdout) == table(text)
+    # one shorter read deep in the file: the head looks regular, the device reports it, the host counts
+    lines = gzip.open(paths[0], "rb").read().rstrip(b"\n").split(b"\n")
+    lines[4 * 200_000 + 1] = lines[4 * 200_000 + 1][:50]
+    lines[4 * 200_000 + 3] = lines[4 * 200_000 + 3][:50]
+    odd_text = b"\n".join(lines) + b"\n"
+    import struct
+    import zlib
+
+    odd = str(tmp_path / "odd.fastq.gz")
+    with open(odd, "wb") as f:
+        for i in range(0, len(odd_text), 0xff00):
+            b = odd_text[i:i + 0xff00]
+            raw = zlib.compressobj(1, zlib.DEFLATED, -15)
+            body = raw.compress(b) + raw.flush()
+            f.write(bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0]) + b"BC" + struct.pack("<HH", 2, 18 + len(body) + 8 - 1) +
+                    body + struct.pack("<II", zlib.crc32(b), len(b)))
+    a = run("-l", lib_path, "-i", odd, "-a", "4", "--timing", check=True)
+    b = run("-l", lib_path, "-i", odd, "-a", "4", "--timing", "--host-inflate", check=True)
+    assert a.stdout == b.stdout
+    assert timing(a)["device_ingest_samples"] == 0 and "FASTQ" in timing(a)["host_ingest_because"]
