@@ -226,7 +226,8 @@ int sgc_reduce_prepare(const int* devices, int n_devices);
  * submit: n_blocks consecutive blocks, in file order, continuing where the previous call stopped;
  * gz + block_begin[i] .. gz + block_begin[i + 1] is block i (host memory), block_isize[i] its
  * ISIZE field.  One call is one wave: it should carry thousands of blocks (one device thread
- * each) and must inflate to less than 4 GiB.  Blocks may end anywhere in a record.
+ * each; the decode of a block is a long serial chain, so a wave takes about as long
+ * whether it holds ten thousand blocks or three hundred thousand) and must inflate to less than 64 GiB.  Blocks may end anywhere in a record.
  * finish: end of the input; *n_records = records counted. */
 typedef struct sgc_fastq_stream sgc_fastq_stream;
 int sgc_fastq_stream_create(sgc_counter* counter, uint32_t read_len, uint32_t span_start, uint32_t span_len,

@@ -1195,6 +1195,7 @@ int sgc_counter_create(const sgc_library* lib, int is_reverse, uint32_t offset, 
   if (!guard.ok()) return set_error(SGC_ERR_CUDA, "cudaSetDevice failed");
   sgc_counter* c = new sgc_counter();
   c->lib = lib;
+  c->device = lib->device;
   c->is_reverse = is_reverse != 0;
   c->offset = offset;
   c->recursion = position_recursion != 0;
@@ -1236,7 +1237,7 @@ int sgc_counter_create(const sgc_library* lib, int is_reverse, uint32_t offset, 
 
 void sgc_counter_destroy(sgc_counter* c) {
   if (!c) return;
-  DeviceGuard guard(c->lib->device);
+  DeviceGuard guard(c->device);  // (not c->lib: a garbage collector may have destroyed the library first)
   cudaStreamSynchronize(c->stream);
   for (sgc_fastq_stream* s : std::vector<sgc_fastq_stream*>(c->fastq_streams)) fastq_stream_release(s);
   if (c->copy_stream) {

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kInflateThreads) inflate_blocks_kernel(const u
 }
 
 // bytes [lo, hi) of the text are the current region: the carried tail, then this wave's text
-__device__ __forceinline__ void region_of(const StreamState* st, uint32_t n_text, uint64_t* lo, uint64_t* hi) {
+__device__ __forceinline__ void region_of(const StreamState* st, uint64_t n_text, uint64_t* lo, uint64_t* hi) {
   *lo = kHeadroom - st->tail;
   *hi = (uint64_t)kHeadroom + n_text;
 }
@@ -114,7 +114,7 @@ __device__ __forceinline__ uint32_t newline_mask16(const uint8_t* __restrict__ t
   return mask;
 }
 
-__global__ void __launch_bounds__(kChunkThreads) newline_count_kernel(const uint8_t* __restrict__ text, uint32_t n_text,
+__global__ void __launch_bounds__(kChunkThreads) newline_count_kernel(const uint8_t* __restrict__ text, uint64_t n_text,
                                                                      const StreamState* st, uint32_t* __restrict__ counts) {
   uint64_t lo, hi;
   region_of(st, n_text, &lo, &hi);
@@ -138,7 +138,7 @@ __global__ void wave_totals_kernel(const uint32_t* __restrict__ first_line, uint
   st->next_tail = 0;  // set by span_extract_kernel when a last complete record exists
 }
 
-__global__ void __launch_bounds__(kChunkThreads) span_extract_kernel(const uint8_t* __restrict__ text, uint32_t n_text,
+__global__ void __launch_bounds__(kChunkThreads) span_extract_kernel(const uint8_t* __restrict__ text, uint64_t n_text,
                                                                     StreamState* st, const uint32_t* __restrict__ first_line,
                                                                     uint32_t read_len, uint32_t span_start, uint32_t span_len,
                                                                     uint32_t span_stride, uint8_t* __restrict__ spans) {
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kChunkThreads) span_extract_kernel(const uint8
 
 // the bytes after the last complete record, parked in `tail_buf`, then put in front of the next
 // wave's text (two steps: source and destination may overlap when a wave is tiny)
-__global__ void tail_save_kernel(const uint8_t* __restrict__ text, uint32_t n_text, StreamState* st, uint8_t* __restrict__ tail_buf) {
+__global__ void tail_save_kernel(const uint8_t* __restrict__ text, uint64_t n_text, StreamState* st, uint8_t* __restrict__ tail_buf) {
   const uint64_t hi = (uint64_t)kHeadroom + n_text;
   const uint32_t tail = st->next_tail;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < tail; i += gridDim.x * blockDim.x) tail_buf[i] = text[hi - tail + i];
@@ -256,7 +256,7 @@ int stream_error(sgc_fastq_stream* s, const StreamState& st, uint64_t first_bloc
 }
 
 // frames and counts the region made of the carried tail and n_text fresh bytes at d_text + kHeadroom
-int frame_and_count(sgc_fastq_stream* s, uint32_t n_text, uint64_t first_block) {
+int frame_and_count(sgc_fastq_stream* s, uint64_t n_text, uint64_t first_block) {
   const uint32_t n_chunks = (uint32_t)(((uint64_t)kHeadroom + n_text + kChunk - 1) / kChunk);
   int rc = grow(&s->d_counts, &s->counts_cap, (size_t)n_chunks + 1);
   if (rc == SGC_OK) rc = grow(&s->d_first, &s->first_cap, (size_t)n_chunks + 1);
@@ -375,7 +375,7 @@ int sgc_fastq_stream_submit(sgc_fastq_stream* s, const uint8_t* gz, const uint64
     n_text += block_isize[i];
   }
   s->h_outoff[n_blocks] = kHeadroom + n_text;
-  if (n_text >= (1ull << 32) - 2 * kHeadroom) return set_error(SGC_ERR_BATCH_TOO_LARGE, "a wave of blocks must inflate to less than 4 GiB");
+  if (n_text >= (64ull << 30)) return set_error(SGC_ERR_BATCH_TOO_LARGE, "a wave of blocks must inflate to less than 64 GiB");
   const uint64_t gz_bytes = block_begin[n_blocks] - block_begin[0];
   int rc = grow(&s->d_gz, &s->gz_cap, (size_t)gz_bytes + 16);
   if (rc == SGC_OK) rc = grow(&s->d_text, &s->text_cap, (size_t)kHeadroom + n_text + 64);
@@ -388,7 +388,7 @@ int sgc_fastq_stream_submit(sgc_fastq_stream* s, const uint8_t* gz, const uint64
   inflate_blocks_kernel<<<(n_blocks + kInflateThreads - 1) / kInflateThreads, kInflateThreads, kInflateSmem, s->stream>>>(
       s->d_gz, s->d_begin, s->d_outoff, n_blocks, s->d_text, s->d_state);
   SGC_CUDA_TRY(cudaGetLastError());
-  rc = frame_and_count(s, (uint32_t)n_text, s->blocks_total);
+  rc = frame_and_count(s, n_text, s->blocks_total);
   if (rc) return rc;
   s->blocks_total += n_blocks;
   return SGC_OK;

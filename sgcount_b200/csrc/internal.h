@@ -66,6 +66,7 @@ int opaque_count(const sgc_counter* c, const uint8_t* d_lines, const uint32_t* d
 
 struct sgc_counter {
   const sgc_library* lib = nullptr;
+  int device = 0;  // lib->device, kept so that destroying the counter never looks at the library
   int is_reverse = 0;
   uint32_t offset = 0;
   int recursion = 1;

@@ -434,80 +434,31 @@ bool count_sample_on_device(const sgc_library* lib, uint32_t n_guides, uint32_t 
   const auto t_start = std::chrono::steady_clock::now();
   sgc_counter* c = nullptr;
   sgc_fastq_stream* stream = nullptr;
-  uint8_t* pinned[2] = {nullptr, nullptr};
-  size_t pinned_cap = 0;
   struct Guard {
     sgc_counter*& c;
     sgc_fastq_stream*& s;
-    uint8_t* (&p)[2];
     ~Guard() {
       sgc_fastq_stream_destroy(s);
       sgc_counter_destroy(c);
-      for (auto* x : p)
-        if (x) sgc_host_free(x);
     }
-  } guard{c, stream, pinned};
+  } guard{c, stream};
   check(sgc_counter_create(lib, offset.reverse, span_offset, recursion, rc_mode, nullptr, nullptr, &c));
   check(sgc_fastq_stream_create(c, read_len, span_start, span_len, &stream));
-  // waves of blocks: as many as fit 3 GiB of text (one device thread per block: the more the better)
+  // Waves of blocks.  One device thread inflates each block and a wave takes about as long with
+  // 300 000 blocks as with 10 000, so a wave is as large as 12 GiB of text allows.  The compressed
+  // bytes go to the device straight from the mapping (page cache -> the driver's staging buffers).
   const size_t n_blocks = isize.size();
-  std::vector<std::pair<size_t, size_t>> waves;
-  for (size_t a = 0; a < n_blocks;) {
-    size_t b = a;
-    uint64_t text = 0;
-    while (b < n_blocks && b - a < 49152 && text + isize[b] < (3ull << 30)) text += isize[b++];
-    if (b == a) b = a + 1;
-    waves.emplace_back(a, b);
-    pinned_cap = std::max<size_t>(pinned_cap, begin[b] - begin[a]);
-    a = b;
-  }
-  for (auto& p : pinned) {
-    void* q = nullptr;
-    check(sgc_host_alloc(&q, pinned_cap + 64));
-    p = static_cast<uint8_t*>(q);
-  }
-  // a side thread brings the compressed bytes of the next wave into pinned memory (page cache ->
-  // pinned, in parallel pieces) while the device works on the current one
-  std::mutex mu;
-  std::condition_variable cv;
-  size_t filled = 0, consumed = 0;  // waves copied into / released from the two buffers
-  std::thread reader([&] {
-    for (size_t w = 0; w < waves.size(); ++w) {
-      {
-        std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return w < consumed + 2; });
-      }
-      const size_t a = waves[w].first, b = waves[w].second;
-      copy_lines(pinned[w & 1], reinterpret_cast<const char*>(file.data + begin[a]), begin[b] - begin[a]);
-      {
-        std::lock_guard<std::mutex> lk(mu);
-        filled = w + 1;
-      }
-      cv.notify_all();
-    }
-  });
   std::string error;
   int status = SGC_OK;
-  std::vector<uint64_t> rebased;
-  for (size_t w = 0; w < waves.size(); ++w) {
-    const size_t a = waves[w].first, b = waves[w].second;
-    {
-      std::unique_lock<std::mutex> lk(mu);
-      cv.wait(lk, [&] { return filled > w; });
-    }
-    if (status == SGC_OK) {
-      rebased.assign(begin.begin() + a, begin.begin() + b + 1);
-      for (auto& x : rebased) x -= begin[a];
-      status = sgc_fastq_stream_submit(stream, pinned[w & 1], rebased.data(), isize.data() + a, (uint32_t)(b - a));
-      if (status != SGC_OK) error = sgc_last_error();
-    }
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      consumed = w + 1;
-    }
-    cv.notify_all();
+  for (size_t a = 0; a < n_blocks && status == SGC_OK;) {
+    size_t b = a;
+    uint64_t text = 0;
+    while (b < n_blocks && b - a < 262144 && text + isize[b] < (12ull << 30)) text += isize[b++];
+    if (b == a) b = a + 1;
+    status = sgc_fastq_stream_submit(stream, file.data, begin.data() + a, isize.data() + a, (uint32_t)(b - a));
+    if (status != SGC_OK) error = sgc_last_error();
+    a = b;
   }
-  reader.join();
   uint64_t n_records = 0;
   if (status == SGC_OK) {
     status = sgc_fastq_stream_finish(stream, &n_records);

@@ -16,7 +16,7 @@ import sgcount_b200 as sg
 from sgcount_b200 import synth
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16 << 20
-WAVE = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+WAVE = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
 arr = synth.make_library(0xB2000002, 77441, 20)
 library = sg.Library([arr[i].tobytes() for i in range(len(arr))], [b"lib.%d" % i for i in range(len(arr))])
 permuter = sg.Permuter.new(library)
