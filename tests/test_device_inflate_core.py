@@ -27,8 +27,10 @@ def built():
     assert os.path.exists(EXE)
 
 
-def run(path, cap=None):
-    p = subprocess.run([EXE, str(path)] + ([str(cap)] if cap else []), capture_output=True, text=True, timeout=120)
+def run(path, cap=None, align=0):
+    """decodes every member of the file; the output of member m is placed at alignment (m + align) % 8
+    between guard bytes (on the device the neighbouring bytes belong to other threads)"""
+    p = subprocess.run([EXE, str(path), str(cap or (1 << 30)), str(align)], capture_output=True, text=True, timeout=120)
     return p.returncode, p.stdout.strip()
 
 
@@ -46,7 +48,8 @@ def test_matches_zlib_on_every_block_kind(tmp_path, name):
     for vname, blob in variants.items():
         path = tmp_path / f"{name}.{vname}.gz"
         path.write_bytes(blob)
-        assert run(path) == (0, want([data])), (name, vname)
+        for align in (0, 1, 5):
+            assert run(path, align=align) == (0, want([data])), (name, vname, align)
 
 
 def test_header_options_members_and_bgzf_blocks(tmp_path):
@@ -119,7 +122,7 @@ def test_differential_fuzz_against_zlib(tmp_path):
             blob += c.compress(d) + c.flush()
         path = tmp_path / f"case{case}.gz"
         path.write_bytes(blob)
-        assert run(path) == (0, want(datas)), case
+        assert run(path, align=case) == (0, want(datas)), case
         # corrupt one bit of the first member's body
         if len(blob) > 40:
             bad = bytearray(blob)
