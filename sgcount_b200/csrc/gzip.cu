@@ -36,17 +36,18 @@ constexpr uint32_t kHeadroom = 1u << 16;  // room in front of a wave's text for 
 constexpr uint32_t kChunk = 4096;         // bytes per newline-count chunk
 constexpr uint32_t kChunkThreads = 256;   // 16 bytes per thread
 
-// look-ahead tables in shared memory, one column per thread: element e of thread t at [e * T + t]
+// look-ahead tables and per-length code counts in shared memory, one column per thread: element e
+// of thread t at [e * T + t]; the symbol lists stay in local memory
 struct DeviceTables {
   uint16_t* col;
-  uint16_t lcount[inflate::kMaxBits + 1], lsym[inflate::kLitLenSyms];
-  uint16_t dcount[inflate::kMaxBits + 1], dsym[inflate::kDistSyms];
-  __host__ __device__ __forceinline__ uint16_t get_lcount(int i) const { return lcount[i]; }
-  __host__ __device__ __forceinline__ void set_lcount(int i, uint16_t v) { lcount[i] = v; }
+  uint16_t lsym[inflate::kLitLenSyms], dsym[inflate::kDistSyms];  // local memory: one access per long code
+  static constexpr int kCounts = (1 << inflate::kFastBits) + (1 << inflate::kDistFastBits);
+  __host__ __device__ __forceinline__ uint16_t get_lcount(int i) const { return col[(kCounts + i) * kInflateThreads]; }
+  __host__ __device__ __forceinline__ void set_lcount(int i, uint16_t v) { col[(kCounts + i) * kInflateThreads] = v; }
   __host__ __device__ __forceinline__ uint16_t get_lsym(int i) const { return lsym[i]; }
   __host__ __device__ __forceinline__ void set_lsym(int i, uint16_t v) { lsym[i] = v; }
-  __host__ __device__ __forceinline__ uint16_t get_dcount(int i) const { return dcount[i]; }
-  __host__ __device__ __forceinline__ void set_dcount(int i, uint16_t v) { dcount[i] = v; }
+  __host__ __device__ __forceinline__ uint16_t get_dcount(int i) const { return col[(kCounts + 16 + i) * kInflateThreads]; }
+  __host__ __device__ __forceinline__ void set_dcount(int i, uint16_t v) { col[(kCounts + 16 + i) * kInflateThreads] = v; }
   __host__ __device__ __forceinline__ uint16_t get_dsym(int i) const { return dsym[i]; }
   __host__ __device__ __forceinline__ void set_dsym(int i, uint16_t v) { dsym[i] = v; }
   __host__ __device__ __forceinline__ uint16_t get_lfast(int i) const { return col[i * kInflateThreads]; }
@@ -54,7 +55,7 @@ struct DeviceTables {
   __host__ __device__ __forceinline__ uint16_t get_dfast(int i) const { return col[((1 << inflate::kFastBits) + i) * kInflateThreads]; }
   __host__ __device__ __forceinline__ void set_dfast(int i, uint16_t v) { col[((1 << inflate::kFastBits) + i) * kInflateThreads] = v; }
 };
-constexpr size_t kInflateSmem = ((1 << inflate::kFastBits) + (1 << inflate::kDistFastBits)) * kInflateThreads * sizeof(uint16_t);
+constexpr size_t kInflateSmem = (DeviceTables::kCounts + 32) * kInflateThreads * sizeof(uint16_t);
 
 // what the kernels of a stream hand from wave to wave, and back to the host
 struct StreamState {
@@ -377,7 +378,7 @@ int sgc_fastq_stream_submit(sgc_fastq_stream* s, const uint8_t* gz, const uint64
   s->h_outoff[n_blocks] = kHeadroom + n_text;
   if (n_text >= (64ull << 30)) return set_error(SGC_ERR_BATCH_TOO_LARGE, "a wave of blocks must inflate to less than 64 GiB");
   const uint64_t gz_bytes = block_begin[n_blocks] - block_begin[0];
-  int rc = grow(&s->d_gz, &s->gz_cap, (size_t)gz_bytes + 16);
+  int rc = grow(&s->d_gz, &s->gz_cap, (size_t)gz_bytes + 64);  // the decoder prefetches up to 47 bytes past a block
   if (rc == SGC_OK) rc = grow(&s->d_text, &s->text_cap, (size_t)kHeadroom + n_text + 64);
   if (rc == SGC_OK) rc = grow(&s->d_begin, &s->begin_cap, (size_t)n_blocks + 1);
   if (rc == SGC_OK) rc = grow(&s->d_outoff, &s->outoff_cap, (size_t)n_blocks + 1);

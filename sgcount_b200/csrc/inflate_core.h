@@ -56,45 +56,73 @@ struct PlainTables {
   SGC_HD void set_dfast(int i, uint16_t v) { dfast[i] = v; }
 };
 
-// LSB-first bit reader over a byte range, refilled 32 bits at a time with ALIGNED word loads (one
-// load per refill, no byte loop).  The words that hold the first and last byte of the range must be
-// readable, i.e. up to 3 bytes before `in` and 3 bytes after in + len may be touched; bits past
-// the range read as zero, and `overrun` says that the decoder asked for bits beyond it.
+// LSB-first bit reader over a byte range, refilled 32 bits at a time from a register queue that
+// is itself filled with ALIGNED 16-byte loads one block ahead: the load of block i + 1 is issued
+// when the decoder starts on block i, four refills before its first word is needed, so the
+// latency of the input stream never sits on the decode chain.  Up to 15 bytes before `in` and
+// 47 bytes after in + len may be touched; bits past the range read as zero, and `overrun` says
+// that the decoder asked for bits beyond it.
+struct Block16 {
+  uint32_t w[4];
+};
+SGC_HD Block16 load_block16(const uint8_t* p) {
+  Block16 b;
+#ifdef __CUDA_ARCH__
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  b.w[0] = v.x;
+  b.w[1] = v.y;
+  b.w[2] = v.z;
+  b.w[3] = v.w;
+#else
+  __builtin_memcpy(b.w, p, 16);
+#endif
+  return b;
+}
+
 struct BitReader {
-  const uint32_t* words;  // in, rounded down to a word
+  const uint8_t* ahead;   // the block after `pre`
+  Block16 blk, pre;       // the block being consumed, and the next one (already loaded)
+  uint32_t wi;            // next word of blk
   size_t len;             // bytes of the range
-  size_t next;            // byte offset (from `in`) of the next word to load; may be negative mod 2^64 at first
-  uint32_t lead;          // in - (const uint8_t*)words
+  size_t next;            // byte offset (from `in`) of the next word; may be negative mod 2^64 at first
   uint64_t buf;
   int cnt;
   bool overrun;
   SGC_HD void init(const uint8_t* in, size_t n, size_t at) {
     const uintptr_t a = (uintptr_t)(in + at);
-    words = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint8_t* b0 = reinterpret_cast<const uint8_t*>(a & ~(uintptr_t)15);
+    const uint32_t lead = (uint32_t)(a & 3u);
     len = n;
-    lead = (uint32_t)(a & 3u);
-    next = at - lead;  // offset of words[0] relative to `in` (wraps when the word starts before `in`)
-    buf = 0;
-    cnt = 0;
+    wi = (uint32_t)(a & 15u) >> 2;
+    next = at - lead;  // offset of the word that holds the position (wraps when it starts before `in`)
+    blk = load_block16(b0);
+    pre = load_block16(b0 + 16);
+    ahead = b0 + 32;
     overrun = false;
     // first word: drop the bytes in front of the position
-    uint32_t w = load_word();
+    const uint32_t w = load_word();
     buf = (uint64_t)(w >> (8 * lead));
     cnt = 32 - 8 * (int)lead;
   }
   SGC_HD uint32_t load_word() {
+    uint32_t w = wi == 0 ? blk.w[0] : (wi == 1 ? blk.w[1] : (wi == 2 ? blk.w[2] : blk.w[3]));
     // bytes of this word that lie inside [0, len) keep their value, the others read as zero
     const size_t off = next;  // may be "negative" for the very first word only
-    uint32_t w = 0;
     if ((ptrdiff_t)off < (ptrdiff_t)len) {
-      w = *words;
       const ptrdiff_t over = (ptrdiff_t)off + 4 - (ptrdiff_t)len;  // bytes of the word past the range
       if (over > 0) w &= over >= 4 ? 0u : (0xFFFFFFFFu >> (8 * (int)over));
-    } else if ((ptrdiff_t)off >= (ptrdiff_t)len + 8) {
-      overrun = true;  // more than the slack a decoder may look ahead
+    } else {
+      w = 0;
+      if ((ptrdiff_t)off >= (ptrdiff_t)len + 8) overrun = true;  // more than the slack a decoder may look ahead
     }
-    ++words;
     next += 4;
+    if (++wi == 4) {
+      wi = 0;
+      blk = pre;
+      // never a load that reaches 48 bytes or more past the range (the caller guarantees 47)
+      if ((ptrdiff_t)(next + 16) < (ptrdiff_t)len + 32) pre = load_block16(ahead);
+      ahead += 16;
+    }
     return w;
   }
   SGC_HD void refill() {  // more than 32 valid bits afterwards

@@ -17,7 +17,7 @@ int main(int argc, char** argv) {
   for (size_t got; (got = fread(buf, 1, sizeof buf, f)) > 0;) data.insert(data.end(), buf, buf + got);
   fclose(f);
   const size_t n_data = data.size();
-  data.resize(n_data + 8);  // the decoder loads aligned words: up to 3 bytes past the end are touched
+  data.resize(n_data + 64);  // the decoder prefetches aligned 16-byte blocks: up to 47 bytes past the end are touched
   const size_t cap = argc > 2 ? (size_t)atoll(argv[2]) : (size_t)1 << 30;
   // The member is decoded at every alignment in turn, between guard bytes: on the device its
   // neighbours in the text are written by other threads, so not one byte outside
