@@ -202,6 +202,28 @@ def fastq_leg(lib_arr, n_reads: int, with_oracle: bool, gpus: int = 1):
                "what": "sgcount CLI on a multi-member gzip FASTQ (1 Mi reads per member, so at most `members` inflate "
                        "threads have work): member-parallel inflate + record framing, H2D, count kernel, D2H; table "
                        "build and process start-up are outside count_s"}
+        # the same reads as BGZF (bgzip's blocked gzip, 64 KB blocks cut anywhere): the CLI inflates,
+        # frames and counts such a file on the device (sgc_fastq_stream_*), no host core in the loop
+        bgzf = os.path.join(tmp, "sample0.bgzf.fastq.gz")
+        sample.write_fastq_bgzf(bgzf, 0, n_reads, gz_level=1)
+        out_d = os.path.join(tmp, "counts_dev.tsv")
+        best_d, err_d = run_cli(exe, lib_path, [bgzf], ["-a", str(OFFSET)], out_d)
+        if err_d:
+            res["device_ingest"] = {"unavailable": err_d}
+        else:
+            td, wd = best_d
+            same = open(out_d).read().replace("sample0.bgzf", "sample0") == text_one
+            res["device_ingest"] = {"value": td["reads"] / td["count_s"], "unit": "reads/s", "count_s": td["count_s"],
+                                    "process_wall_s": wd, "gz_bytes": os.path.getsize(bgzf), "blocks": td.get("device_blocks"),
+                                    "device_ingest_samples": td.get("device_ingest_samples"), "same_table": same,
+                                    "what": "the same reads as a BGZF file through the same CLI: one device thread inflates "
+                                            "each 64 KB block, a newline scan frames the records, the guide-window spans are "
+                                            "cut out and counted; only the compressed bytes cross PCIe"}
+            assert same, "device ingest table differs from the host path's"
+            best_h, err_h = run_cli(exe, lib_path, [bgzf], ["-a", str(OFFSET), "--host-inflate"], out_d)
+            if not err_h:
+                res["device_ingest"]["host_inflate_same_file"] = {"value": best_h[0]["reads"] / best_h[0]["count_s"],
+                                                                  "unit": "reads/s", "count_s": best_h[0]["count_s"]}
         if gpus > 1:
             out_n = os.path.join(tmp, "counts_n.tsv")
             best, err = run_cli(exe, lib_path, [fq], ["-a", str(OFFSET), "--gpus", str(gpus)], out_n)

@@ -16,8 +16,10 @@
 
 #ifdef __CUDACC__
 #define SGC_HD __host__ __device__ __forceinline__
+#define SGC_HD_COLD __host__ __device__ __noinline__  // block headers: kept out of the symbol loop's code
 #else
 #define SGC_HD inline
+#define SGC_HD_COLD inline
 #endif
 
 namespace sgc {
@@ -335,7 +337,7 @@ SGC_HD bool install_codes(Tables& t, const uint8_t* ll, int nl, const uint8_t* d
 
 // The code tables of a fixed (type 1) or dynamic (type 2) block, read from the block header.
 template <typename Tables>
-SGC_HD int read_codes(BitReader& br, Tables& t, uint32_t type) {
+SGC_HD_COLD int read_codes(BitReader& br, Tables& t, uint32_t type) {
   uint8_t lengths[kLitLenSyms + kDistSyms];
   int nl, nd;
   if (type == 1) {  // fixed code
@@ -454,6 +456,13 @@ SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t 
           state = kDone;
         } else {
           ow.put((uint8_t)sym);
+          // literals come in runs (a sequence line): if the next code is a short literal too, take
+          // it in the same step (at least 17 bits are left after the first code)
+          const uint16_t e2 = t.get_lfast((int)br.peek(kFastBits));
+          if (e2 && (e2 >> 4) < 256 && ow.op < out_cap) {
+            br.drop(e2 & 15);
+            ow.put((uint8_t)(e2 >> 4));
+          }
         }
       } else if (sym == 256) {
         if (br.overrun) {
