@@ -47,7 +47,7 @@ OFFSET = 5
 READS_PER_GPU = 50_000_000
 WORKLOAD = "config2: Brunello-shaped 77441x20bp library, 1 sample x 50M x 75bp reads, 1-mismatch, Forward(5)"
 FALLBACK_HBM_GBS = 6650.0
-PARITY_PREFIX = 250_000  # reads per shard the oracle re-counts
+PARITY_PREFIX = 1_000_000  # reads per shard the oracle re-counts
 
 # BASELINE.json configs 3-5.  sample = (sample index, reverse, offset).
 CONFIGS = {

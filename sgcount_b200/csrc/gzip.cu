@@ -37,23 +37,27 @@ constexpr uint32_t kChunk = 4096;         // bytes per newline-count chunk
 constexpr uint32_t kChunkThreads = 256;   // 16 bytes per thread
 
 // look-ahead tables and per-length code counts in shared memory, one column per thread: element e
-// of thread t at [e * T + t]; the symbol lists stay in local memory
+// of thread t at [e * T + t]; the symbol lists stay in local memory (one access per long code).
+// The handle is two pointers, passed by value (inflate_core.h).
+struct DeviceSymbols {
+  uint16_t lsym[inflate::kLitLenSyms], dsym[inflate::kDistSyms];
+};
 struct DeviceTables {
   uint16_t* col;
-  uint16_t lsym[inflate::kLitLenSyms], dsym[inflate::kDistSyms];  // local memory: one access per long code
+  DeviceSymbols* syms;
   static constexpr int kCounts = (1 << inflate::kFastBits) + (1 << inflate::kDistFastBits);
   __host__ __device__ __forceinline__ uint16_t get_lcount(int i) const { return col[(kCounts + i) * kInflateThreads]; }
-  __host__ __device__ __forceinline__ void set_lcount(int i, uint16_t v) { col[(kCounts + i) * kInflateThreads] = v; }
-  __host__ __device__ __forceinline__ uint16_t get_lsym(int i) const { return lsym[i]; }
-  __host__ __device__ __forceinline__ void set_lsym(int i, uint16_t v) { lsym[i] = v; }
+  __host__ __device__ __forceinline__ void set_lcount(int i, uint16_t v) const { col[(kCounts + i) * kInflateThreads] = v; }
+  __host__ __device__ __forceinline__ uint16_t get_lsym(int i) const { return syms->lsym[i]; }
+  __host__ __device__ __forceinline__ void set_lsym(int i, uint16_t v) const { syms->lsym[i] = v; }
   __host__ __device__ __forceinline__ uint16_t get_dcount(int i) const { return col[(kCounts + 16 + i) * kInflateThreads]; }
-  __host__ __device__ __forceinline__ void set_dcount(int i, uint16_t v) { col[(kCounts + 16 + i) * kInflateThreads] = v; }
-  __host__ __device__ __forceinline__ uint16_t get_dsym(int i) const { return dsym[i]; }
-  __host__ __device__ __forceinline__ void set_dsym(int i, uint16_t v) { dsym[i] = v; }
+  __host__ __device__ __forceinline__ void set_dcount(int i, uint16_t v) const { col[(kCounts + 16 + i) * kInflateThreads] = v; }
+  __host__ __device__ __forceinline__ uint16_t get_dsym(int i) const { return syms->dsym[i]; }
+  __host__ __device__ __forceinline__ void set_dsym(int i, uint16_t v) const { syms->dsym[i] = v; }
   __host__ __device__ __forceinline__ uint16_t get_lfast(int i) const { return col[i * kInflateThreads]; }
-  __host__ __device__ __forceinline__ void set_lfast(int i, uint16_t v) { col[i * kInflateThreads] = v; }
+  __host__ __device__ __forceinline__ void set_lfast(int i, uint16_t v) const { col[i * kInflateThreads] = v; }
   __host__ __device__ __forceinline__ uint16_t get_dfast(int i) const { return col[((1 << inflate::kFastBits) + i) * kInflateThreads]; }
-  __host__ __device__ __forceinline__ void set_dfast(int i, uint16_t v) { col[((1 << inflate::kFastBits) + i) * kInflateThreads] = v; }
+  __host__ __device__ __forceinline__ void set_dfast(int i, uint16_t v) const { col[((1 << inflate::kFastBits) + i) * kInflateThreads] = v; }
 };
 constexpr size_t kInflateSmem = (DeviceTables::kCounts + 32) * kInflateThreads * sizeof(uint16_t);
 
@@ -76,8 +80,8 @@ __global__ void __launch_bounds__(kInflateThreads) inflate_blocks_kernel(const u
   extern __shared__ uint16_t sm[];
   const uint32_t m = blockIdx.x * kInflateThreads + threadIdx.x;
   if (m >= n) return;
-  DeviceTables t;
-  t.col = sm + threadIdx.x;
+  DeviceSymbols symbols;
+  const DeviceTables t{sm + threadIdx.x, &symbols};
   const uint64_t base = begin[0];
   const uint8_t* in = gz + (begin[m] - base);
   const size_t in_len = (size_t)(begin[m + 1] - begin[m]);

@@ -38,24 +38,30 @@ enum Status : int {
 constexpr int kMaxBits = 15;
 constexpr int kLitLenSyms = 288, kDistSyms = 32, kFastBits = 8, kDistFastBits = 6;
 
+// A `Tables` type is a HANDLE, passed by value: a pointer or two to wherever the tables live.
+// (The decoder's state must stay in registers; an object whose address is handed to the
+// out-of-line header parser would be pinned to memory for the whole loop.)
 // Plain-array tables (host, and the reference point for the device layout).
-struct PlainTables {
+struct PlainTableStorage {
   uint16_t lcount[kMaxBits + 1], lsym[kLitLenSyms];
   uint16_t dcount[kMaxBits + 1], dsym[kDistSyms];
   uint16_t lfast[1 << kFastBits];  // (symbol << 4) | code length, 0 = longer than kFastBits
   uint16_t dfast[1 << kDistFastBits];
-  SGC_HD uint16_t get_lcount(int i) const { return lcount[i]; }
-  SGC_HD void set_lcount(int i, uint16_t v) { lcount[i] = v; }
-  SGC_HD uint16_t get_lsym(int i) const { return lsym[i]; }
-  SGC_HD void set_lsym(int i, uint16_t v) { lsym[i] = v; }
-  SGC_HD uint16_t get_dcount(int i) const { return dcount[i]; }
-  SGC_HD void set_dcount(int i, uint16_t v) { dcount[i] = v; }
-  SGC_HD uint16_t get_dsym(int i) const { return dsym[i]; }
-  SGC_HD void set_dsym(int i, uint16_t v) { dsym[i] = v; }
-  SGC_HD uint16_t get_lfast(int i) const { return lfast[i]; }
-  SGC_HD void set_lfast(int i, uint16_t v) { lfast[i] = v; }
-  SGC_HD uint16_t get_dfast(int i) const { return dfast[i]; }
-  SGC_HD void set_dfast(int i, uint16_t v) { dfast[i] = v; }
+};
+struct PlainTables {
+  PlainTableStorage* s;
+  SGC_HD uint16_t get_lcount(int i) const { return s->lcount[i]; }
+  SGC_HD void set_lcount(int i, uint16_t v) const { s->lcount[i] = v; }
+  SGC_HD uint16_t get_lsym(int i) const { return s->lsym[i]; }
+  SGC_HD void set_lsym(int i, uint16_t v) const { s->lsym[i] = v; }
+  SGC_HD uint16_t get_dcount(int i) const { return s->dcount[i]; }
+  SGC_HD void set_dcount(int i, uint16_t v) const { s->dcount[i] = v; }
+  SGC_HD uint16_t get_dsym(int i) const { return s->dsym[i]; }
+  SGC_HD void set_dsym(int i, uint16_t v) const { s->dsym[i] = v; }
+  SGC_HD uint16_t get_lfast(int i) const { return s->lfast[i]; }
+  SGC_HD void set_lfast(int i, uint16_t v) const { s->lfast[i] = v; }
+  SGC_HD uint16_t get_dfast(int i) const { return s->dfast[i]; }
+  SGC_HD void set_dfast(int i, uint16_t v) const { s->dfast[i] = v; }
 };
 
 // LSB-first bit reader over a byte range, refilled 32 bits at a time from a register queue that
@@ -203,40 +209,42 @@ struct OutWriter {
     ++op;
     if (k == 8) flush_word();
   }
-  // eight bytes at once (low byte first)
-  SGC_HD void put8(uint64_t v) {
-    if (first != 0 || k != 0) {
-      if (first == 0) {
-        uint8_t* w = word_ptr();
-        store_u64(w, acc | (v << (8 * k)));
-        acc = v >> (8 * (8 - k));  // k in 1..7
-        op += 8;
-      } else {
-        for (int i = 0; i < 8; ++i) put((uint8_t)(v >> (8 * i)));
-      }
-    } else {
-      store_u64(base + op, v);
-      op += 8;
+  // n <= 8 bytes at once (the low n bytes of v, low byte first)
+  SGC_HD void put_n(uint64_t v, uint32_t n) {
+    if (n < 8) v &= (1ull << (8 * n)) - 1;
+    if (first != 0) {  // still in the member's first word, shared with its neighbour
+      for (uint32_t i = 0; i < n; ++i) put((uint8_t)(v >> (8 * i)));
+      return;
     }
+    uint8_t* w = word_ptr();
+    acc |= v << (8 * k);  // k < 8
+    const uint32_t nk = k + n;
+    if (nk >= 8) {
+      store_u64(w, acc);
+      acc = k ? v >> (8 * (8 - k)) : 0;
+      k = nk - 8;
+    } else {
+      k = nk;
+    }
+    op += n;
   }
   SGC_HD void finish() {  // the last, partial word
     uint8_t* w = word_ptr();
     for (uint32_t i = first; i < k; ++i) w[i] = (uint8_t)(acc >> (8 * i));
     first = k;  // nothing left to write
   }
-  // byte j < op of the member's output, flushed or not
-  SGC_HD uint8_t get(size_t j) const {
-    const uintptr_t a = (uintptr_t)base + j, w = (uintptr_t)base + op - k;
-    if (a >= w) return (uint8_t)(acc >> (8 * (a & 7)));
-    return *reinterpret_cast<const uint8_t*>(a);
-  }
-  // bytes [j, j + 8) of the output, all of them in words that have been flushed (j + 8 <= op - k)
-  SGC_HD uint64_t get8_flushed(size_t j) const {
-    const uintptr_t a = (uintptr_t)base + j;
+  // Eight bytes of the output starting at byte j <= op - 1, flushed or not: memory where the
+  // words have gone out, the register for the word in progress.  Bytes at or beyond `op` are
+  // unspecified (a caller copying a short period masks them off).
+  SGC_HD uint64_t get8(size_t j) const {
+    const uintptr_t a = (uintptr_t)base + j, cur = (uintptr_t)base + op - k;  // cur: the word in progress
+    if (a >= cur) return acc >> (8 * (uint32_t)(a - cur));
     const uint8_t* w = reinterpret_cast<const uint8_t*>(a & ~(uintptr_t)7);
     const uint32_t sh = 8 * (uint32_t)(a & 7);
     uint64_t v = load_u64(w) >> sh;
-    if (sh) v |= load_u64(w + 8) << (64 - sh);
+    if (sh && (uintptr_t)w + 8 < cur) v |= load_u64(w + 8) << (64 - sh);
+    const uintptr_t d = cur - a;  // bytes of the result that come from memory: the rest from the register
+    if (d < 8) v = (v & ((1ull << (8 * d)) - 1)) | (acc << (8 * d));
     return v;
   }
 };
@@ -322,7 +330,7 @@ SGC_HD void fill_lookahead(const uint16_t* count, int bits, GetSym get_sym, SetF
 
 // Tables of one block from the two length arrays; also fills the look-ahead tables.
 template <typename Tables>
-SGC_HD bool install_codes(Tables& t, const uint8_t* ll, int nl, const uint8_t* dl, int nd) {
+SGC_HD bool install_codes(Tables t, const uint8_t* ll, int nl, const uint8_t* dl, int nd) {
   uint16_t lc[kMaxBits + 1], dc[kMaxBits + 1];
   if (!build_canonical(ll, nl, [&](int i, uint16_t v) { t.set_lcount(i, v); }, [&](int i, uint16_t v) { t.set_lsym(i, v); }, lc))
     return false;
@@ -336,8 +344,9 @@ SGC_HD bool install_codes(Tables& t, const uint8_t* ll, int nl, const uint8_t* d
 }
 
 // The code tables of a fixed (type 1) or dynamic (type 2) block, read from the block header.
+// (`br` is the caller's COPY of its reader: see gunzip_member.)
 template <typename Tables>
-SGC_HD_COLD int read_codes(BitReader& br, Tables& t, uint32_t type) {
+SGC_HD_COLD int read_codes(BitReader& br, Tables t, uint32_t type) {
   uint8_t lengths[kLitLenSyms + kDistSyms];
   int nl, nd;
   if (type == 1) {  // fixed code
@@ -404,7 +413,7 @@ SGC_HD_COLD int read_codes(BitReader& br, Tables& t, uint32_t type) {
 // doing one step of whatever state it is in, instead of drifting apart for good.  A long match
 // (a quality line is one 75-byte match) is copied in steps, so no lane waits for another's copy.
 template <typename Tables>
-SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, Tables& t, size_t* consumed,
+SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, Tables t, size_t* consumed,
                          size_t* produced, uint32_t* crc32, uint32_t* isize) {
   // ---- RFC 1952 header
   if (in_len < 18) return in_len < 4 || (in[0] == 0x1f && in[1] == 0x8b) ? kTruncated : kBadHeader;
@@ -433,8 +442,8 @@ SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t 
   uint32_t last = 0;
   uint32_t run = 0;      // bytes of the pending match / stored block still to copy
   uint32_t dist = 0;     // distance of the pending match
-  uint64_t pattern = 0;  // dist < 8: the dist bytes the match repeats, lowest byte first
-  uint32_t phase = 0;    //           and which of them comes next
+  uint64_t pattern = 0;  // dist < 8: the next eight bytes of the repetition, lowest byte first
+  uint32_t phase = 0;    //           and 8 mod dist
   size_t stored_at = 0;  // input position of the stored bytes
   while (state != kDone) {
     if (state == kSymbol) {
@@ -495,10 +504,10 @@ SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t 
             rc = kOutputFull;
             state = kDone;
           } else {
-            if (dist < 8) {  // a short period: keep the repeated bytes in a register
-              pattern = 0;
-              for (uint32_t i = 0; i < dist; ++i) pattern |= (uint64_t)ow.get(ow.op - dist + i) << (8 * i);
-              phase = 0;
+            if (dist < 8) {  // a short period: keep eight bytes of the repetition in a register
+              pattern = ow.get8(ow.op - dist) & ((1ull << (8 * dist)) - 1);
+              for (uint32_t sh = 8 * dist; sh < 64; sh *= 2) pattern |= pattern << sh;
+              phase = 8 % dist;  // how far eight bytes advance the period
             }
             state = kCopy;
           }
@@ -506,20 +515,13 @@ SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t 
       }
     } else if (state == kCopy) {
       const uint32_t n = run < 8 ? run : 8;
-      if (dist >= 16 && n == 8) {
-        // the source lies wholly in flushed words: two aligned loads, one store
-        ow.put8(ow.get8_flushed(ow.op - dist));
-      } else if (dist >= 8) {
-        uint8_t tmp[8];
-        for (uint32_t i = 0; i < 8; ++i) tmp[i] = i < n ? ow.get(ow.op + i - dist) : 0;  // the source ends before this step's first byte
-        for (uint32_t i = 0; i < 8; ++i)
-          if (i < n) ow.put(tmp[i]);
+      if (dist >= 8) {
+        ow.put_n(ow.get8(ow.op - dist), n);  // the source ends before this step's first byte
       } else {
-        for (uint32_t i = 0; i < 8; ++i)
-          if (i < n) {
-            ow.put((uint8_t)(pattern >> (8 * phase)));
-            phase = phase + 1 == dist ? 0 : phase + 1;
-          }
+        // a short period: `pattern` holds the next eight bytes of the repetition; eight bytes on,
+        // the repetition is 8 mod dist bytes further into its period
+        ow.put_n(pattern, n);
+        if (phase) pattern = (pattern >> (8 * phase)) | (pattern << (8 * (dist - phase)));
       }
       run -= n;
       if (run == 0) state = kSymbol;
@@ -564,7 +566,10 @@ SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t 
         rc = br.overrun ? kTruncated : kBadBlock;
         state = kDone;
       } else {
-        rc = read_codes(br, t, type);
+        // through a copy: only the copy's address leaves this function, `br` itself stays in registers
+        BitReader header_reader = br;
+        rc = read_codes(header_reader, t, type);
+        br = header_reader;
         state = rc == kOk ? kSymbol : kDone;
       }
     }

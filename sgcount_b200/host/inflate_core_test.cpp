@@ -26,7 +26,8 @@ int main(int argc, char** argv) {
   const size_t align0 = argc > 3 ? (size_t)atoll(argv[3]) : 0;  // alignment of the first member's output
   size_t room = cap < ((size_t)64 << 20) ? cap : ((size_t)64 << 20);
   std::vector<unsigned char> store(room + 2 * kGuard + 16);
-  sgc::inflate::PlainTables t;
+  sgc::inflate::PlainTableStorage table_storage;
+  sgc::inflate::PlainTables t{&table_storage};
   size_t pos = 0, members = 0;
   unsigned long long total = 0, h = 1469598103934665603ull;
   while (pos < n_data) {

@@ -261,8 +261,10 @@ def test_span_records_and_whole_lines_give_the_same_table(tmp_path):
         assert c.stdout == d.stdout
         import re
 
+        # the member with the short read comes as whole lines, and so does every member framed after
+        # it was seen (the inflate threads run side by side: how many that is depends on timing)
         n_span = int(re.search(r'"span_reads": (\d+)', c.stderr).group(1))
-        assert 0 < n_span < 300_000
+        assert 0 <= n_span <= 300_000 - 20_000
 
 
 @pytest.mark.gpu
