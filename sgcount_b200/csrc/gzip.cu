@@ -7,7 +7,7 @@
 // 64 KB, each announcing its size in a 'BC' extra field — needs no host core at all:
 //
 //   inflate_blocks_kernel   ONE THREAD per block runs the sequential DEFLATE decoder of
-//                           inflate_core.h (canonical Huffman, 8- and 6-bit look-ahead tables in
+//                           inflate_core.h (canonical Huffman, 7- and 5-bit look-ahead tables in
 //                           bank-interleaved shared memory, the rest of the code tables in local
 //                           memory), writing its text where the prefix sum of the blocks' ISIZE
 //                           fields puts it.  Tens of thousands of blocks are in flight, so the

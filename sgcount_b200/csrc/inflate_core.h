@@ -5,8 +5,8 @@
 // Written from the RFCs for this use: many small members (BGZF blocks, the blocked gzip that
 // sequencers and bgzip write) decoded side by side, one thread each, so the state per stream must
 // be small.  Huffman codes are kept in canonical form — count of codes per length + symbols in code
-// order, 640 bytes for the literal/length alphabet — and decoded through an 8-bit look-ahead table
-// (covers every code of up to 8 bits: the bases and quality characters of a FASTQ) with the
+// order, 640 bytes for the literal/length alphabet — and decoded through a 7-bit look-ahead table
+// (covers every code of up to 7 bits: the bases and quality characters of a FASTQ) with the
 // bit-serial canonical walk behind it for longer codes.  The tables live wherever the `Tables`
 // policy puts them: plain arrays on the host, bank-interleaved shared memory on the device.
 #pragma once
@@ -36,7 +36,17 @@ enum Status : int {
 };
 
 constexpr int kMaxBits = 15;
-constexpr int kLitLenSyms = 288, kDistSyms = 32, kFastBits = 8, kDistFastBits = 6;
+// Width of the look-ahead tables (literal/length, distance); overridable for A/B builds.  Measured on the
+// device (profiles/r2_inflate_tables_ab.txt): the tables share the SM with the L1 the decoders read their
+// input, their matches and their symbol lists through, and 7 + 5 bits (24.5 KB per 64 threads) beat 8 + 6
+// (45 KB) by a third and 9 + 6 by a factor of two.
+#ifndef SGC_INFLATE_FAST_BITS
+#define SGC_INFLATE_FAST_BITS 7
+#endif
+#ifndef SGC_INFLATE_DIST_FAST_BITS
+#define SGC_INFLATE_DIST_FAST_BITS 5
+#endif
+constexpr int kLitLenSyms = 288, kDistSyms = 32, kFastBits = SGC_INFLATE_FAST_BITS, kDistFastBits = SGC_INFLATE_DIST_FAST_BITS;
 
 // A `Tables` type is a HANDLE, passed by value: a pointer or two to wherever the tables live.
 // (The decoder's state must stay in registers; an object whose address is handed to the
