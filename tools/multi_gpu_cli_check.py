@@ -69,3 +69,25 @@ for gpus in sorted({1, torch.cuda.device_count()}):
               f"tables {t['device_tables_s']:.2f} s", flush=True)
 assert len(set(single.values())) == 1, "single-sample tables differ between GPU counts / framings"
 print("single sample: tables identical on 1 and", torch.cuda.device_count(), "GPUs, offset detected once")
+
+# The same 8 samples as BGZF: inflate and record framing run on the device that counts the sample,
+# so the host's cores are out of the loop and the samples scale with the devices.
+bpaths = []
+for s, (rev, off) in enumerate(truth):
+    p = os.path.join(tmp, f"b{s}.fastq.gz")
+    synth.Sample(seed, s, arr, 75, off, rev).write_fastq_bgzf(p, 0, n_reads, gz_level=1)
+    bpaths.append(p)
+btables = {}
+for gpus in sorted({1, torch.cuda.device_count()}):
+    out = os.path.join(tmp, f"bout{gpus}.tsv")
+    p = subprocess.run([exe, "-l", lib, "-i", *bpaths, "-g", g2s, "-o", out, "-t", str(max(gpus, 2)), "--gpus", str(gpus),
+                        "--timing"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert want in p.stderr, p.stderr
+    t = json.loads([l for l in p.stderr.splitlines() if l.startswith("{")][-1])
+    btables[gpus] = open(out, "rb").read()
+    print(f"BGZF samples, gpus={gpus}: count_s {t['count_s']:.3f}  {t['reads'] / t['count_s'] / 1e6:.1f} M reads/s  "
+          f"device_ingest_samples {t['device_ingest_samples']}  blocks {t['device_blocks']}", flush=True)
+assert len(set(btables.values())) == 1
+assert list(btables.values())[0].replace(b"\tb", b"\ts") == list(tables.values())[0], "BGZF and gzip tables differ"
+print("BGZF samples: tables identical on 1 and", torch.cuda.device_count(), "GPUs and equal to the gzip samples' table")
