@@ -12,7 +12,7 @@ from sgcount_b200 import synth
 
 N = int(os.environ.get("TUNE_READS", 50_000_000))
 d = torch.empty(N * 76 + 512, dtype=torch.uint8, device="cuda")
-for k in (16, 20, 24, 28, 30):
+for k in [int(x) for x in os.environ.get('WIDE_KS', '16,20,24,28,30').split(',')]:
     arr = synth.make_library(0xB2000002 + k, 77441, k)
     library = sg.Library([arr[i].tobytes() for i in range(len(arr))], [b"g%d" % i for i in range(len(arr))])
     permuter = sg.Permuter.new(library)
