@@ -226,7 +226,7 @@ def fastq_leg(lib_arr, n_reads: int, with_oracle: bool, gpus: int = 1):
                                                                   "unit": "reads/s", "count_s": best_h[0]["count_s"]}
         if gpus > 1:
             out_n = os.path.join(tmp, "counts_n.tsv")
-            best, err = run_cli(exe, lib_path, [fq], ["-a", str(OFFSET), "--gpus", str(gpus)], out_n)
+            best, err = run_cli(exe, lib_path, [fq], ["-a", str(OFFSET), "--gpus", str(gpus), "--read-shards", str(gpus)], out_n)
             if err:
                 res["read_sharded"] = {"unavailable": err}
             else:
@@ -235,8 +235,10 @@ def fastq_leg(lib_arr, n_reads: int, with_oracle: bool, gpus: int = 1):
                 res["read_sharded"] = {"gpus": gpus, "value": tn["reads"] / tn["count_s"], "unit": "reads/s",
                                        "count_s": tn["count_s"], "read_shards_per_sample": tn.get("read_shards_per_sample"),
                                        "same_table_as_one_gpu": same,
-                                       "what": "the same ONE sample with --gpus N: batches dealt round the devices, "
-                                               "sgc_reduce_counts (NCCL) sums the shard vectors"}
+                                       "what": "the same ONE sample with --gpus N --read-shards N: batches dealt round the "
+                                               "devices, sgc_reduce_counts (NCCL) sums the shard vectors.  A correctness leg: "
+                                               "a 16 M-read gzip file is host-bound on one GPU already, and loading NCCL + "
+                                               "ncclCommInitAll (seconds) is inside count_s"}
                 assert same, "CLI --gpus N table differs from --gpus 1"
         if with_oracle:
             from oracle import oracle as orc
@@ -423,11 +425,16 @@ def plan_units(cfg, world):
     """(sample position, first read, n reads, rank) of every shard: whole samples are dealt round
     the ranks; a sample with several shards has its shards dealt round the ranks."""
     units = []
-    per = cfg["reads_per_sample"] // cfg["shards_per_sample"]
-    assert per * cfg["shards_per_sample"] == cfg["reads_per_sample"] and per % 32 == 0  # whole tiles, 16-byte aligned
+    n_shards = cfg["shards_per_sample"]
+    # more ranks than shards (config 3's four samples on eight GPUs): cut every sample further, so
+    # that no rank idles — read shards of a sample are summed like config 5's
+    while len(cfg["samples"]) * n_shards < world and cfg["reads_per_sample"] % (2 * n_shards * 32) == 0:
+        n_shards *= 2
+    per = cfg["reads_per_sample"] // n_shards
+    assert per * n_shards == cfg["reads_per_sample"] and per % 32 == 0  # whole tiles, 16-byte aligned
     for si in range(len(cfg["samples"])):
-        for sh in range(cfg["shards_per_sample"]):
-            slot = si * cfg["shards_per_sample"] + sh
+        for sh in range(n_shards):
+            slot = si * n_shards + sh
             units.append((si, sh * per, per, slot % world))
     return units
 

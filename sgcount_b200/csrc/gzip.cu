@@ -64,7 +64,7 @@ constexpr size_t kInflateSmem = (DeviceTables::kCounts + 32) * kInflateThreads *
 // what the kernels of a stream hand from wave to wave, and back to the host
 struct StreamState {
   unsigned int bad_block;       // first block (index within its wave) that did not decode, or 0xFFFFFFFF
-  int bad_status;               // its inflate::Status (or 100 + : size / length disagreement)
+  int bad_status;               // its inflate::Status; 100: size / length disagreement; 101: CRC-32 mismatch
   unsigned int format_error;    // 1 irregular read length, 2 not FASTQ framing, 4 a record longer than the headroom
   unsigned int tail;            // bytes carried in front of the next wave
   unsigned int next_tail;
@@ -94,6 +94,40 @@ __global__ void __launch_bounds__(kInflateThreads) inflate_blocks_kernel(const u
   if (rc != inflate::kOk) {
     const unsigned int prev = atomicMin(&st->bad_block, m);
     if (m < prev) st->bad_status = rc;  // (benign race between two bad blocks: either status will do)
+  }
+}
+
+// CRC-32 of every block's text against the trailer of its member (RFC 1952; flate2 checks it for
+// the reference): one warp per block, 32 pieces joined as inflate_core.h describes.
+constexpr int kCrcWarps = 8;
+__global__ void __launch_bounds__(kCrcWarps * 32) crc_blocks_kernel(const uint8_t* __restrict__ gz,
+                                                                   const uint64_t* __restrict__ begin,
+                                                                   const uint64_t* __restrict__ out_off, uint32_t n,
+                                                                   const uint8_t* __restrict__ text, StreamState* st) {
+  __shared__ uint32_t table[256];
+  table[threadIdx.x] = inflate::crc_table_entry(threadIdx.x);
+  __syncthreads();
+  const uint32_t m = blockIdx.x * kCrcWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= n) return;
+  const uint8_t* d = text + out_off[m];
+  const size_t len = (size_t)(out_off[m + 1] - out_off[m]);
+  const size_t c = inflate::crc_piece_len(len), first = len - 31 * c;
+  const size_t at = lane == 0 ? 0 : first + (lane - 1) * c;
+  uint32_t crc = inflate::crc_bytes(d + at, lane == 0 ? first : c, [&](uint32_t i) { return table[i]; });
+  uint32_t p = inflate::crc_x8n(c);  // the same in every lane
+#pragma unroll
+  for (int s = 1; s < 32; s *= 2) {
+    const uint32_t other = __shfl_down_sync(0xffffffffu, crc, s);
+    if ((lane & (2 * s - 1)) == 0) crc = inflate::crc_multmodp(p, crc) ^ other;
+    p = inflate::crc_multmodp(p, p);
+  }
+  if (lane == 0) {
+    const uint8_t* t = gz + (begin[m + 1] - begin[0]) - 8;
+    const uint32_t stored = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+    if (crc != stored) {
+      const unsigned int prev = atomicMin(&st->bad_block, m);
+      if (m < prev) st->bad_status = 101;
+    }
   }
 }
 
@@ -250,8 +284,12 @@ int stream_error(sgc_fastq_stream* s, const StreamState& st, uint64_t first_bloc
   s->failed = true;
   char buf[200];
   if (st.bad_block != 0xFFFFFFFFu) {
-    snprintf(buf, sizeof buf, "gzip block %llu did not inflate on the device (status %d)",
-             (unsigned long long)(first_block + st.bad_block), st.bad_status);
+    if (st.bad_status == 101)
+      snprintf(buf, sizeof buf, "gzip block %llu: CRC-32 of the inflated bytes differs from the member's trailer",
+               (unsigned long long)(first_block + st.bad_block));
+    else
+      snprintf(buf, sizeof buf, "gzip block %llu did not inflate on the device (status %d)",
+               (unsigned long long)(first_block + st.bad_block), st.bad_status);
     return set_error(SGC_ERR_GZIP, buf);
   }
   snprintf(buf, sizeof buf, "not fixed-length 4-line FASTQ (%s)",
@@ -392,6 +430,8 @@ int sgc_fastq_stream_submit(sgc_fastq_stream* s, const uint8_t* gz, const uint64
   SGC_CUDA_TRY(cudaMemcpyAsync(s->d_outoff, s->h_outoff.data(), ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, s->stream));
   inflate_blocks_kernel<<<(n_blocks + kInflateThreads - 1) / kInflateThreads, kInflateThreads, kInflateSmem, s->stream>>>(
       s->d_gz, s->d_begin, s->d_outoff, n_blocks, s->d_text, s->d_state);
+  crc_blocks_kernel<<<(n_blocks + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, s->stream>>>(s->d_gz, s->d_begin, s->d_outoff,
+                                                                                           n_blocks, s->d_text, s->d_state);
   SGC_CUDA_TRY(cudaGetLastError());
   rc = frame_and_count(s, n_text, s->blocks_total);
   if (rc) return rc;

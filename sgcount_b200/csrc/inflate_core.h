@@ -599,3 +599,60 @@ SGC_HD int gunzip_member(const uint8_t* in, size_t in_len, uint8_t* out, size_t 
 
 }  // namespace inflate
 }  // namespace sgc
+
+// ---- CRC-32 (RFC 1952 8.) of a member's output, computed by 32 cooperating lanes -------------------
+// Lane l takes one contiguous piece of the bytes, runs the table-driven CRC over it, and the
+// pieces are joined with crc(A || B) = x^(8 |B|) * crc(A) + crc(B) (polynomial arithmetic modulo
+// the CRC polynomial; the identity zlib's crc32_combine uses).  All pieces but the first have the
+// same length, so every level of the join tree multiplies by one power of x^(8 c).
+namespace sgc {
+namespace inflate {
+
+constexpr uint32_t kCrcPoly = 0xEDB88320u;  // reflected
+
+// entry i of the byte table
+SGC_HD uint32_t crc_table_entry(uint32_t i) {
+  uint32_t c = i;
+  for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
+  return c;
+}
+
+// a(x) * b(x) mod p(x), reflected representation (bit 31 = x^0)
+SGC_HD uint32_t crc_multmodp(uint32_t a, uint32_t b) {
+  uint32_t m = 1u << 31, p = 0;
+  for (;;) {
+    if (a & m) {
+      p ^= b;
+      if ((a & (m - 1)) == 0) break;
+    }
+    m >>= 1;
+    b = (b & 1) ? (b >> 1) ^ kCrcPoly : b >> 1;
+  }
+  return p;
+}
+
+// x^(8 n) mod p(x)
+SGC_HD uint32_t crc_x8n(uint64_t n) {
+  uint32_t p = 1u << 31;          // x^0
+  uint32_t sq = 1u << (31 - 8);   // x^8
+  while (n) {
+    if (n & 1) p = crc_multmodp(sq, p);
+    sq = crc_multmodp(sq, sq);
+    n >>= 1;
+  }
+  return p;
+}
+
+// standard CRC-32 of bytes [0, n) given a 256-entry table accessor
+template <typename Table>
+SGC_HD uint32_t crc_bytes(const uint8_t* p, size_t n, Table table) {
+  uint32_t c = 0xFFFFFFFFu;
+  for (size_t i = 0; i < n; ++i) c = table((c ^ p[i]) & 0xFFu) ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+
+// how n bytes are cut into 32 pieces: pieces 1..31 have `c` bytes, piece 0 the rest (possibly none)
+SGC_HD size_t crc_piece_len(size_t n) { return n / 32; }
+
+}  // namespace inflate
+}  // namespace sgc

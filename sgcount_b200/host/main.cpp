@@ -89,7 +89,7 @@ const char* kUsage =
     "  -q, --quiet                            Does not show progress\n"
     "  -z, --include-zero                     Include zero count sgRNAs in output table\n"
     "      --gpus <N>                         Spread the samples (and, with fewer samples than devices, read shards of each sample) over N devices [default: 1]\n"
-    "      --read-shards <N>                  Cut every sample into N read shards, dealt round the devices and summed with an NCCL reduce [default: gpus / samples]\n"
+    "      --read-shards <N>                  Cut every sample into N read shards, dealt round the devices and summed with an NCCL reduce [default: gpus / samples when there are fewer samples than devices and an input of 1 GiB or more, else 1]\n"
     "      --device <D>                       First device to use [default: 0]\n"
     "      --ingest-threads <N>               Threads inflating the gzip members of one sample [default: cores / samples in flight]\n"
     "      --rc-keep-n                        Reverse complement keeps N (default: the fxread bit trick, N -> J)\n"
@@ -647,8 +647,14 @@ int main(int argc, char** argv) {
     const int gpus = std::min(args.gpus, ndev - args.device);
     // fewer samples than devices: every sample is cut into read shards over `per_sample` devices,
     // summed with NCCL at the end; its communicators are created on a side thread meanwhile
-    const size_t per_sample =
-        args.read_shards ? args.read_shards : (n_samples < (size_t)gpus ? (size_t)gpus / n_samples : 1);
+    // (only worth it for big inputs: the shards are summed with NCCL, whose start-up takes seconds)
+    uint64_t largest_input = 0;
+    for (const auto& p : args.input_paths) {
+      struct stat st;
+      if (stat(p.c_str(), &st) == 0) largest_input = std::max<uint64_t>(largest_input, (uint64_t)st.st_size);
+    }
+    const size_t per_sample = args.read_shards ? args.read_shards
+                                               : (n_samples < (size_t)gpus && largest_input >= (1ull << 30) ? (size_t)gpus / n_samples : 1);
     std::thread nccl_warmup;
     struct JoinGuard {
       std::thread& t;
@@ -673,9 +679,19 @@ int main(int argc, char** argv) {
         for (auto* x : l) sgc_library_destroy(x);
       }
     } lib_guard{libs};
-    for (int d = 0; d < gpus; ++d)
-      check(sgc_library_create(args.device + d, reinterpret_cast<const uint8_t*>(hlib.seqs.data()), hlib.n, hlib.k,
-                               args.exact ? 0 : 1, &libs[d]));
+    {  // side by side: most of the time is the creation of each device's CUDA context
+      std::vector<std::thread> builders;
+      std::vector<std::string> errors(gpus);
+      for (int d = 0; d < gpus; ++d)
+        builders.emplace_back([&, d] {
+          if (sgc_library_create(args.device + d, reinterpret_cast<const uint8_t*>(hlib.seqs.data()), hlib.n, hlib.k,
+                                 args.exact ? 0 : 1, &libs[d]) != SGC_OK)
+            errors[d] = sgc_last_error();
+        });
+      for (auto& t : builders) t.join();
+      for (const auto& e : errors)
+        if (!e.empty()) fail("%s", e.c_str());
+    }
 
     t_tables = seconds_since_start();
     std::vector<OffsetValue> offsets(n_samples);

@@ -216,8 +216,8 @@ def test_one_sample_over_every_device_with_nccl(tmp_path):
     one = run("-l", lib_path, "-i", fq, "-o", str(tmp_path / "one.tsv"), check=True)
     # whole lines: 68 MB per device, so every device gets at least one 64 MB batch (as span
     # records, the default, the whole sample is one batch)
-    many = run("-l", lib_path, "-i", fq, "-o", str(tmp_path / "many.tsv"), "--gpus", str(n_dev), "--timing",
-               "--whole-lines", check=True)
+    many = run("-l", lib_path, "-i", fq, "-o", str(tmp_path / "many.tsv"), "--gpus", str(n_dev), "--read-shards", str(n_dev),
+               "--timing", "--whole-lines", check=True)
     assert open(tmp_path / "one.tsv").read() == open(tmp_path / "many.tsv").read()
     assert '"read_shards_per_sample": %d' % n_dev in many.stderr
     assert many.stderr.count("Calculated Offsets: [Forward(3)]") == 1

@@ -57,7 +57,7 @@ single = {}
 for gpus in sorted({1, torch.cuda.device_count()}):
     for extra in ([], ["--whole-lines"]):
         out = os.path.join(tmp, f"big{gpus}{len(extra)}.tsv")
-        p = subprocess.run([exe, "-l", lib, "-i", big, "-o", out, "--gpus", str(gpus), "--timing", *extra],
+        p = subprocess.run([exe, "-l", lib, "-i", big, "-o", out, "--gpus", str(gpus), "--read-shards", str(gpus), "--timing", *extra],
                            capture_output=True, text=True)
         assert p.returncode == 0, p.stderr
         assert p.stderr.count("Calculated Offsets: [Forward(9)]") == 1, p.stderr
