@@ -123,6 +123,16 @@ def test_irregular_input_is_reported_not_miscounted():
     with pytest.raises(sg.SgcError) as e:
         device_counts(library, permuter, bytes(blob), 75, 20, off)
     assert e.value.code in (_cabi.ERR_GZIP, _cabi.ERR_FASTQ_FORMAT)
+    # a damaged byte that leaves the DEFLATE structure intact (a stored block): only the CRC-32 sees it
+    stored = bytearray(bgzf(fastq_text(seqs), level=0))
+    begin, _ = sg.bgzf_blocks(bytes(stored))
+    at = int(begin[1]) + 18 + 5 + 1000  # inside the second block's literal bytes, in a quality line or a header
+    stored[at] ^= 0x01
+    with pytest.raises(sg.SgcError) as e:
+        device_counts(library, permuter, bytes(stored), 75, 20, off)
+    assert e.value.code in (_cabi.ERR_GZIP, _cabi.ERR_FASTQ_FORMAT)
+    if e.value.code == _cabi.ERR_GZIP:
+        assert "CRC-32" in str(e.value)
     # and the plain case still works afterwards
     n, got = device_counts(library, permuter, bgzf(fastq_text(seqs)), 75, 20, off)
     want = host_counts(library, permuter, seqs, off)
