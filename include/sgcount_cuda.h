@@ -219,10 +219,15 @@ int sgc_reduce_prepare(const int* devices, int n_devices);
  * newline scan, the guide-window span of every sequence line is cut out and counted, and the only
  * bytes that cross PCIe are the compressed ones.
  *
- * counter: created with the SPAN offset of sgc_span_geometry for reads of read_len bytes; the
- * stream counts into it (same device, same CUDA stream).  Only fixed-length 4-line FASTQ is framed
- * here; anything else fails with SGC_ERR_FASTQ_FORMAT (a corrupt block: SGC_ERR_GZIP) and the
- * caller resets the counter and counts the sample through sgc_counter_submit instead.
+ * Two modes.  read_len > 0: every read has read_len bytes; `counter` was created with the SPAN
+ * offset of sgc_span_geometry and the stream cuts the span [span_start, span_start + span_len) out
+ * of every sequence line (the streaming count kernel).  read_len == 0 (span_* ignored): reads of
+ * any length; `counter` is an ordinary counter (the sample's own Offset) and the sequence lines are
+ * counted where they lie in the inflated text (the line kernel); a wave must then inflate to less
+ * than 4 GiB.  The stream counts into `counter` (same device, same CUDA stream).  Only 4-line
+ * FASTQ is framed here; anything else — and in the first mode a read of another length — fails
+ * with SGC_ERR_FASTQ_FORMAT (a corrupt block or a CRC-32 mismatch: SGC_ERR_GZIP) and the caller
+ * starts over with the other mode or with sgc_counter_submit.
  * submit: n_blocks consecutive blocks, in file order, continuing where the previous call stopped;
  * gz + block_begin[i] .. gz + block_begin[i + 1] is block i (host memory), block_isize[i] its
  * ISIZE field.  One call is one wave: it should carry thousands of blocks (one device thread

@@ -386,8 +386,9 @@ def bgzf_blocks(blob: bytes):
 
 
 class FastqStream:
-    """sgc_fastq_stream: BGZF blocks of a fixed-length FASTQ inflated, framed and counted on the
-    device.  `counter` must have been created with the span Offset of span_geometry()."""
+    """sgc_fastq_stream: BGZF blocks of a FASTQ inflated, framed and counted on the device.
+    read_len > 0: fixed-length reads, `counter` created with the span Offset of span_geometry();
+    read_len == 0: reads of any length, `counter` an ordinary counter."""
 
     def __init__(self, counter: Counter, read_len: int, span_start: int, span_len: int):
         self._counter = counter

@@ -83,6 +83,8 @@ struct CountParams {
   const uint8_t* lines;
   const uint8_t* lines_end;  // lines + n_bytes: no load starts at or past it
   const uint32_t* line_off;  // NULL => fixed stride
+  const uint32_t* line_end;  // with line_off: read r is lines[line_off[r] .. line_end[r]) — lines scattered in a
+                             // larger text (the device ingest's variable-length mode); NULL => line_off[r + 1] - 1
   uint64_t n_reads;
   uint64_t first_read;       // index of the first read this launch handles
   uint32_t stride, read_len;
@@ -442,7 +444,10 @@ __global__ void __launch_bounds__(kLineWarps * 32) count_lines_kernel(CountParam
       const uint64_t r = p.first_read + i;
       uint64_t start;
       int n;
-      if (p.line_off) {
+      if (p.line_end) {
+        start = p.line_off[r];
+        n = (int)(p.line_end[r] - p.line_off[r]);
+      } else if (p.line_off) {
         const uint32_t a = p.line_off[r], b = p.line_off[r + 1];
         start = a - p.off_base;
         n = (int)(b - a) - 1;
@@ -998,6 +1003,7 @@ int launch_count(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const
   CountParams p = make_params(c, d_lines, d_off, stride, read_len, d_assign);
   p.off_base = off_base;
   p.lines_end = d_lines + n_bytes;
+  p.line_end = c->gather_end;  // set only by count_gathered_lines
   uint64_t done = first;
   const uint64_t launches_before = c->last.launches_total;
   c->last = sgc_launch_info{};
@@ -1151,6 +1157,22 @@ int count_batch(sgc_counter* c, const uint8_t* d_lines, uint64_t n_bytes, const 
   }
   return launch_count(c, d_lines, n_bytes, d_off, off_base, stride, read_len, counted, n_reads, d_assign, stream);
 }
+
+}  // namespace
+
+// Reads scattered in a device-resident text: read r is d_text[d_start[r] .. d_end[r]) (gzip.cu: the
+// sequence lines of FASTQ records in place, no packing).  Counted by the line kernel.
+int sgc::count_gathered_lines(sgc_counter* c, const uint8_t* d_text, uint64_t n_bytes, const uint32_t* d_start,
+                              const uint32_t* d_end, uint64_t n_reads) {
+  if (n_reads == 0) return SGC_OK;
+  DeviceGuard guard(c->device);
+  c->gather_end = d_end;
+  const int rc = count_batch(c, d_text, n_bytes, d_start, 0, 0, 0, n_reads, nullptr, c->stream);
+  c->gather_end = nullptr;
+  return rc;
+}
+
+namespace {
 
 int check_batch(const sgc_counter* c, const uint8_t* lines, uint64_t n_bytes, const uint32_t* line_off,
                 uint32_t stride, uint32_t read_len, uint64_t n_reads) {

@@ -180,7 +180,8 @@ __global__ void wave_totals_kernel(const uint32_t* __restrict__ first_line, uint
 __global__ void __launch_bounds__(kChunkThreads) span_extract_kernel(const uint8_t* __restrict__ text, uint64_t n_text,
                                                                     StreamState* st, const uint32_t* __restrict__ first_line,
                                                                     uint32_t read_len, uint32_t span_start, uint32_t span_len,
-                                                                    uint32_t span_stride, uint8_t* __restrict__ spans) {
+                                                                    uint32_t span_stride, uint8_t* __restrict__ spans,
+                                                                    uint32_t* __restrict__ seq_start, uint32_t* __restrict__ seq_end) {
   uint64_t lo, hi;
   region_of(st, n_text, &lo, &hi);
   const uint64_t lines = st->lines, records = st->records;
@@ -206,7 +207,17 @@ __global__ void __launch_bounds__(kChunkThreads) span_extract_kernel(const uint8
     mask &= mask - 1;
     const uint64_t p = at + j;  // a newline: the end of line `line` of the region
     const uint64_t r = line >> 2;
-    if ((line & 3) == 0 && r < records) {
+    if (read_len == 0 && r < records) {
+      // reads of any length: the sequence line stays where it is, [seq_start[r], seq_end[r]) of the text
+      if ((line & 3) == 0) {
+        seq_start[r] = (uint32_t)(p + 1);
+      } else if ((line & 3) == 1) {
+        seq_end[r] = (uint32_t)p;
+        if (text[p + 1] != '+') atomicOr(&st->format_error, 2u);  // (p + 1 < hi: the record is complete)
+      } else if ((line & 3) == 3 && p + 1 < hi && text[p + 1] != '@') {
+        atomicOr(&st->format_error, 2u);
+      }
+    } else if ((line & 3) == 0 && r < records) {
       // the header of record r ends here; its sequence is the next read_len bytes, then "\n+"
       const uint64_t s = p + 1;
       if (s + read_len + 1 >= hi || text[s + read_len] != '\n' || text[s + read_len + 1] != '+') {
@@ -215,7 +226,8 @@ __global__ void __launch_bounds__(kChunkThreads) span_extract_kernel(const uint8
         uint8_t* dst = spans + r * span_stride;
         for (uint32_t b = 0; b < span_len; ++b) dst[b] = text[s + span_start + b];
       }
-    } else if ((line & 3) == 3 && r + 1 == records) {
+    }
+    if ((line & 3) == 3 && r + 1 == records) {
       st->next_tail = (unsigned int)(hi - (p + 1));  // what follows the last complete record
     }
     ++line;
@@ -269,6 +281,8 @@ struct sgc_fastq_stream {
   cudaStream_t stream = nullptr;
   StreamState* d_state = nullptr;
   uint8_t *d_gz = nullptr, *d_text = nullptr, *d_spans = nullptr, *d_tail = nullptr;
+  uint32_t *d_seq_start = nullptr, *d_seq_end = nullptr;  // variable-length mode
+  size_t seq_cap_a = 0, seq_cap_b = 0;
   uint64_t *d_begin = nullptr, *d_outoff = nullptr;
   uint32_t *d_counts = nullptr, *d_first = nullptr, *d_sums = nullptr;
   size_t gz_cap = 0, text_cap = 0, spans_cap = 0, begin_cap = 0, outoff_cap = 0, counts_cap = 0, first_cap = 0, sums_cap = 0;
@@ -312,12 +326,22 @@ int frame_and_count(sgc_fastq_stream* s, uint64_t n_text, uint64_t first_block) 
   rc = exclusive_scan_u32(s->d_counts, n_chunks + 1, s->d_first, s->d_sums, s->stream);
   if (rc) return rc;
   wave_totals_kernel<<<1, 1, 0, s->stream>>>(s->d_first, n_chunks, s->d_state);
-  // at most one record per (1 + read_len + 3) bytes of text
-  const size_t max_records = ((size_t)kHeadroom + n_text) / (s->read_len + 4) + 1;
-  rc = grow(&s->d_spans, &s->spans_cap, max_records * s->span_stride + 256);
+  // how many records the region holds decides the size of the span / offset buffers
+  StreamState pre;
+  SGC_CUDA_TRY(cudaMemcpyAsync(&pre, s->d_state, sizeof pre, cudaMemcpyDeviceToHost, s->stream));
+  SGC_CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (pre.bad_block != 0xFFFFFFFFu) return stream_error(s, pre, first_block);
+  const size_t max_records = (size_t)pre.records + 1;
+  if (s->read_len) {
+    rc = grow(&s->d_spans, &s->spans_cap, max_records * s->span_stride + 256);
+  } else {
+    rc = grow(&s->d_seq_start, &s->seq_cap_a, max_records);
+    if (rc == SGC_OK) rc = grow(&s->d_seq_end, &s->seq_cap_b, max_records);
+  }
   if (rc) return rc;
   span_extract_kernel<<<n_chunks, kChunkThreads, 0, s->stream>>>(s->d_text, n_text, s->d_state, s->d_first, s->read_len,
-                                                                 s->span_start, s->span_len, s->span_stride, s->d_spans);
+                                                                 s->span_start, s->span_len, s->span_stride, s->d_spans,
+                                                                 s->d_seq_start, s->d_seq_end);
   tail_save_kernel<<<8, 256, 0, s->stream>>>(s->d_text, n_text, s->d_state, s->d_tail);
   wave_commit_kernel<<<1, 1, 0, s->stream>>>(s->d_state);
   SGC_CUDA_TRY(cudaGetLastError());
@@ -326,8 +350,11 @@ int frame_and_count(sgc_fastq_stream* s, uint64_t n_text, uint64_t first_block) 
   SGC_CUDA_TRY(cudaStreamSynchronize(s->stream));
   if (st.bad_block != 0xFFFFFFFFu || st.format_error) return stream_error(s, st, first_block);
   if (st.records) {
-    rc = sgc_counter_submit_device(s->counter, s->d_spans, st.records * s->span_stride + 64, nullptr, s->span_stride,
-                                   s->span_len, st.records, nullptr);
+    if (s->read_len)
+      rc = sgc_counter_submit_device(s->counter, s->d_spans, st.records * s->span_stride + 64, nullptr, s->span_stride,
+                                     s->span_len, st.records, nullptr);
+    else  // the sequence lines in place, through the line kernel
+      rc = count_gathered_lines(s->counter, s->d_text, (uint64_t)kHeadroom + n_text, s->d_seq_start, s->d_seq_end, st.records);
     if (rc) return rc;
   }
   s->records_total = st.records_total;
@@ -350,6 +377,8 @@ void sgc::fastq_stream_release(sgc_fastq_stream* s) {
   cudaFree(s->d_text);
   cudaFree(s->d_spans);
   cudaFree(s->d_tail);
+  cudaFree(s->d_seq_start);
+  cudaFree(s->d_seq_end);
   cudaFree(s->d_begin);
   cudaFree(s->d_outoff);
   cudaFree(s->d_counts);
@@ -357,6 +386,7 @@ void sgc::fastq_stream_release(sgc_fastq_stream* s) {
   cudaFree(s->d_sums);
   s->d_state = nullptr;
   s->d_gz = s->d_text = s->d_spans = s->d_tail = nullptr;
+  s->d_seq_start = s->d_seq_end = nullptr;
   s->d_begin = s->d_outoff = nullptr;
   s->d_counts = s->d_first = s->d_sums = nullptr;
 }
@@ -366,7 +396,7 @@ extern "C" {
 int sgc_fastq_stream_create(sgc_counter* counter, uint32_t read_len, uint32_t span_start, uint32_t span_len,
                             sgc_fastq_stream** out) {
   if (!counter || !out) return set_error(SGC_ERR_INVALID_ARG, "NULL argument");
-  if (span_len == 0 || (uint64_t)span_start + span_len > read_len || read_len + 4u > kHeadroom)
+  if (read_len != 0 && (span_len == 0 || (uint64_t)span_start + span_len > read_len || read_len + 4u > kHeadroom))
     return set_error(SGC_ERR_INVALID_ARG, "the span does not fit the read");
   DeviceGuard guard(counter->lib->device);
   sgc_fastq_stream* s = new sgc_fastq_stream();
@@ -419,6 +449,8 @@ int sgc_fastq_stream_submit(sgc_fastq_stream* s, const uint8_t* gz, const uint64
   }
   s->h_outoff[n_blocks] = kHeadroom + n_text;
   if (n_text >= (64ull << 30)) return set_error(SGC_ERR_BATCH_TOO_LARGE, "a wave of blocks must inflate to less than 64 GiB");
+  if (s->read_len == 0 && n_text >= (1ull << 32) - 2 * kHeadroom)
+    return set_error(SGC_ERR_BATCH_TOO_LARGE, "in variable-length mode a wave of blocks must inflate to less than 4 GiB");
   const uint64_t gz_bytes = block_begin[n_blocks] - block_begin[0];
   int rc = grow(&s->d_gz, &s->gz_cap, (size_t)gz_bytes + 64);  // the decoder prefetches up to 47 bytes past a block
   if (rc == SGC_OK) rc = grow(&s->d_text, &s->text_cap, (size_t)kHeadroom + n_text + 64);

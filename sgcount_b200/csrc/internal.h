@@ -81,6 +81,7 @@ struct sgc_counter {
   int32_t hot[4] = {-2, -2, -2, -2};
   bool auto_skew = true, skew_planned = false;
   void* d_top = nullptr;  // the plan's read-back buffer
+  const uint32_t* gather_end = nullptr;  // count_gathered_lines: per-read end offsets (transient)
   // host-batch staging (sgc_counter_submit)
   cudaStream_t copy_stream = nullptr;
   uint8_t* d_stage[2] = {nullptr, nullptr};
@@ -96,6 +97,9 @@ struct sgc_counter {
 };
 
 namespace sgc {
+// count.cu: reads scattered in a device-resident text, read r = d_text[d_start[r] .. d_end[r])
+int count_gathered_lines(sgc_counter* c, const uint8_t* d_text, uint64_t n_bytes, const uint32_t* d_start,
+                         const uint32_t* d_end, uint64_t n_reads);
 // gzip.cu: frees the device side of a stream whose counter is going away (the handle stays valid
 // for sgc_fastq_stream_destroy)
 void fastq_stream_release(struct sgc_fastq_stream* s);

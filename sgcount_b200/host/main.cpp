@@ -413,10 +413,14 @@ bool bgzf_index(const uint8_t* d, size_t n, std::vector<uint64_t>& begin, std::v
 // One sample through the device ingest.  Returns false (after resetting nothing: the caller
 // starts a fresh counter) when the file is not BGZF or the device reports input it does not take —
 // a read of another length, FASTA, a damaged block — so that the host path counts the sample.
+// `variable`: reads of any length (the sequence lines are counted where they lie in the inflated
+// text); otherwise every read has read_len bytes and only its guide-window span is kept.
 bool count_sample_on_device(const sgc_library* lib, uint32_t n_guides, uint32_t k, const std::string& path, OffsetValue offset,
-                            uint32_t read_len, bool recursion, int rc_mode, SampleResult& r, std::string& why_not) {
-  uint32_t span_start = 0, span_len = 0, span_offset = 0;
-  if (sgc_span_geometry(k, read_len, offset.reverse, offset.index, recursion, &span_start, &span_len, &span_offset) != SGC_OK) {
+                            uint32_t read_len, bool variable, bool recursion, int rc_mode, SampleResult& r,
+                            std::string& why_not) {
+  uint32_t span_start = 0, span_len = 0, span_offset = offset.index;
+  if (!variable && sgc_span_geometry(k, read_len, offset.reverse, offset.index, recursion, &span_start, &span_len,
+                                     &span_offset) != SGC_OK) {
     why_not = "the guide window does not fit the reads";
     return false;
   }
@@ -443,7 +447,7 @@ bool count_sample_on_device(const sgc_library* lib, uint32_t n_guides, uint32_t 
     }
   } guard{c, stream};
   check(sgc_counter_create(lib, offset.reverse, span_offset, recursion, rc_mode, nullptr, nullptr, &c));
-  check(sgc_fastq_stream_create(c, read_len, span_start, span_len, &stream));
+  check(sgc_fastq_stream_create(c, variable ? 0 : read_len, span_start, span_len, &stream));
   // Waves of blocks.  One device thread inflates each block and a wave takes about as long with
   // 300 000 blocks as with 10 000, so a wave is as large as 12 GiB of text allows.  The compressed
   // bytes go to the device straight from the mapping (page cache -> the driver's staging buffers).
@@ -453,7 +457,9 @@ bool count_sample_on_device(const sgc_library* lib, uint32_t n_guides, uint32_t 
   for (size_t a = 0; a < n_blocks && status == SGC_OK;) {
     size_t b = a;
     uint64_t text = 0;
-    while (b < n_blocks && b - a < 262144 && text + isize[b] < (12ull << 30)) text += isize[b++];
+    // (variable-length mode addresses the text with 32-bit offsets: 3 GiB per wave)
+    const uint64_t wave_text = variable ? (3ull << 30) : (12ull << 30);
+    while (b < n_blocks && b - a < 262144 && text + isize[b] < wave_text) text += isize[b++];
     if (b == a) b = a + 1;
     status = sgc_fastq_stream_submit(stream, file.data, begin.data() + a, isize.data() + a, (uint32_t)(b - a));
     if (status != SGC_OK) error = sgc_last_error();
@@ -471,7 +477,8 @@ bool count_sample_on_device(const sgc_library* lib, uint32_t n_guides, uint32_t 
   if (status != SGC_OK) fail("%s", error.c_str());
   r.counts.resize(n_guides);
   check(sgc_counter_finish(c, r.counts.data(), &r.total, &r.matched));
-  r.span_reads = n_records;
+  r.span_reads = variable ? 0 : n_records;
+  r.line_reads = variable ? n_records : 0;
   r.device_ingest = true;
   r.device_blocks = n_blocks;
   r.submit_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
@@ -713,9 +720,10 @@ int main(int argc, char** argv) {
     std::mutex err_mu;
     std::string first_error;
     std::vector<uint32_t> first_len(n_samples);
-    std::vector<char> head_uniform(n_samples, 0);  // 4-line FASTQ whose head reads all have one length
+    std::vector<char> head_uniform(n_samples, 0), head_fastq(n_samples, 0);  // 4-line FASTQ? head reads of one length?
     for (size_t i = 0; i < n_samples; ++i) {
       first_len[i] = (uint32_t)heads[i].first_len;
+      head_fastq[i] = heads[i].fastq;
       head_uniform[i] = heads[i].fastq && heads[i].uniform;
     }
     heads.clear();
@@ -733,12 +741,21 @@ int main(int argc, char** argv) {
           // anything else, or anything the device declines, through the host's inflate threads
           bool on_device = false;
           std::string why_not = "switched off";
-          if (!args.host_inflate && !args.whole_lines && head_uniform[s] && per_sample == 1 &&
-              args.input_paths[s].size() > 3 && args.input_paths[s].compare(args.input_paths[s].size() - 3, 3, ".gz") == 0)
+          if (!args.host_inflate && head_fastq[s] && per_sample == 1 && args.input_paths[s].size() > 3 &&
+              args.input_paths[s].compare(args.input_paths[s].size() - 3, 3, ".gz") == 0) {
+            // fixed-length reads as span records; reads of several lengths (seen in the head, or
+            // reported by the device deeper in the file) with their sequence lines in place
+            bool variable = !head_uniform[s] || args.whole_lines;
             on_device = count_sample_on_device(sample_libs[0], hlib.n, hlib.k, args.input_paths[s], offsets[s], first_len[s],
-                                               !args.no_position_recursion, args.rc_mode, results[s], why_not);
-          else if (!head_uniform[s])
-            why_not = "reads of several lengths (or FASTA)";
+                                               variable, !args.no_position_recursion, args.rc_mode, results[s], why_not);
+            if (!on_device && !variable && why_not.find("FASTQ") != std::string::npos) {
+              results[s] = SampleResult();
+              on_device = count_sample_on_device(sample_libs[0], hlib.n, hlib.k, args.input_paths[s], offsets[s], first_len[s],
+                                                 true, !args.no_position_recursion, args.rc_mode, results[s], why_not);
+            }
+          } else if (!head_fastq[s]) {
+            why_not = "not FASTQ";
+          }
           if (!on_device) {
             results[s] = count_sample(sample_libs, hlib.n, hlib.k, args.input_paths[s], offsets[s], first_len[s],
                                       !args.no_position_recursion, args.rc_mode, ingest_threads, !args.whole_lines);

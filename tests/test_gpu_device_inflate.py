@@ -41,7 +41,11 @@ def host_counts(library, permuter, seqs, off, recursion=True):
 
 
 def device_counts(library, permuter, blob, read_len, k, off, recursion=True, wave=64):
-    start, length, span_off = sg.span_geometry(k, read_len, off, recursion)
+    """read_len > 0: span mode (fixed-length reads); read_len == 0: reads of any length"""
+    if read_len:
+        start, length, span_off = sg.span_geometry(k, read_len, off, recursion)
+    else:
+        start, length, span_off = 0, 0, off
     c = sg.Counter(library, permuter, span_off, recursion)
     stream = sg.FastqStream(c, read_len, start, length)
     begin, isize = sg.bgzf_blocks(blob)
@@ -73,6 +77,32 @@ def test_device_path_equals_host_path(reverse, offset, k):
         n, got = device_counts(library, permuter, blob, read_len, k, off, wave=wave)
         assert n == len(seqs), label
         assert np.array_equal(got[0], want[0]) and got[1:] == want[1:], label
+
+
+@pytest.mark.parametrize("reverse,offset", [(False, 5), (True, 9)])
+def test_reads_of_any_length_are_counted_in_place(reverse, offset):
+    """variable-length mode (read_len = 0): adapter-trimmed reads, some shorter than offset + k, their
+    sequence lines counted where they lie in the inflated text by the line kernel"""
+    rng = np.random.default_rng(52 + offset)
+    k = 20
+    guides = make_library(rng, 400, k)
+    seqs = make_reads(rng, guides, 20_000, 75, offset, reverse, True, wild=b"J" if reverse else b"N")
+    assert len({len(s) for s in seqs}) > 5
+    library = sg.Library(guides, [b"g%d" % i for i in range(len(guides))])
+    permuter = sg.Permuter.new(library)
+    off = sg.Offset(reverse, offset)
+    want = host_counts(library, permuter, seqs, off)
+    text = fastq_text(seqs)
+    for label, blob, wave in [("l6", bgzf(text), 64), ("l1 small waves", bgzf(text, level=1), 2),
+                              ("tiny blocks", bgzf(text, block=999, level=9), 40), ("no final newline", bgzf(fastq_text(seqs, False)), 9)]:
+        n, got = device_counts(library, permuter, blob, 0, k, off, wave=wave)
+        assert n == len(seqs), label
+        assert np.array_equal(got[0], want[0]) and got[1:] == want[1:], label
+    # fixed-length reads go through this mode just as well
+    fixed = make_reads(rng, guides, 5000, 60, offset, reverse, False)
+    n, got = device_counts(library, permuter, bgzf(fastq_text(fixed)), 0, k, off)
+    want = host_counts(library, permuter, fixed, off)
+    assert n == 5000 and np.array_equal(got[0], want[0]) and got[1:] == want[1:]
 
 
 def test_synthetic_bgzf_file_and_full_size_blocks(tmp_path):

@@ -325,4 +325,19 @@ def test_bgzf_samples_are_inflated_framed_and_counted_on_the_device(tmp_path):
     a = run("-l", lib_path, "-i", odd, "-a", "4", "--timing", check=True)
     b = run("-l", lib_path, "-i", odd, "-a", "4", "--timing", "--host-inflate", check=True)
     assert a.stdout == b.stdout
-    assert timing(a)["device_ingest_samples"] == 0 and "FASTQ" in timing(a)["host_ingest_because"]
+    # the span mode reports the odd read; the CLI starts over in the variable-length mode, still on the device
+    assert timing(a)["device_ingest_samples"] == 1 and timing(a)["span_reads"] == 0
+    # a FASTA sample in BGZF blocks is not framed on the device at all
+    seqs = [l for l in lines[1::4]][:20000]
+    fa = str(tmp_path / "reads.fa.gz")
+    with open(fa, "wb") as f:
+        text = b"".join(b">r\n" + s + b"\n" for s in seqs)
+        for i in range(0, len(text), 0xff00):
+            blk = text[i:i + 0xff00]
+            raw = zlib.compressobj(1, zlib.DEFLATED, -15)
+            body = raw.compress(blk) + raw.flush()
+            f.write(bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0]) + b"BC" + struct.pack("<HH", 2, 18 + len(body) + 8 - 1) +
+                    body + struct.pack("<II", zlib.crc32(blk), len(blk)))
+    c = run("-l", lib_path, "-i", fa, "-a", "4", "--timing", check=True)
+    assert timing(c)["device_ingest_samples"] == 0 and timing(c)["host_ingest_because"] == "not FASTQ"
+    assert len(c.stdout.splitlines()) > 500
