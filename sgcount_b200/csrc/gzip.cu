@@ -76,8 +76,7 @@ struct StreamState {
 __global__ void __launch_bounds__(kInflateThreads) inflate_blocks_kernel(const uint8_t* __restrict__ gz,
                                                                         const uint64_t* __restrict__ begin,
                                                                         const uint64_t* __restrict__ out_off, uint32_t n,
-                                                                        uint8_t* __restrict__ text, StreamState* st,
-                                                                        uint32_t first_block) {
+                                                                        uint8_t* __restrict__ text, StreamState* st) {
   extern __shared__ uint16_t sm[];
   const uint32_t m = blockIdx.x * kInflateThreads + threadIdx.x;
   if (m >= n) return;
@@ -93,8 +92,8 @@ __global__ void __launch_bounds__(kInflateThreads) inflate_blocks_kernel(const u
   int rc = inflate::gunzip_member(in, in_len, out, cap, t, &consumed, &produced, &crc, &isize);
   if (rc == inflate::kOk && (consumed != in_len || produced != cap || isize != (uint32_t)cap)) rc = 100;
   if (rc != inflate::kOk) {
-    const unsigned int prev = atomicMin(&st->bad_block, first_block + m);
-    if (first_block + m < prev) st->bad_status = rc;  // (benign race between two bad blocks: either status will do)
+    const unsigned int prev = atomicMin(&st->bad_block, m);
+    if (m < prev) st->bad_status = rc;  // (benign race between two bad blocks: either status will do)
   }
 }
 
@@ -104,8 +103,7 @@ constexpr int kCrcWarps = 8;
 __global__ void __launch_bounds__(kCrcWarps * 32) crc_blocks_kernel(const uint8_t* __restrict__ gz,
                                                                    const uint64_t* __restrict__ begin,
                                                                    const uint64_t* __restrict__ out_off, uint32_t n,
-                                                                   const uint8_t* __restrict__ text, StreamState* st,
-                                                                   uint32_t first_block) {
+                                                                   const uint8_t* __restrict__ text, StreamState* st) {
   __shared__ uint32_t table[256];
   table[threadIdx.x] = inflate::crc_table_entry(threadIdx.x);
   __syncthreads();
@@ -127,8 +125,8 @@ __global__ void __launch_bounds__(kCrcWarps * 32) crc_blocks_kernel(const uint8_
     const uint8_t* t = gz + (begin[m + 1] - begin[0]) - 8;
     const uint32_t stored = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
     if (crc != stored) {
-      const unsigned int prev = atomicMin(&st->bad_block, first_block + m);
-      if (first_block + m < prev) st->bad_status = 101;
+      const unsigned int prev = atomicMin(&st->bad_block, m);
+      if (m < prev) st->bad_status = 101;
     }
   }
 }
@@ -280,8 +278,7 @@ struct sgc_fastq_stream {
   sgc_counter* counter = nullptr;  // NULL once released (its counter was destroyed first)
   int device = 0;
   uint32_t read_len = 0, span_start = 0, span_len = 0, span_stride = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
-  cudaEvent_t ready = nullptr, copied = nullptr;
+  cudaStream_t stream = nullptr;
   StreamState* d_state = nullptr;
   uint8_t *d_gz = nullptr, *d_text = nullptr, *d_spans = nullptr, *d_tail = nullptr;
   uint32_t *d_seq_start = nullptr, *d_seq_end = nullptr;  // variable-length mode
@@ -371,14 +368,6 @@ void sgc::fastq_stream_release(sgc_fastq_stream* s) {
   if (!s || !s->counter) return;
   DeviceGuard guard(s->device);
   cudaStreamSynchronize(s->stream);
-  if (s->copy_stream) {
-    cudaStreamSynchronize(s->copy_stream);
-    cudaStreamDestroy(s->copy_stream);
-    s->copy_stream = nullptr;
-  }
-  if (s->ready) cudaEventDestroy(s->ready);
-  if (s->copied) cudaEventDestroy(s->copied);
-  s->ready = s->copied = nullptr;
   auto& list = s->counter->fastq_streams;
   list.erase(std::remove(list.begin(), list.end(), s), list.end());
   s->counter = nullptr;
@@ -427,9 +416,6 @@ int sgc_fastq_stream_create(sgc_counter* counter, uint32_t read_len, uint32_t sp
   } cleanup{s};
   SGC_CUDA_TRY(cudaMalloc(&s->d_state, sizeof(StreamState)));
   SGC_CUDA_TRY(cudaMalloc(&s->d_tail, kHeadroom));
-  SGC_CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-  SGC_CUDA_TRY(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
-  SGC_CUDA_TRY(cudaEventCreateWithFlags(&s->copied, cudaEventDisableTiming));
   StreamState st0{};
   st0.bad_block = 0xFFFFFFFFu;
   SGC_CUDA_TRY(cudaMemcpyAsync(s->d_state, &st0, sizeof st0, cudaMemcpyHostToDevice, s->stream));
@@ -471,25 +457,13 @@ int sgc_fastq_stream_submit(sgc_fastq_stream* s, const uint8_t* gz, const uint64
   if (rc == SGC_OK) rc = grow(&s->d_begin, &s->begin_cap, (size_t)n_blocks + 1);
   if (rc == SGC_OK) rc = grow(&s->d_outoff, &s->outoff_cap, (size_t)n_blocks + 1);
   if (rc) return rc;
+  SGC_CUDA_TRY(cudaMemcpyAsync(s->d_gz, gz + block_begin[0], gz_bytes, cudaMemcpyHostToDevice, s->stream));
   SGC_CUDA_TRY(cudaMemcpyAsync(s->d_begin, block_begin, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, s->stream));
   SGC_CUDA_TRY(cudaMemcpyAsync(s->d_outoff, s->h_outoff.data(), ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, s->stream));
-  // The compressed bytes travel in pieces on a second stream, and every piece's blocks are
-  // inflated as soon as it has arrived: the copy of piece i + 1 (from pageable memory, ~12 GB/s)
-  // runs under the inflate of piece i.
-  constexpr uint32_t kPiece = 32768;
-  SGC_CUDA_TRY(cudaEventRecord(s->ready, s->stream));  // the buffers of the previous wave are free
-  SGC_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->ready, 0));
-  for (uint32_t a = 0; a < n_blocks; a += kPiece) {
-    const uint32_t b = std::min(n_blocks, a + kPiece);
-    const uint64_t from = block_begin[a] - block_begin[0], bytes = block_begin[b] - block_begin[a];
-    SGC_CUDA_TRY(cudaMemcpyAsync(s->d_gz + from, gz + block_begin[a], bytes, cudaMemcpyHostToDevice, s->copy_stream));
-    SGC_CUDA_TRY(cudaEventRecord(s->copied, s->copy_stream));
-    SGC_CUDA_TRY(cudaStreamWaitEvent(s->stream, s->copied, 0));
-    inflate_blocks_kernel<<<(b - a + kInflateThreads - 1) / kInflateThreads, kInflateThreads, kInflateSmem, s->stream>>>(
-        s->d_gz + from, s->d_begin + a, s->d_outoff + a, b - a, s->d_text, s->d_state, a);
-    crc_blocks_kernel<<<(b - a + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, s->stream>>>(
-        s->d_gz + from, s->d_begin + a, s->d_outoff + a, b - a, s->d_text, s->d_state, a);
-  }
+  inflate_blocks_kernel<<<(n_blocks + kInflateThreads - 1) / kInflateThreads, kInflateThreads, kInflateSmem, s->stream>>>(
+      s->d_gz, s->d_begin, s->d_outoff, n_blocks, s->d_text, s->d_state);
+  crc_blocks_kernel<<<(n_blocks + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, s->stream>>>(s->d_gz, s->d_begin, s->d_outoff,
+                                                                                           n_blocks, s->d_text, s->d_state);
   SGC_CUDA_TRY(cudaGetLastError());
   rc = frame_and_count(s, n_text, s->blocks_total);
   if (rc) return rc;
