@@ -201,14 +201,20 @@ int sgc_counter_state(sgc_counter*, uint64_t** d_state, uint64_t* n_words);
  * its per-sample Counters at count.rs:136; a sample cut into read shards needs them summed):
  * state[root] = sum over i of state[i], i.e. counts, total_reads and matched_reads of the whole
  * sample land in shards[root]; the other shards' vectors are left unspecified (reset them before
- * reuse).  Shards on different devices are summed with ONE ncclReduce(ncclUint64, ncclSum) of
- * n_guides + 2 words over NVLink, each rank's call enqueued on its counter's own stream (libnccl.so.2
- * is loaded on first use; communicators are cached per device set); shards that share a device
- * are folded on that device first.  Asynchronous: sgc_counter_finish(shards[root]) waits for it.
- * Every counter must come from a library of the same guides.  Errors: SGC_ERR_NCCL. */
+ * reuse).  Shards that share a device are folded on that device first.  Across devices:
+ *   - with NCCL communicators for the device set in place (sgc_reduce_prepare was called, or an
+ *     earlier reduce created them): ONE ncclReduce(ncclUint64, ncclSum) of n_guides + 2 words over
+ *     NVLink, each rank's call enqueued on its counter's own stream (libnccl.so.2 is loaded on first
+ *     use; communicators are cached per device set);
+ *   - otherwise (nobody asked for NCCL): every other device's vector is copied peer to peer into a
+ *     scratch vector on the root's device and added there — loading NCCL and ncclCommInitAll take
+ *     seconds, more than counting a whole sample of tens of millions of reads.
+ * Asynchronous: sgc_counter_finish(shards[root]) waits for it.  Every counter must come from a
+ * library of the same guides.  Errors: SGC_ERR_NCCL. */
 int sgc_reduce_counts(sgc_counter* const* shards, int n_shards, int root);
-/* Optional: create the communicators for counters on these devices ahead of time (loading NCCL and
- * ncclCommInitAll take seconds; the CLI does this on a side thread while it builds its tables). */
+/* Selects NCCL for every later sgc_reduce_counts of this process and creates the communicators for
+ * counters on these devices (loading NCCL and ncclCommInitAll take seconds; the CLI does this on a
+ * side thread, for inputs large enough to outlast it, while it builds its tables). */
 int sgc_reduce_prepare(const int* devices, int n_devices);
 
 /* ---- FASTQ straight from BGZF blocks -----------------------------------------------------------
@@ -240,6 +246,14 @@ int sgc_fastq_stream_create(sgc_counter* counter, uint32_t read_len, uint32_t sp
 void sgc_fastq_stream_destroy(sgc_fastq_stream*);
 int sgc_fastq_stream_submit(sgc_fastq_stream*, const uint8_t* gz, const uint64_t* block_begin,
                             const uint32_t* block_isize, uint32_t n_blocks);
+/* The same for a wave the caller has cut at record boundaries, so that waves do not depend on each
+ * other and may go to different streams (devices): of the wave's inflated text the first head_skip
+ * and the last tail_skip bytes belong to the neighbouring waves (a block that holds a cut is
+ * submitted with both).  self_contained != 0 asserts that what is left starts and ends on a
+ * record boundary (SGC_ERR_FASTQ_FORMAT otherwise). */
+int sgc_fastq_stream_submit_range(sgc_fastq_stream*, const uint8_t* gz, const uint64_t* block_begin,
+                                  const uint32_t* block_isize, uint32_t n_blocks, uint32_t head_skip,
+                                  uint32_t tail_skip, int self_contained);
 int sgc_fastq_stream_finish(sgc_fastq_stream*, uint64_t* n_records);
 
 /* Statistics of the last sgc_counter_submit_device call, for benchmarking. */

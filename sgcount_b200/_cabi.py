@@ -96,6 +96,7 @@ SIGNATURES = {
     "sgc_fastq_stream_create": (_int, [_vp, _u32, _u32, _u32, C.POINTER(_vp)]),
     "sgc_fastq_stream_destroy": (None, [_vp]),
     "sgc_fastq_stream_submit": (_int, [_vp, _vp, _vp, _vp, _u32]),
+    "sgc_fastq_stream_submit_range": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _int]),
     "sgc_fastq_stream_finish": (_int, [_vp, C.POINTER(_u64)]),
     "sgc_counter_launch_info": (_int, [_vp, C.POINTER(LaunchInfo)]),
 }

@@ -245,6 +245,13 @@ def reduce_counts(shards: Sequence["Counter"], root: int = 0) -> None:
         c._result = None
 
 
+def reduce_prepare(devices: Sequence[int]) -> None:
+    """sgc_reduce_prepare: NCCL communicators for these devices; every later reduce_counts of the
+    process then goes through NCCL (without it, devices are summed with peer copies)"""
+    arr = (C.c_int * len(devices))(*devices)
+    check(_cabi.load().sgc_reduce_prepare(arr, len(devices)))
+
+
 def position_counts(reader: ReadBatch, device: int = 0) -> np.ndarray:
     """offsetter.rs:55-79 on the device -> uint32[size][4]"""
     lib = _cabi.load()

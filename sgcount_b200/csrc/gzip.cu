@@ -68,6 +68,8 @@ struct StreamState {
   unsigned int format_error;    // 1 irregular read length, 2 not FASTQ framing, 4 a record longer than the headroom
   unsigned int tail;            // bytes carried in front of the next wave
   unsigned int next_tail;
+  unsigned int head_skip;       // bytes at the start of this wave's text that belong to the previous wave
+  unsigned int self_contained;  // the caller cut this wave at record boundaries: nothing may be left over
   unsigned long long lines;     // newlines of the current wave's region
   unsigned long long records;   // records of the current wave
   unsigned long long records_total;
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kCrcWarps * 32) crc_blocks_kernel(const uint8_
 
 // bytes [lo, hi) of the text are the current region: the carried tail, then this wave's text
 __device__ __forceinline__ void region_of(const StreamState* st, uint64_t n_text, uint64_t* lo, uint64_t* hi) {
-  *lo = kHeadroom - st->tail;
+  *lo = kHeadroom - st->tail + st->head_skip;
   *hi = (uint64_t)kHeadroom + n_text;
 }
 
@@ -247,8 +249,14 @@ __global__ void tail_save_kernel(const uint8_t* __restrict__ text, uint64_t n_te
   const uint32_t tail = st->next_tail;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < tail; i += gridDim.x * blockDim.x) tail_buf[i] = text[hi - tail + i];
 }
+__global__ void wave_begin_kernel(StreamState* st, unsigned int head_skip, unsigned int self_contained) {
+  st->head_skip = head_skip;
+  st->self_contained = self_contained;
+}
 __global__ void wave_commit_kernel(StreamState* st) {
+  if (st->self_contained && st->next_tail) atomicOr(&st->format_error, 8u);  // the cut was not a record boundary
   st->tail = st->next_tail;
+  st->head_skip = 0;
   st->records_total += st->records;
 }
 __global__ void tail_restore_kernel(uint8_t* __restrict__ text, const StreamState* st, const uint8_t* __restrict__ tail_buf) {
@@ -308,7 +316,9 @@ int stream_error(sgc_fastq_stream* s, const StreamState& st, uint64_t first_bloc
   }
   snprintf(buf, sizeof buf, "not fixed-length 4-line FASTQ (%s)",
            (st.format_error & 2) ? "a record does not start with '@'"
-                                 : ((st.format_error & 4) ? "a record longer than 64 KB" : "a read of another length, or a line that is not '+'"));
+                                 : ((st.format_error & 4) ? "a record longer than 64 KB"
+                                                          : ((st.format_error & 8) ? "a wave was not cut at a record boundary"
+                                                                                   : "a read of another length, or a line that is not '+'")));
   return set_error(SGC_ERR_FASTQ_FORMAT, buf);
 }
 
@@ -435,6 +445,12 @@ void sgc_fastq_stream_destroy(sgc_fastq_stream* s) {
 
 int sgc_fastq_stream_submit(sgc_fastq_stream* s, const uint8_t* gz, const uint64_t* block_begin, const uint32_t* block_isize,
                             uint32_t n_blocks) {
+  return sgc_fastq_stream_submit_range(s, gz, block_begin, block_isize, n_blocks, 0, 0, 0);
+}
+
+int sgc_fastq_stream_submit_range(sgc_fastq_stream* s, const uint8_t* gz, const uint64_t* block_begin,
+                                  const uint32_t* block_isize, uint32_t n_blocks, uint32_t head_skip, uint32_t tail_skip,
+                                  int self_contained) {
   if (!s || !gz || !block_begin || !block_isize) return set_error(SGC_ERR_INVALID_ARG, "NULL argument");
   if (s->failed || !s->counter) return set_error(SGC_ERR_INVALID_ARG, "the stream has failed or its counter is gone");
   if (n_blocks == 0) return SGC_OK;
@@ -465,7 +481,9 @@ int sgc_fastq_stream_submit(sgc_fastq_stream* s, const uint8_t* gz, const uint64
   crc_blocks_kernel<<<(n_blocks + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, s->stream>>>(s->d_gz, s->d_begin, s->d_outoff,
                                                                                            n_blocks, s->d_text, s->d_state);
   SGC_CUDA_TRY(cudaGetLastError());
-  rc = frame_and_count(s, n_text, s->blocks_total);
+  if ((uint64_t)head_skip + tail_skip > n_text) return set_error(SGC_ERR_INVALID_ARG, "the skips exceed the wave's text");
+  wave_begin_kernel<<<1, 1, 0, s->stream>>>(s->d_state, head_skip, self_contained ? 1u : 0u);
+  rc = frame_and_count(s, n_text - tail_skip, s->blocks_total);
   if (rc) return rc;
   s->blocks_total += n_blocks;
   return SGC_OK;

@@ -105,6 +105,45 @@ __global__ void add_state_kernel(unsigned long long* __restrict__ dst, const uns
   if (i < n) dst[i] += src[i];
 }
 
+bool g_force_nccl = false;  // sgc_reduce_prepare has been called: the caller wants NCCL, wait for it
+
+// state[root] += state of every other leader, through a scratch vector on the root's device
+int peer_reduce(const std::map<int, sgc_counter*>& leader, sgc_counter* root, size_t words) {
+  DeviceGuard guard(root->device);
+  unsigned long long* scratch = nullptr;
+  SGC_CUDA_TRY(cudaMalloc(&scratch, words * sizeof(uint64_t)));
+  struct Free {
+    void* p;
+    cudaStream_t s;
+    ~Free() {
+      cudaStreamSynchronize(s);
+      cudaFree(p);
+    }
+  } free_scratch{scratch, root->stream};
+  for (const auto& kv : leader) {
+    sgc_counter* l = kv.second;
+    if (l == root) continue;
+    cudaEvent_t ev;
+    {
+      DeviceGuard src(l->device);
+      SGC_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      const cudaError_t e = cudaEventRecord(ev, l->stream);
+      if (e != cudaSuccess) {
+        cudaEventDestroy(ev);
+        SGC_CUDA_TRY(e);
+      }
+    }
+    cudaError_t e = cudaStreamWaitEvent(root->stream, ev, 0);  // the shard's counting has finished
+    if (e == cudaSuccess)
+      e = cudaMemcpyPeerAsync(scratch, root->device, l->d_state, l->device, words * sizeof(uint64_t), root->stream);
+    cudaEventDestroy(ev);
+    SGC_CUDA_TRY(e);
+    add_state_kernel<<<(unsigned)((words + 255) / 256), 256, 0, root->stream>>>(root->d_state, scratch, words);
+    SGC_CUDA_TRY(cudaGetLastError());
+  }
+  return SGC_OK;
+}
+
 }  // namespace
 }  // namespace sgc
 
@@ -146,7 +185,18 @@ extern "C" int sgc_reduce_counts(sgc_counter* const* shards, int n_shards, int r
   // 2. one rank per device
   std::vector<int> devices;
   for (auto& kv : leader) devices.push_back(kv.first);  // sorted by the map
-  std::lock_guard<std::mutex> lk(g_comm_mu);  // communicators are shared: one reduce at a time per process
+  // NCCL when its communicators for these devices exist (sgc_reduce_prepare made them, or an
+  // earlier reduce did).  Creating them takes seconds — longer than counting a whole sample of
+  // tens of millions of reads — so a reduce that finds none (and nobody creating them) copies the
+  // n_guides + 2 words of every other device straight into a buffer on the root's device
+  // (cudaMemcpyPeerAsync: NVLink peer-to-peer) and adds them there.
+  std::unique_lock<std::mutex> lk(g_comm_mu, std::try_to_lock);  // communicators are shared: one reduce at a time
+  const bool nccl_ready = lk.owns_lock() && g_comms.count(devices) != 0;
+  if (!nccl_ready && !g_force_nccl) {
+    if (lk.owns_lock()) lk.unlock();
+    return peer_reduce(leader, shards[root], words);
+  }
+  if (!lk.owns_lock()) lk.lock();
   CommSet* csp = nullptr;
   int rc = comms_for(devices, &csp);
   if (rc) return rc;
@@ -179,6 +229,7 @@ extern "C" int sgc_reduce_prepare(const int* devices, int n_devices) {
   std::sort(sorted.begin(), sorted.end());
   sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
   if (sorted.size() < 2) return SGC_OK;
+  g_force_nccl = true;
   std::lock_guard<std::mutex> lk(g_comm_mu);
   CommSet* cs = nullptr;
   return comms_for(sorted, &cs);

@@ -580,6 +580,18 @@ bool SeqBlockReader::next(SeqBlock& out) {
   return true;
 }
 
+size_t fastq_last_record_end(const char* text, size_t n) {
+  std::vector<size_t> nl;  // newline positions
+  for (const char* p = text; (p = static_cast<const char*>(memchr(p, '\n', (size_t)(text + n - p)))) != nullptr; ++p)
+    nl.push_back((size_t)(p - text));
+  // line j (j >= 1) is text(nl[j-1], nl[j]); the bytes before nl[0] are a line of unknown start
+  for (size_t i = nl.size() >= 5 ? nl.size() - 4 : 0; i >= 1; --i) {
+    const size_t h = nl[i - 1] + 1, s = nl[i] + 1, plus = nl[i + 1] + 1, q = nl[i + 2] + 1;
+    if (text[h] == '@' && plus < n && text[plus] == '+' && nl[i + 1] - s == nl[i + 3] - q) return nl[i + 3] + 1;
+  }
+  return SIZE_MAX;
+}
+
 FastxReader::FastxReader(const std::string& path, unsigned inflate_threads) : src_(path, inflate_threads) {}
 
 void FastxReader::sniff(const char* line, size_t len) {

@@ -160,6 +160,13 @@ class SeqBlockReader {
   std::unique_ptr<Impl> impl_;
 };
 
+// Offset just past the last complete FASTQ record that can be recognised in text[0, n) without
+// knowing where the text starts in its file (a BGZF block begins anywhere in a record), or
+// SIZE_MAX.  A record start is a line that begins with '@', whose third line begins with '+' and
+// whose second and fourth lines have the same length; a quality line that begins with '@' cannot
+// pass, because two lines further comes a sequence line, which never begins with '+'.
+size_t fastq_last_record_end(const char* text, size_t n);
+
 class FastxReader {
  public:
   explicit FastxReader(const std::string& path, unsigned inflate_threads = 1);

@@ -50,6 +50,20 @@ int main(int argc, char** argv) {
       printf("%llu %llu\n", n, bytes);
       return 0;
     }
+    if (argc > 3 && !strcmp(argv[3], "cut")) {  // fastq_last_record_end of the raw bytes of a file
+      FILE* f = fopen(argv[1], "rb");
+      if (!f) return 2;
+      std::vector<char> data;
+      char buf[1 << 16];
+      for (size_t got; (got = fread(buf, 1, sizeof buf, f)) > 0;) data.insert(data.end(), buf, buf + got);
+      fclose(f);
+      const size_t cut = sgh::fastq_last_record_end(data.data(), data.size());
+      if (cut == SIZE_MAX)
+        printf("none\n");
+      else
+        printf("%zu\n", cut);
+      return 0;
+    }
     if (argc > 4 && !strcmp(argv[3], "spans")) {  // span framing: fastx_dump <path> <threads> spans read_len,start,len,stride
       sgh::SpanSpec spec;
       if (sscanf(argv[4], "%u,%u,%u,%u", &spec.read_len, &spec.start, &spec.len, &spec.stride) != 4) return 2;

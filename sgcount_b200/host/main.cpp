@@ -33,6 +33,7 @@
 
 #include "../../include/sgcount_cuda.h"
 #include "fastx.h"
+#include "inflate.h"
 
 namespace {
 
@@ -410,13 +411,74 @@ bool bgzf_index(const uint8_t* d, size_t n, std::vector<uint64_t>& begin, std::v
   return !isize.empty();
 }
 
-// One sample through the device ingest.  Returns false (after resetting nothing: the caller
-// starts a fresh counter) when the file is not BGZF or the device reports input it does not take —
-// a read of another length, FASTA, a damaged block — so that the host path counts the sample.
+// One wave of the device ingest: blocks [first, first + n) of the file, of whose inflated text the
+// first head_skip and the last tail_skip bytes belong to the neighbouring waves.
+struct Wave {
+  size_t first = 0, n = 0;
+  uint32_t head_skip = 0, tail_skip = 0;
+};
+
+// Cuts the blocks into waves of about `blocks_per_wave` that each start and end on a record
+// boundary, so that the waves do not depend on each other and can go to different devices.  A
+// block's text starts anywhere inside a record; where a wave is to end, this thread inflates that
+// ONE block (64 KB) and looks for the last complete record in it (fastq_last_record_end); the block
+// then belongs to both waves, each skipping the other's part.  False when no boundary can be
+// found near a cut (the caller then submits the blocks as one dependent sequence).
+bool plan_waves(const uint8_t* file, const std::vector<uint64_t>& begin, const std::vector<uint32_t>& isize,
+                size_t blocks_per_wave, uint64_t text_per_wave, std::vector<Wave>& waves) {
+  const size_t n_blocks = isize.size();
+  size_t a = 0;
+  uint32_t head_skip = 0;
+  while (a < n_blocks) {
+    size_t b = a;
+    uint64_t text = 0;
+    while (b < n_blocks && b - a < blocks_per_wave && text + isize[b] < text_per_wave) text += isize[b++];
+    if (b == a) b = a + 1;
+    Wave w;
+    w.first = a;
+    w.head_skip = head_skip;
+    if (b >= n_blocks) {  // the last wave runs to the end of the file
+      w.n = n_blocks - a;
+      waves.push_back(w);
+      break;
+    }
+    // the last block of the wave that holds a recognisable record boundary
+    size_t j = b - 1;
+    size_t cut = SIZE_MAX;
+    for (;; --j) {
+      if (isize[j] >= 64) {
+        sgh::Bytes text_j;
+        size_t used = 0;
+        if (!sgh::gunzip_member(file + begin[j], (size_t)(begin[j + 1] - begin[j]), text_j, used)) return false;
+        cut = sgh::fastq_last_record_end(text_j.data(), text_j.size());
+        if (cut != SIZE_MAX && !(j == a && cut <= head_skip)) break;  // (a cut inside the part we skip is no use)
+        cut = SIZE_MAX;
+      }
+      if (j == a || b - j > 64) return false;
+    }
+    w.n = j + 1 - a;
+    w.tail_skip = (uint32_t)(isize[j] - cut);
+    waves.push_back(w);
+    if (cut == isize[j]) {  // the block ends on a record boundary
+      a = j + 1;
+      head_skip = 0;
+    } else {
+      a = j;
+      head_skip = (uint32_t)cut;
+    }
+  }
+  return true;
+}
+
+// One sample through the device ingest, on one device or — `libs.size()` > 1 — with its waves
+// dealt to several, one host thread each, the devices' count vectors summed at the end
+// (sgc_reduce_counts).  Returns false when the file is not BGZF or the device reports input it
+// does not take — a read of another length (span mode), FASTA, a damaged block — so that the
+// caller can try the other mode or the host path.
 // `variable`: reads of any length (the sequence lines are counted where they lie in the inflated
 // text); otherwise every read has read_len bytes and only its guide-window span is kept.
-bool count_sample_on_device(const sgc_library* lib, uint32_t n_guides, uint32_t k, const std::string& path, OffsetValue offset,
-                            uint32_t read_len, bool variable, bool recursion, int rc_mode, SampleResult& r,
+bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_t n_guides, uint32_t k, const std::string& path,
+                            OffsetValue offset, uint32_t read_len, bool variable, bool recursion, int rc_mode, SampleResult& r,
                             std::string& why_not) {
   uint32_t span_start = 0, span_len = 0, span_offset = offset.index;
   if (!variable && sgc_span_geometry(k, read_len, offset.reverse, offset.index, recursion, &span_start, &span_len,
@@ -436,51 +498,110 @@ bool count_sample_on_device(const sgc_library* lib, uint32_t n_guides, uint32_t 
     return false;
   }
   const auto t_start = std::chrono::steady_clock::now();
-  sgc_counter* c = nullptr;
-  sgc_fastq_stream* stream = nullptr;
-  struct Guard {
-    sgc_counter*& c;
-    sgc_fastq_stream*& s;
-    ~Guard() {
-      sgc_fastq_stream_destroy(s);
-      sgc_counter_destroy(c);
-    }
-  } guard{c, stream};
-  check(sgc_counter_create(lib, offset.reverse, span_offset, recursion, rc_mode, nullptr, nullptr, &c));
-  check(sgc_fastq_stream_create(c, variable ? 0 : read_len, span_start, span_len, &stream));
+  const size_t n_blocks = isize.size(), n_dev = libs.size();
   // Waves of blocks.  One device thread inflates each block and a wave takes about as long with
-  // 300 000 blocks as with 10 000, so a wave is as large as 12 GiB of text allows.  The compressed
-  // bytes go to the device straight from the mapping (page cache -> the driver's staging buffers).
-  const size_t n_blocks = isize.size();
-  std::string error;
-  int status = SGC_OK;
-  for (size_t a = 0; a < n_blocks && status == SGC_OK;) {
-    size_t b = a;
-    uint64_t text = 0;
-    // (variable-length mode addresses the text with 32-bit offsets: 3 GiB per wave)
-    const uint64_t wave_text = variable ? (3ull << 30) : (12ull << 30);
-    while (b < n_blocks && b - a < 262144 && text + isize[b] < wave_text) text += isize[b++];
-    if (b == a) b = a + 1;
-    status = sgc_fastq_stream_submit(stream, file.data, begin.data() + a, isize.data() + a, (uint32_t)(b - a));
-    if (status != SGC_OK) error = sgc_last_error();
-    a = b;
+  // 300 000 blocks as with 10 000, so a wave is as large as 12 GiB of text allows (variable-length
+  // mode addresses the text with 32-bit offsets: 3 GiB); with several devices, two waves each.
+  // The compressed bytes go to the device straight from the mapping (page cache -> the driver's
+  // staging buffers).
+  const uint64_t wave_text = variable ? (3ull << 30) : (12ull << 30);
+  std::vector<Wave> waves;
+  bool independent = n_dev > 1;
+  if (independent) {
+    size_t per_wave = std::min<size_t>(262144, std::max<size_t>(16384, n_blocks / (2 * n_dev) + 1));
+    if (const char* e = getenv("SGC_WAVE_BLOCKS"); e && atol(e) > 0) per_wave = (size_t)atol(e);  // tests: many small waves
+    independent = plan_waves(file.data, begin, isize, per_wave, wave_text, waves);
+    if (!independent) waves.clear();
+  }
+  if (!independent) {  // one device, one dependent sequence of waves (the stream carries partial records over)
+    for (size_t a = 0; a < n_blocks;) {
+      size_t b = a;
+      uint64_t text = 0;
+      while (b < n_blocks && b - a < 262144 && text + isize[b] < wave_text) text += isize[b++];
+      if (b == a) b = a + 1;
+      Wave w;
+      w.first = a;
+      w.n = b - a;
+      waves.push_back(w);
+      a = b;
+    }
+  }
+  const size_t n_lanes = independent ? std::min(n_dev, waves.size()) : 1;
+  struct Lane {
+    sgc_counter* c = nullptr;
+    sgc_fastq_stream* stream = nullptr;
+    uint64_t records = 0;
+    int status = SGC_OK;
+    std::string error;
+  };
+  struct Guard {
+    std::vector<Lane> lanes;
+    ~Guard() {
+      for (auto& l : lanes) {
+        sgc_fastq_stream_destroy(l.stream);
+        sgc_counter_destroy(l.c);
+      }
+    }
+  } g;
+  g.lanes.resize(n_lanes);
+  for (size_t d = 0; d < n_lanes; ++d) {
+    check(sgc_counter_create(libs[d], offset.reverse, span_offset, recursion, rc_mode, nullptr, nullptr, &g.lanes[d].c));
+    check(sgc_fastq_stream_create(g.lanes[d].c, variable ? 0 : read_len, span_start, span_len, &g.lanes[d].stream));
+  }
+  std::atomic<size_t> next_wave{0};
+  std::atomic<bool> failed{false};
+  auto run_lane = [&](Lane& l) {
+    for (;;) {
+      const size_t w = next_wave.fetch_add(1);
+      if (w >= waves.size() || failed.load()) break;
+      const Wave& wv = waves[w];
+      l.status = sgc_fastq_stream_submit_range(l.stream, file.data, begin.data() + wv.first, isize.data() + wv.first,
+                                               (uint32_t)wv.n, wv.head_skip, wv.tail_skip, independent ? 1 : 0);
+      if (l.status != SGC_OK) {
+        l.error = sgc_last_error();
+        failed.store(true);
+        break;
+      }
+    }
+    if (l.status == SGC_OK && !failed.load()) {
+      l.status = sgc_fastq_stream_finish(l.stream, &l.records);
+      if (l.status != SGC_OK) {
+        l.error = sgc_last_error();
+        failed.store(true);
+      }
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (size_t d = 1; d < n_lanes; ++d) pool.emplace_back([&, d] { run_lane(g.lanes[d]); });
+    run_lane(g.lanes[0]);
+    for (auto& t : pool) t.join();
   }
   uint64_t n_records = 0;
-  if (status == SGC_OK) {
-    status = sgc_fastq_stream_finish(stream, &n_records);
-    if (status != SGC_OK) error = sgc_last_error();
+  for (auto& l : g.lanes) {
+    if (l.status == SGC_ERR_GZIP || l.status == SGC_ERR_FASTQ_FORMAT) {
+      why_not = l.error;
+      return false;
+    }
+    if (l.status != SGC_OK) fail("%s", l.error.c_str());
+    n_records += l.records;
   }
-  if (status == SGC_ERR_GZIP || status == SGC_ERR_FASTQ_FORMAT) {
-    why_not = error;
+  if (failed.load()) {
+    why_not = "a wave failed";
     return false;
   }
-  if (status != SGC_OK) fail("%s", error.c_str());
+  if (n_lanes > 1) {
+    std::vector<sgc_counter*> shards;
+    for (auto& l : g.lanes) shards.push_back(l.c);
+    check(sgc_reduce_counts(shards.data(), (int)shards.size(), 0));
+  }
   r.counts.resize(n_guides);
-  check(sgc_counter_finish(c, r.counts.data(), &r.total, &r.matched));
+  check(sgc_counter_finish(g.lanes[0].c, r.counts.data(), &r.total, &r.matched));
   r.span_reads = variable ? 0 : n_records;
   r.line_reads = variable ? n_records : 0;
   r.device_ingest = true;
   r.device_blocks = n_blocks;
+  r.shards = (unsigned)n_lanes;
   r.submit_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
   return true;
 }
@@ -669,7 +790,9 @@ int main(int argc, char** argv) {
         if (t.joinable()) t.join();
       }
     } nccl_join{nccl_warmup};
-    if (per_sample > 1 && gpus > 1) {
+    // (NCCL for inputs large enough to outlast its start-up; below that sgc_reduce_counts sums the
+    // devices with peer copies)
+    if (per_sample > 1 && gpus > 1 && largest_input >= (8ull << 30)) {
       nccl_warmup = std::thread([&] {
         for (size_t s = 0; s < n_samples; ++s) {  // one communicator set per distinct device group
           std::vector<int> devs;
@@ -741,16 +864,16 @@ int main(int argc, char** argv) {
           // anything else, or anything the device declines, through the host's inflate threads
           bool on_device = false;
           std::string why_not = "switched off";
-          if (!args.host_inflate && head_fastq[s] && per_sample == 1 && args.input_paths[s].size() > 3 &&
+          if (!args.host_inflate && head_fastq[s] && args.input_paths[s].size() > 3 &&
               args.input_paths[s].compare(args.input_paths[s].size() - 3, 3, ".gz") == 0) {
             // fixed-length reads as span records; reads of several lengths (seen in the head, or
             // reported by the device deeper in the file) with their sequence lines in place
             bool variable = !head_uniform[s] || args.whole_lines;
-            on_device = count_sample_on_device(sample_libs[0], hlib.n, hlib.k, args.input_paths[s], offsets[s], first_len[s],
+            on_device = count_sample_on_device(sample_libs, hlib.n, hlib.k, args.input_paths[s], offsets[s], first_len[s],
                                                variable, !args.no_position_recursion, args.rc_mode, results[s], why_not);
             if (!on_device && !variable && why_not.find("FASTQ") != std::string::npos) {
               results[s] = SampleResult();
-              on_device = count_sample_on_device(sample_libs[0], hlib.n, hlib.k, args.input_paths[s], offsets[s], first_len[s],
+              on_device = count_sample_on_device(sample_libs, hlib.n, hlib.k, args.input_paths[s], offsets[s], first_len[s],
                                                  true, !args.no_position_recursion, args.rc_mode, results[s], why_not);
             }
           } else if (!head_fastq[s]) {

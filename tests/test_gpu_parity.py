@@ -359,13 +359,17 @@ def test_reduce_counts_of_read_shards_on_one_device():
         sg.reduce_counts([shards[0], shards[0]])
 
 
-def test_reduce_counts_across_devices_with_nccl():
-    """read shards on every device of the box, one ncclReduce of u64[n_guides + 2] to device 0"""
+@pytest.mark.parametrize("path", ["peer copies", "nccl"])  # in this order: sgc_reduce_prepare switches the process to NCCL
+def test_reduce_counts_across_devices(path):
+    """read shards on every device of the box summed into one: peer-to-peer copies + add when nobody
+    has asked for NCCL, one ncclReduce of u64[n_guides + 2] once sgc_reduce_prepare has"""
     import torch
 
     n_dev = torch.cuda.device_count()
     if n_dev < 2:
         pytest.skip("needs at least two devices")
+    if path == "nccl":
+        sg.reduce_prepare(list(range(n_dev)))
     rng = np.random.default_rng(13)
     guides = make_library(rng, 2000, 20)
     seqs = make_reads(rng, guides, 40_000, 75, 5)

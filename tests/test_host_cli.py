@@ -341,3 +341,54 @@ def test_bgzf_samples_are_inflated_framed_and_counted_on_the_device(tmp_path):
     c = run("-l", lib_path, "-i", fa, "-a", "4", "--timing", check=True)
     assert timing(c)["device_ingest_samples"] == 0 and timing(c)["host_ingest_because"] == "not FASTQ"
     assert len(c.stdout.splitlines()) > 500
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variable", [False, True])
+def test_bgzf_sample_cut_into_independent_waves_over_several_counters(variable, tmp_path):
+    """--read-shards N on BGZF input: the host cuts the blocks into waves that start and end on record
+    boundaries (it inflates the one block at each cut), the waves go to N streams / counters (devices,
+    when there are several) and the count vectors are summed.  Same table as one dependent stream."""
+    import json
+    import struct
+    import zlib
+
+    from sgcount_b200 import synth
+
+    seed = 0xB2000008
+    arr = synth.make_library(seed, 3000, 20)
+    lib_path = str(tmp_path / "lib.fa")
+    with open(lib_path, "wb") as f:
+        f.write(b"".join(b">lib.%d\n%s\n" % (i, arr[i].tobytes()) for i in range(len(arr))))
+    fq = str(tmp_path / "s.fastq.gz")
+    if not variable:
+        synth.Sample(seed, 0, arr, 75, 6, False).write_fastq_bgzf(fq, 0, 400_000)
+    else:
+        plain = str(tmp_path / "plain.fastq.gz")
+        synth.Sample(seed, 0, arr, 75, 6, False).write_fastq(plain, 0, 200_000)
+        lines = gzip.open(plain, "rb").read().rstrip(b"\n").split(b"\n")
+        rng = __import__("random").Random(3)
+        for r in range(0, len(lines), 4):  # trim a third of the reads (and their quality lines)
+            if rng.random() < 0.33:
+                n = rng.randrange(0, 70)
+                lines[r + 1], lines[r + 3] = lines[r + 1][:n], lines[r + 3][:n]
+        text = b"\n".join(lines) + b"\n"
+        with open(fq, "wb") as f:
+            for i in range(0, len(text), 0xff00):
+                b = text[i:i + 0xff00]
+                raw = zlib.compressobj(1, zlib.DEFLATED, -15)
+                body = raw.compress(b) + raw.flush()
+                f.write(bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0]) + b"BC" + struct.pack("<HH", 2, 18 + len(body) + 8 - 1) +
+                        body + struct.pack("<II", zlib.crc32(b), len(b)))
+    one = run("-l", lib_path, "-i", fq, "-a", "6", "--timing", check=True)
+    host = run("-l", lib_path, "-i", fq, "-a", "6", "--host-inflate", check=True)
+    env = dict(os.environ, SGC_WAVE_BLOCKS="37")
+    p = subprocess.run([BIN, "-l", lib_path, "-i", fq, "-a", "6", "--timing", "--read-shards", "3"], capture_output=True,
+                       text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stderr
+    t1 = json.loads([l for l in one.stderr.splitlines() if l.startswith("{")][-1])
+    t3 = json.loads([l for l in p.stderr.splitlines() if l.startswith("{")][-1])
+    assert t1["device_ingest_samples"] == 1 and t3["device_ingest_samples"] == 1
+    assert t3["read_shards_per_sample"] == 3
+    assert one.stdout == host.stdout == p.stdout and len(p.stdout.splitlines()) > 1000
+    assert [l for l in one.stderr.splitlines() if l.startswith("Finished")] == [l for l in p.stderr.splitlines() if l.startswith("Finished")]

@@ -189,3 +189,30 @@ def test_span_framing(tmp_path):
         n, h, n_span = out.split()
         assert rc == 0 and f"{n} {h}" == span_fnv(odd, 75, 4, 22), (threads, out, err)
         assert int(n_span) <= 40000 - len([1 for _ in aligned2[3].split(b"\n+\n")]) + 1
+
+
+def test_last_record_end_of_a_text_that_starts_anywhere(tmp_path):
+    """fastq_last_record_end: where a BGZF block's text can be cut so that the next wave of the device
+    ingest starts on a record — the text begins anywhere inside a record, quality lines may begin
+    with '@' or '+', reads have any length"""
+    rng = random.Random(14)
+    recs = []
+    for i in range(400):
+        n = rng.choice([75, 75, 60, 1, 0])
+        qual = bytes(rng.choice(b"@+IF#") for _ in range(n))
+        recs.append(b"@r%d x\n%s\n+\n%s\n" % (i, bytes(rng.choice(b"ACGTN") for _ in range(n)), qual))
+    text = b"".join(recs)
+    ends, at = [], 0
+    for r in recs:
+        at += len(r)
+        ends.append(at)
+    for trial in range(60):
+        a = rng.randrange(0, len(text) - 2000)
+        b = rng.randrange(a + 700, min(len(text), a + 5000))
+        (tmp_path / "piece").write_bytes(text[a:b])
+        rc, out, _ = dump(tmp_path / "piece", 1, "cut")
+        # the last record wholly inside [a, b) that does not start at a itself (its start cannot be told)
+        inside = [e for s, e in zip([0] + ends, ends) if s > a and e <= b]
+        assert rc == 0 and out == (str(inside[-1] - a) if inside else "none"), (trial, a, b)
+    (tmp_path / "piece").write_bytes(b"ACGT\nACGT")
+    assert dump(tmp_path / "piece", 1, "cut")[1] == "none"
