@@ -91,3 +91,29 @@ for gpus in sorted({1, torch.cuda.device_count()}):
 assert len(set(btables.values())) == 1
 assert list(btables.values())[0].replace(b"\tb", b"\ts") == list(tables.values())[0], "BGZF and gzip tables differ"
 print("BGZF samples: tables identical on 1 and", torch.cuda.device_count(), "GPUs and equal to the gzip samples' table")
+
+# Config 5 end to end from gzip, on the device: ONE BGZF sample whose blocks the host cuts into waves at
+# record boundaries; the waves go round the devices (inflate, framing and counting on each), the count
+# vectors are summed at the end (peer copies; NCCL for inputs of 8 GiB or more).
+bgzf_reads = int(sys.argv[3]) if len(sys.argv) > 3 else 16 * n_reads
+bigb = os.path.join(tmp, "bigb.fastq.gz")
+t0 = time.time()
+synth.Sample(seed, 100, arr, 75, 9, False).write_fastq_bgzf(bigb, 0, bgzf_reads, gz_level=1)
+print(f"one BGZF sample of {bgzf_reads} reads: {os.path.getsize(bigb) / 1e6:.0f} MB written in {time.time() - t0:.1f} s", flush=True)
+one_b = {}
+for gpus in sorted({1, torch.cuda.device_count()}):
+    out = os.path.join(tmp, f"bigb{gpus}.tsv")
+    best = None
+    for _ in range(2):
+        p = subprocess.run([exe, "-l", lib, "-i", bigb, "-o", out, "--gpus", str(gpus), "--read-shards", str(gpus), "--timing"],
+                           capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        t = json.loads([l for l in p.stderr.splitlines() if l.startswith("{")][-1])
+        best = t if best is None or t["count_s"] < best["count_s"] else best
+    assert p.stderr.count("Calculated Offsets: [Forward(9)]") == 1, p.stderr
+    one_b[gpus] = open(out, "rb").read()
+    print(f"one BGZF sample, gpus={gpus}: count_s {best['count_s']:.3f}  {best['reads'] / best['count_s'] / 1e6:.1f} M reads/s  "
+          f"device_ingest_samples {best['device_ingest_samples']}  shards {best['read_shards_per_sample']}  blocks {best['device_blocks']}",
+          flush=True)
+assert len(set(one_b.values())) == 1, "tables differ between GPU counts"
+print("one BGZF sample: tables identical on 1 and", torch.cuda.device_count(), "GPUs")
