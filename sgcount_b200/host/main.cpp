@@ -360,6 +360,7 @@ struct SampleResult {
   double wait_s = 0, copy_s = 0, submit_s = 0;
   unsigned shards = 1;  // devices the sample's reads were spread over
   uint64_t span_reads = 0, line_reads = 0;  // reads that travelled as span records / whole lines
+  double dev_index_s = 0, dev_create_s = 0, dev_waves_s = 0, dev_finish_s = 0;  // phases of the device ingest
   bool device_ingest = false;               // inflate and record framing ran on the device (BGZF input)
   uint64_t device_blocks = 0;
   std::string host_because;                 // why the device ingest was not used
@@ -486,6 +487,10 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
     why_not = "the guide window does not fit the reads";
     return false;
   }
+  const auto t_start = std::chrono::steady_clock::now();
+  auto seconds = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
   MappedFile file(path);
   if (!file.data) {
     why_not = "cannot map the file";
@@ -497,7 +502,7 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
     why_not = "not BGZF";
     return false;
   }
-  const auto t_start = std::chrono::steady_clock::now();
+  const auto t_indexed = std::chrono::steady_clock::now();
   const size_t n_blocks = isize.size(), n_dev = libs.size();
   // Waves of blocks.  One device thread inflates each block and a wave takes about as long with
   // 300 000 blocks as with 10 000, so a wave is as large as 12 GiB of text allows (variable-length
@@ -548,6 +553,7 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
     check(sgc_counter_create(libs[d], offset.reverse, span_offset, recursion, rc_mode, nullptr, nullptr, &g.lanes[d].c));
     check(sgc_fastq_stream_create(g.lanes[d].c, variable ? 0 : read_len, span_start, span_len, &g.lanes[d].stream));
   }
+  const auto t_created = std::chrono::steady_clock::now();
   std::atomic<size_t> next_wave{0};
   std::atomic<bool> failed{false};
   auto run_lane = [&](Lane& l) {
@@ -577,6 +583,7 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
     run_lane(g.lanes[0]);
     for (auto& t : pool) t.join();
   }
+  const auto t_waved = std::chrono::steady_clock::now();
   uint64_t n_records = 0;
   for (auto& l : g.lanes) {
     if (l.status == SGC_ERR_GZIP || l.status == SGC_ERR_FASTQ_FORMAT) {
@@ -602,7 +609,12 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
   r.device_ingest = true;
   r.device_blocks = n_blocks;
   r.shards = (unsigned)n_lanes;
-  r.submit_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+  const auto t_end = std::chrono::steady_clock::now();
+  r.submit_s = seconds(t_start, t_end);
+  r.dev_index_s = seconds(t_start, t_indexed);
+  r.dev_create_s = seconds(t_indexed, t_created);
+  r.dev_waves_s = seconds(t_created, t_waved);
+  r.dev_finish_s = seconds(t_waved, t_end);
   return true;
 }
 
@@ -910,7 +922,9 @@ int main(int argc, char** argv) {
       unsigned long long span_reads = 0, device_blocks = 0;
       unsigned device_samples = 0;
       std::string host_because;
+      double dev_index_s = 0, dev_create_s = 0, dev_waves_s = 0, dev_finish_s = 0;
       for (const auto& r : results) {
+        dev_index_s += r.dev_index_s, dev_create_s += r.dev_create_s, dev_waves_s += r.dev_waves_s, dev_finish_s += r.dev_finish_s;
         reads += r.total, wait_s += r.wait_s, copy_s += r.copy_s, submit_s += r.submit_s;
         span_reads += r.span_reads;
         device_samples += r.device_ingest;
@@ -920,11 +934,11 @@ int main(int argc, char** argv) {
       }
       fprintf(stderr, "{\"count_s\": %.6f, \"reads\": %llu, \"samples\": %zu, \"sample_workers\": %u, "
               "\"ingest_threads\": %u, \"gpus\": %d, \"read_shards_per_sample\": %u, \"span_reads\": %llu, \"device_ingest_samples\": %u, "
-              "\"device_blocks\": %llu, \"host_ingest_because\": \"%s\", \"wait_inflate_s\": %.6f, "
+              "\"device_blocks\": %llu, \"device_phases_s\": [%.4f, %.4f, %.4f, %.4f], \"host_ingest_because\": \"%s\", \"wait_inflate_s\": %.6f, "
               "\"copy_to_pinned_s\": %.6f, \"submit_sync_s\": %.6f, \"read_inputs_s\": %.3f, "
               "\"device_tables_s\": %.3f, \"offsets_s\": %.3f}\n",
               count_s, reads, n_samples, workers, ingest_threads, gpus, max_shards, span_reads, device_samples, device_blocks,
-              host_because.c_str(), wait_s, copy_s, submit_s, t_inputs,
+              dev_index_s, dev_create_s, dev_waves_s, dev_finish_s, host_because.c_str(), wait_s, copy_s, submit_s, t_inputs,
               t_tables - t_inputs, t_offsets - t_tables);
     }
 
