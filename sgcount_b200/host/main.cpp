@@ -511,9 +511,13 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
   // staging buffers).
   const uint64_t wave_text = variable ? (3ull << 30) : (12ull << 30);
   std::vector<Wave> waves;
-  bool independent = n_dev > 1;
+  // lanes = streams that take waves side by side: one per device, or two on the only device when
+  // the file is large (the copy of one wave's compressed bytes runs under the other's inflate,
+  // and the buffers stay a quarter the size)
+  const size_t lanes_wanted = n_dev > 1 ? n_dev : (n_blocks > 65536 ? 2 : 1);
+  bool independent = lanes_wanted > 1;
   if (independent) {
-    size_t per_wave = std::min<size_t>(262144, std::max<size_t>(16384, n_blocks / (2 * n_dev) + 1));
+    size_t per_wave = n_dev > 1 ? std::min<size_t>(262144, std::max<size_t>(16384, n_blocks / (2 * n_dev) + 1)) : 32768;
     if (const char* e = getenv("SGC_WAVE_BLOCKS"); e && atol(e) > 0) per_wave = (size_t)atol(e);  // tests: many small waves
     independent = plan_waves(file.data, begin, isize, per_wave, wave_text, waves);
     if (!independent) waves.clear();
@@ -531,7 +535,7 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
       a = b;
     }
   }
-  const size_t n_lanes = independent ? std::min(n_dev, waves.size()) : 1;
+  const size_t n_lanes = independent ? std::min(lanes_wanted, waves.size()) : 1;
   struct Lane {
     sgc_counter* c = nullptr;
     sgc_fastq_stream* stream = nullptr;
@@ -550,7 +554,7 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
   } g;
   g.lanes.resize(n_lanes);
   for (size_t d = 0; d < n_lanes; ++d) {
-    check(sgc_counter_create(libs[d], offset.reverse, span_offset, recursion, rc_mode, nullptr, nullptr, &g.lanes[d].c));
+    check(sgc_counter_create(libs[d % n_dev], offset.reverse, span_offset, recursion, rc_mode, nullptr, nullptr, &g.lanes[d].c));
     check(sgc_fastq_stream_create(g.lanes[d].c, variable ? 0 : read_len, span_start, span_len, &g.lanes[d].stream));
   }
   const auto t_created = std::chrono::steady_clock::now();
@@ -608,7 +612,7 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
   r.line_reads = variable ? n_records : 0;
   r.device_ingest = true;
   r.device_blocks = n_blocks;
-  r.shards = (unsigned)n_lanes;
+  r.shards = (unsigned)std::min(n_lanes, n_dev);
   const auto t_end = std::chrono::steady_clock::now();
   r.submit_s = seconds(t_start, t_end);
   r.dev_index_s = seconds(t_start, t_indexed);
