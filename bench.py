@@ -824,6 +824,44 @@ def run_gpu(args):
     p_counts, p_total, p_matched = p_counter.finish()
     del p_counter
 
+    # ---- skew: a tenth of the resident reads rewritten to carry ONE guide.  The reference's fold
+    # (counter.rs:232-235) costs the same whatever the abundances; here the counter's automatic plan
+    # has to make it so (rank 0 reports; every rank does the same work) -----------------------------
+    def timed_launches(c, n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            c.submit_device(d_lines.data_ptr(), n_bytes, n_reads, stride, READ_LEN)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    rows = d_lines[:n_bytes].view(n_reads, stride)
+    hot_row = rows[0].clone()
+    hot_row[OFFSET:OFFSET + K] = torch.from_numpy(lib_arr[12345].copy()).to(dev)
+    mask = torch.rand(n_reads, device=dev) < 0.1
+    rows[mask] = hot_row
+    del mask
+    torch.cuda.synchronize()
+    sk = sg.Counter(library, permuter, sg.Offset.Forward(OFFSET), True, _cabi.RC_BITTRICK, stream=stream)
+    sk_first = timed_launches(sk, 1)  # carries the plan: sample launch, top guides, one synchronisation
+    sk_ms = timed_launches(sk, 5)
+    sk_info = sk.launch_info()
+    sk_counts = sk.finish()[0]
+    plain = sg.Counter(library, permuter, sg.Offset.Forward(OFFSET), True, _cabi.RC_BITTRICK, stream=stream)
+    plain.set_replicas(1)
+    plain_ms = timed_launches(plain, 2)
+    same_skew = bool(np.array_equal(plain.finish()[0] * 3, sk_counts))
+    assert same_skew, "the skew plan changed the counts"
+    skew = {"p_top": 0.1, "ms": sk_ms, "ms_uniform": kernel_ms, "ratio": sk_ms / kernel_ms, "first_launch_ms": sk_first,
+            "replicas": int(sk_info.replicas), "hot_guides": int(sk_info.hot_guides), "ms_without_plan": plain_ms,
+            "top_share": float(sk_counts.max()) / float(max(int(sk_counts.sum()), 1)), "same_counts": same_skew,
+            "what": "10 % of the 50 M resident reads rewritten to carry one guide; default counter (automatic plan) "
+                    "against the uniform sample's kernel time and against the same counter with the plan switched off"}
+    del sk, plain, rows, hot_row
+    sample.fill_device(first, n_reads, d_lines.data_ptr(), device=local_dev, stream=stream)
+    torch.cuda.synchronize()
+
     # ---- end to end: pinned host lines -> sgc_counter_submit -> counts on the host -------------
     lib = _cabi.load()
     host_ptr = ctypes.c_void_p()
@@ -979,6 +1017,7 @@ def run_gpu(args):
                                   "sgc_counter_submit pinned SPAN records, bytes [offset-1, offset+k+1) of every read "
                                   f"in {s_stride}-byte records (sgc_span_geometry), as the CLI's ingest frames them for "
                                   "fixed-length reads; cutting them out of the lines is host framing work, not timed here"},
+            "skew": skew,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
