@@ -236,9 +236,9 @@ def fastq_leg(lib_arr, n_reads: int, with_oracle: bool, gpus: int = 1):
                                        "count_s": tn["count_s"], "read_shards_per_sample": tn.get("read_shards_per_sample"),
                                        "same_table_as_one_gpu": same,
                                        "what": "the same ONE sample with --gpus N --read-shards N: batches dealt round the "
-                                               "devices, sgc_reduce_counts (NCCL) sums the shard vectors.  A correctness leg: "
-                                               "a 16 M-read gzip file is host-bound on one GPU already, and loading NCCL + "
-                                               "ncclCommInitAll (seconds) is inside count_s"}
+                                               "devices, sgc_reduce_counts sums the shard vectors (peer copies: the CLI asks "
+                                               "for NCCL only for inputs of 8 GiB or more, its start-up takes seconds).  A "
+                                               "correctness leg: a 16 M-read gzip file is host-bound on one GPU already"}
                 assert same, "CLI --gpus N table differs from --gpus 1"
         if with_oracle:
             from oracle import oracle as orc
