@@ -505,11 +505,11 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
   const auto t_indexed = std::chrono::steady_clock::now();
   const size_t n_blocks = isize.size(), n_dev = libs.size();
   // Waves of blocks.  One device thread inflates each block and a wave takes about as long with
-  // 300 000 blocks as with 10 000, so a wave is as large as 12 GiB of text allows (variable-length
-  // mode addresses the text with 32-bit offsets: 3 GiB); with several devices, two waves each.
-  // The compressed bytes go to the device straight from the mapping (page cache -> the driver's
-  // staging buffers).
-  const uint64_t wave_text = variable ? (3ull << 30) : (12ull << 30);
+  // 60 000 blocks as with 10 000, so waves are large: up to 65 536 blocks / 4 GiB of text (variable-
+  // length mode addresses the text with 32-bit offsets: 3 GiB), which also bounds the device
+  // memory of a stream to ~6 GB however large the file.  The compressed bytes go to the device
+  // straight from the mapping (page cache -> the driver's staging buffers).
+  const uint64_t wave_text = variable ? (3ull << 30) : (4ull << 30);
   std::vector<Wave> waves;
   // lanes = streams that take waves side by side: one per device, or two on the only device when
   // the file is large (the copy of one wave's compressed bytes runs under the other's inflate,
@@ -517,7 +517,7 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
   const size_t lanes_wanted = n_dev > 1 ? n_dev : (n_blocks > 65536 ? 2 : 1);
   bool independent = lanes_wanted > 1;
   if (independent) {
-    size_t per_wave = n_dev > 1 ? std::min<size_t>(262144, std::max<size_t>(16384, n_blocks / (2 * n_dev) + 1)) : 32768;
+    size_t per_wave = n_dev > 1 ? std::min<size_t>(65536, std::max<size_t>(16384, n_blocks / (2 * n_dev) + 1)) : 32768;
     if (const char* e = getenv("SGC_WAVE_BLOCKS"); e && atol(e) > 0) per_wave = (size_t)atol(e);  // tests: many small waves
     independent = plan_waves(file.data, begin, isize, per_wave, wave_text, waves);
     if (!independent) waves.clear();
@@ -526,7 +526,7 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
     for (size_t a = 0; a < n_blocks;) {
       size_t b = a;
       uint64_t text = 0;
-      while (b < n_blocks && b - a < 262144 && text + isize[b] < wave_text) text += isize[b++];
+      while (b < n_blocks && b - a < 65536 && text + isize[b] < wave_text) text += isize[b++];
       if (b == a) b = a + 1;
       Wave w;
       w.first = a;
