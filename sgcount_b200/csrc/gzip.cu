@@ -297,7 +297,6 @@ struct sgc_fastq_stream {
   std::vector<uint64_t> h_begin, h_outoff;
   uint64_t blocks_total = 0, records_total = 0;
   bool failed = false;
-  double inflate_ms = 0, frame_ms = 0;
 };
 
 namespace {

@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -105,7 +106,7 @@ __global__ void add_state_kernel(unsigned long long* __restrict__ dst, const uns
   if (i < n) dst[i] += src[i];
 }
 
-bool g_force_nccl = false;  // sgc_reduce_prepare has been called: the caller wants NCCL, wait for it
+std::atomic<bool> g_force_nccl{false};  // sgc_reduce_prepare has been called: the caller wants NCCL, wait for it
 
 // state[root] += state of every other leader, through a scratch vector on the root's device
 int peer_reduce(const std::map<int, sgc_counter*>& leader, sgc_counter* root, size_t words) {

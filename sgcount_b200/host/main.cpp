@@ -17,7 +17,6 @@
 #include <unistd.h>
 
 #include <atomic>
-#include <condition_variable>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
