@@ -91,7 +91,7 @@ class GzSource : public ByteSource {
       madvise(p, size_, MADV_SEQUENTIAL);
     }
     threads_ = std::max(1u, threads);
-    if (threads_ > 1 && size_ > (1u << 16)) find_candidates();
+    if (threads_ > 1 && size_ > (1u << 16) && !group_bgzf_blocks()) find_candidates();
     if (cand_.size() <= 1) threads_ = 1;  // a single member: nothing to run in parallel
     if (threads_ > 1 && frame_records) frame_lpr_ = peek_lines_per_record();
     if (threads_ > 1) {
@@ -117,9 +117,10 @@ class GzSource : public ByteSource {
   bool read_more(std::vector<char>& out) override {
     Bytes data;
     bool framed;
+    size_t head;
     SeqBlock block;
     SeqParser::State state;
-    if (!next_member(data, framed, block, state)) return false;
+    if (!next_member(data, framed, head, block, state)) return false;
     if (!data.empty()) {
       const size_t at = out.size();
       out.resize(at + data.size());
@@ -144,11 +145,13 @@ class GzSource : public ByteSource {
   }
 
   // The next member (member-parallel mode) or the next chunk (sequential mode) of decompressed
-  // bytes, possibly none.  `framed`: the worker framed the member's records from a clean state
-  // into `block`, ending in `end_state`.  Returns false at the end of the input.
-  bool next_member(Bytes& raw, bool& framed, SeqBlock& block, SeqParser::State& end_state) {
+  // bytes, possibly none.  `framed`: the worker framed the records of raw[head, size) from a clean
+  // state into `block`, ending in `end_state`; `head` is where it saw the first record start.
+  // Returns false at the end of the input.
+  bool next_member(Bytes& raw, bool& framed, size_t& head, SeqBlock& block, SeqParser::State& end_state) {
     raw.clear();  // keeps its pages: the sequential path refills it, the parallel path recycles it
     framed = false;
+    head = 0;
     if (threads_ > 1 && !sequential_) {
       if (pos_ >= size_) return false;
       // the candidate that starts exactly at pos_
@@ -170,6 +173,7 @@ class GzSource : public ByteSource {
           raw = std::move(job.out);
           framed = job.framed;
           if (framed) {
+            head = job.head;
             block = std::move(job.block);
             end_state = std::move(job.end_state);
           }
@@ -193,8 +197,9 @@ class GzSource : public ByteSource {
     Bytes out;
     size_t end = 0;
     bool ok = false, done = false, taken = false;
-    // record framing of the member, assuming it starts on a record boundary
+    // record framing of the member from its first recognisable record start, out[head]
     bool framed = false;
+    size_t head = 0;
     SeqBlock block;
     SeqParser::State end_state;
   };
@@ -226,6 +231,20 @@ class GzSource : public ByteSource {
       if (p[1] == 0x8b && p[2] == 0x08 && (p[3] & 0xE0) == 0) found.push_back((size_t)(p - data_));
       ++p;
     }
+  }
+  // BGZF: the blocks are 64 KB of text each and say how long they are, so the file is cut into
+  // runs of blocks without looking at a byte of compressed data; one job inflates one run (a few
+  // MB of text, like a member of the files synth writes).  False if the file is anything else.
+  bool group_bgzf_blocks() {
+    std::vector<uint64_t> begin;
+    std::vector<uint32_t> isize;
+    if (!bgzf_index(data_, size_, begin, isize)) return false;
+    const size_t n_blocks = isize.size();
+    const size_t run = std::min<size_t>(64, std::max<size_t>(1, n_blocks / (4 * (size_t)threads_)));
+    for (size_t b = 0; b < n_blocks; b += run) cand_.push_back((size_t)begin[b]);
+    run_text_ = run * 65536 + 1024;
+    grouped_ = true;
+    return true;
   }
   void find_candidates() {
     const size_t last = size_ - 18;  // smallest member: 10 header + 8 trailer
@@ -307,29 +326,51 @@ class GzSource : public ByteSource {
       // next candidate is a coincidence inside compressed data those four bytes are noise: the hint
       // is capped at 64x the compressed size (DEFLATE of sequence data stays far below that)
       const size_t nxt = j + 1 < cand_.size() ? cand_[j + 1] : size_;
-      if (nxt >= cand_[j] + 18) {
+      if (grouped_) {
+        out.reserve(run_text_);
+      } else if (nxt >= cand_[j] + 18) {
         uint32_t isize;
         memcpy(&isize, data_ + nxt - 4, 4);
         const size_t cap = 64 * (nxt - cand_[j]);
         if (isize < (1u << 30)) out.reserve(std::min<size_t>(isize, cap) + 1024);
       }
-      size_t end = 0;
+      size_t end = 0, head = 0;
       bool ok = false, framed = false;
       SeqParser framer;
       try {  // nothing may escape a worker: a failed job sends the consumer down the sequential path
-        ok = inflate_member(cand_[j], out, end);
-        if (ok && frame_lpr_) {
+        if (grouped_) {  // every block of the run, one after the other
+          size_t at = cand_[j];
+          Bytes one;
+          ok = true;
+          while (ok && at < nxt) {
+            ok = inflate_member(at, one, end);
+            if (ok) {
+              out.insert(out.end(), one.begin(), one.end());
+              at = end;
+            }
+          }
+          ok = ok && at == nxt;
+          end = at;
+        } else {
+          ok = inflate_member(cand_[j], out, end);
+        }
+        // the member starts anywhere in a record (BGZF cuts every 64 KB of text): frame from the
+        // first record start on, the consumer finishes the record before it
+        if (ok && frame_lpr_) head = fastx_first_record_start(out.data(), out.size(), frame_lpr_);
+        if (ok && frame_lpr_ && head != SIZE_MAX) {
           framer.st.lines_per_record = frame_lpr_;
           block.lines.reserve(out.size() / 2);
+          const char* const text = out.data() + head;
+          const size_t text_len = out.size() - head;
           try {
             // span records while every read of the sample has had the first one's length
             framer.spans = spans_ && !spans_abandoned_.load(std::memory_order_relaxed) ? spans_ : nullptr;
-            if (!framer.feed(out.data(), out.size(), block)) {
+            if (!framer.feed(text, text_len, block)) {
               spans_abandoned_.store(true, std::memory_order_relaxed);
               framer = SeqParser();
               framer.st.lines_per_record = frame_lpr_;
               block.clear();
-              framer.feed(out.data(), out.size(), block);
+              framer.feed(text, text_len, block);
             }
             framed = true;
           } catch (const std::exception&) {  // the consumer frames these bytes itself and reports
@@ -345,6 +386,7 @@ class GzSource : public ByteSource {
         if (ok) jobs_[j].out = std::move(out);
         if (framed) {
           jobs_[j].framed = true;
+          jobs_[j].head = head;
           jobs_[j].block = std::move(block);
           jobs_[j].end_state = std::move(framer.st);
         }
@@ -398,6 +440,8 @@ class GzSource : public ByteSource {
   std::condition_variable cv_work_, cv_done_;
   size_t next_job_ = 0, consumer_at_ = 0, window_ = 2;
   bool stop_ = false, sequential_ = false;
+  bool grouped_ = false;  // BGZF: a job is the run of blocks between two candidates
+  size_t run_text_ = 0;   // most text a run inflates to
   int frame_lpr_ = 0;  // lines per record the workers frame with; 0 = they do not
   const SpanSpec* spans_ = nullptr;
   std::atomic<bool> spans_abandoned_{false};  // a read of another length was seen: whole lines from here on
@@ -535,11 +579,16 @@ struct SeqBlockReader::Impl {
   std::vector<char> raw_plain;
   bool eof = false;
   SpanSpec spans;  // what the inflate threads frame with (they hold a pointer to it)
+  bool have_spans = false;
+  SeqBlock pending;  // an inflate thread's block, due after the record that was finished before it
+  bool have_pending = false;
+  uint64_t adopted = 0, reframed = 0;
 };
 
 SeqBlockReader::SeqBlockReader(const std::string& path, unsigned inflate_threads, const SpanSpec* spans)
     : impl_(new Impl()) {
   if (spans) impl_->spans = *spans;
+  impl_->have_spans = spans != nullptr;
   if (ends_with(path, ".gz"))
     impl_->gz.reset(new GzSource(path, inflate_threads, /*frame_records=*/true, spans ? &impl_->spans : nullptr));
   else
@@ -551,20 +600,53 @@ bool SeqBlockReader::next(SeqBlock& out) {
   Impl& m = *impl_;
   out.clear();
   if (m.eof) return false;
+  if (m.have_pending) {
+    std::swap(out, m.pending);  // the caller's previous block goes back to the inflate threads
+    m.have_pending = false;
+    m.gz->recycle(Bytes(), std::move(m.pending));
+    m.pending = SeqBlock();
+    return true;
+  }
   bool more;
   if (m.gz) {
     bool framed = false;
+    size_t head = 0;
     SeqBlock block;
     SeqParser::State end_state;
-    more = m.gz->next_member(m.raw, framed, block, end_state);
+    more = m.gz->next_member(m.raw, framed, head, block, end_state);
     if (more) {
-      // the worker framed this member from a clean state: valid iff that is where we are
-      const SeqParser::State& st = m.parser.st;
-      if (framed && st.clean() && (st.lines_per_record == 0 || st.lines_per_record == end_state.lines_per_record)) {
-        std::swap(out, block);  // the caller's previous block goes back to the inflate threads
+      // The worker framed raw[head, size) from a clean state: valid iff that is the state the bytes
+      // before `head` (the end of the record the previous member left open) bring this parser to.
+      bool adopt = false;
+      if (framed) {
+        SeqParser probe;
+        probe.st = m.parser.st;
+        if (head > 0) {
+          probe.spans = block.spans && m.have_spans ? &m.spans : nullptr;  // the same kind of block
+          if (!probe.feed(m.raw.data(), head, out)) {
+            out.clear();
+            probe.st = m.parser.st;
+            probe.spans = nullptr;
+            probe.feed(m.raw.data(), head, out);
+          }
+        }
+        const SeqParser::State& st = probe.st;
+        adopt = st.clean() && (st.lines_per_record == 0 || st.lines_per_record == end_state.lines_per_record);
+      }
+      if (adopt) {
+        if (out.n == 0) {
+          std::swap(out, block);
+        } else {  // this call returns the record that was finished, the next one the worker's block
+          m.pending = std::move(block);
+          block = SeqBlock();
+          m.have_pending = true;
+        }
         m.parser.st = std::move(end_state);
+        ++m.adopted;
       } else {
+        out.clear();
         m.parser.feed(m.raw.data(), m.raw.size(), out);
+        ++m.reframed;
       }
       m.gz->recycle(Bytes(), std::move(block));
     }
@@ -578,6 +660,55 @@ bool SeqBlockReader::next(SeqBlock& out) {
     m.eof = true;
   }
   return true;
+}
+
+uint64_t SeqBlockReader::members_adopted() const { return impl_->adopted; }
+uint64_t SeqBlockReader::members_reframed() const { return impl_->reframed; }
+
+size_t fastx_first_record_start(const char* text, size_t n, int lines_per_record) {
+  if (lines_per_record == 2) {
+    if (n && text[0] == '>') return 0;
+    for (const char* p = text; (p = static_cast<const char*>(memchr(p, '\n', (size_t)(text + n - p)))) != nullptr; ++p)
+      if (p + 1 < text + n && p[1] == '>') return (size_t)(p + 1 - text);
+    return SIZE_MAX;
+  }
+  if (lines_per_record != 4) return SIZE_MAX;
+  // starts of the first lines of the text: a record start is among the first four, a few more
+  // for quality lines that happen to look like headers
+  size_t start[13];
+  int lines = 0;
+  start[lines++] = 0;
+  for (const char* p = text; lines < 13 && (p = static_cast<const char*>(memchr(p, '\n', (size_t)(text + n - p)))) != nullptr; ++p)
+    start[lines++] = (size_t)(p + 1 - text);
+  for (int i = 0; i + 4 < lines; ++i) {
+    if (start[i + 2] >= n) break;
+    if (text[start[i]] == '@' && text[start[i + 2]] == '+' && start[i + 2] - start[i + 1] == start[i + 4] - start[i + 3])
+      return start[i];
+  }
+  return SIZE_MAX;
+}
+
+bool bgzf_index(const uint8_t* d, size_t n, std::vector<uint64_t>& begin, std::vector<uint32_t>& isize) {
+  size_t pos = 0;
+  while (pos < n) {
+    if (n - pos < 28 || d[pos] != 0x1f || d[pos + 1] != 0x8b || d[pos + 2] != 8 || !(d[pos + 3] & 4)) return false;
+    const size_t xlen = d[pos + 10] | ((size_t)d[pos + 11] << 8);
+    if (pos + 12 + xlen > n) return false;
+    size_t bsize = 0;
+    for (size_t at = pos + 12; at + 4 <= pos + 12 + xlen;) {
+      const size_t slen = d[at + 2] | ((size_t)d[at + 3] << 8);
+      if (d[at] == 'B' && d[at + 1] == 'C' && slen == 2 && at + 6 <= pos + 12 + xlen) bsize = (d[at + 4] | ((size_t)d[at + 5] << 8)) + 1;
+      at += 4 + slen;
+    }
+    if (bsize < 28 || pos + bsize > n) return false;
+    begin.push_back(pos);
+    uint32_t sz;
+    memcpy(&sz, d + pos + bsize - 4, 4);
+    isize.push_back(sz);
+    pos += bsize;
+  }
+  begin.push_back(pos);
+  return !isize.empty();
 }
 
 size_t fastq_last_record_end(const char* text, size_t n) {

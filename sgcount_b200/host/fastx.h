@@ -143,9 +143,11 @@ class SeqParser {
 
 // The hot ingest path of count_sample (count.rs:15-45 hands `Counter::new` a record iterator;
 // here the kernels want packed sequence lines): blocks of sequence lines in file order.  For a
-// multi-member gzip file every inflate thread also frames its member's records, assuming the
-// member starts on a record boundary; the consumer checks that assumption against the real
-// framing state and re-frames the member's bytes itself when it does not hold.
+// multi-member gzip file every inflate thread also frames the records of its member (of its run
+// of 64 blocks, for BGZF) from the first record start it can recognise in the text
+// (fastx_first_record_start); the consumer runs the few bytes before that start through the real
+// framing state, takes the thread's block as it is when that state comes out clean, and re-frames
+// the member's bytes itself when it does not.
 class SeqBlockReader {
  public:
   // spans: frame span records instead of whole lines wherever a gzip member's reads all have
@@ -154,11 +156,27 @@ class SeqBlockReader {
   ~SeqBlockReader();
   // Next block (possibly of zero records); false at the end of the input.
   bool next(SeqBlock& out);
+  // gzip members (runs of BGZF blocks) whose framing by an inflate thread was taken as it was /
+  // whose bytes this thread had to frame again
+  uint64_t members_adopted() const;
+  uint64_t members_reframed() const;
 
  private:
   struct Impl;
   std::unique_ptr<Impl> impl_;
 };
+
+// Offset of the first record start that can be recognised in text[0, n), a piece of a FASTA
+// (lines_per_record 2) or FASTQ (4) file that begins anywhere in a record, or SIZE_MAX.  FASTQ: the
+// first line (offset 0 counts as a line start) that begins with '@', whose third line begins with
+// '+' and whose second and fourth lines have the same length (see fastq_last_record_end for why a
+// quality line cannot pass); FASTA: the first line that begins with '>'.  A guess that is wrong
+// (the text began inside a header that contains the marker) is caught by the caller's own state.
+size_t fastx_first_record_start(const char* text, size_t n, int lines_per_record);
+
+// Start offsets of the blocks of a BGZF file (gzip members with a 'BC' extra field that holds the
+// member's size) plus the file size, and every block's ISIZE; false if the bytes are anything else.
+bool bgzf_index(const uint8_t* d, size_t n, std::vector<uint64_t>& begin, std::vector<uint32_t>& isize);
 
 // Offset just past the last complete FASTQ record that can be recognised in text[0, n) without
 // knowing where the text starts in its file (a BGZF block begins anywhere in a record), or

@@ -50,6 +50,20 @@ int main(int argc, char** argv) {
       printf("%llu %llu\n", n, bytes);
       return 0;
     }
+    if (argc > 4 && !strcmp(argv[3], "start")) {  // fastx_first_record_start of the raw bytes of a file: fastx_dump <path> 1 start <2|4>
+      FILE* f = fopen(argv[1], "rb");
+      if (!f) return 2;
+      std::vector<char> data;
+      char buf[1 << 16];
+      for (size_t got; (got = fread(buf, 1, sizeof buf, f)) > 0;) data.insert(data.end(), buf, buf + got);
+      fclose(f);
+      const size_t at = sgh::fastx_first_record_start(data.data(), data.size(), atoi(argv[4]));
+      if (at == SIZE_MAX)
+        printf("none\n");
+      else
+        printf("%zu\n", at);
+      return 0;
+    }
     if (argc > 3 && !strcmp(argv[3], "cut")) {  // fastq_last_record_end of the raw bytes of a file
       FILE* f = fopen(argv[1], "rb");
       if (!f) return 2;
@@ -95,6 +109,7 @@ int main(int argc, char** argv) {
         n += b.n;
       }
       printf("%llu %llx %llu\n", n, h, n_span);
+      fprintf(stderr, "adopted %llu reframed %llu\n", (unsigned long long)br.members_adopted(), (unsigned long long)br.members_reframed());
       return 0;
     }
     if (argc > 3 && !strcmp(argv[3], "blocks")) {  // the packed-sequence-line path of count_sample
@@ -116,6 +131,7 @@ int main(int argc, char** argv) {
         n += b.n;
       }
       printf("%llu %llx\n", n, h);
+      fprintf(stderr, "adopted %llu reframed %llu\n", (unsigned long long)br.members_adopted(), (unsigned long long)br.members_reframed());
       return 0;
     }
     sgh::FastxReader r(argv[1], (unsigned)atoi(argv[2]));

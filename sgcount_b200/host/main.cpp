@@ -359,6 +359,7 @@ struct SampleResult {
   double wait_s = 0, copy_s = 0, submit_s = 0;
   unsigned shards = 1;  // devices the sample's reads were spread over
   uint64_t span_reads = 0, line_reads = 0;  // reads that travelled as span records / whole lines
+  uint64_t members_adopted = 0, members_reframed = 0;  // gzip members framed by their inflate thread / again by the counting thread
   double dev_index_s = 0, dev_create_s = 0, dev_waves_s = 0, dev_finish_s = 0;  // phases of the device ingest
   bool device_ingest = false;               // inflate and record framing ran on the device (BGZF input)
   uint64_t device_blocks = 0;
@@ -386,30 +387,7 @@ struct MappedFile {
   }
 };
 
-// BGZF (bgzip, sequencers): every member carries its own size in a 'BC' extra subfield, so the
-// blocks can be walked without inflating anything.  False if the file is not BGZF throughout.
-bool bgzf_index(const uint8_t* d, size_t n, std::vector<uint64_t>& begin, std::vector<uint32_t>& isize) {
-  size_t pos = 0;
-  while (pos < n) {
-    if (n - pos < 28 || d[pos] != 0x1f || d[pos + 1] != 0x8b || d[pos + 2] != 8 || !(d[pos + 3] & 4)) return false;
-    const size_t xlen = d[pos + 10] | ((size_t)d[pos + 11] << 8);
-    if (pos + 12 + xlen > n) return false;
-    size_t bsize = 0;
-    for (size_t at = pos + 12; at + 4 <= pos + 12 + xlen;) {
-      const size_t slen = d[at + 2] | ((size_t)d[at + 3] << 8);
-      if (d[at] == 'B' && d[at + 1] == 'C' && slen == 2 && at + 6 <= pos + 12 + xlen) bsize = (d[at + 4] | ((size_t)d[at + 5] << 8)) + 1;
-      at += 4 + slen;
-    }
-    if (bsize < 28 || pos + bsize > n) return false;
-    begin.push_back(pos);
-    uint32_t sz;
-    memcpy(&sz, d + pos + bsize - 4, 4);
-    isize.push_back(sz);
-    pos += bsize;
-  }
-  begin.push_back(pos);
-  return !isize.empty();
-}
+using sgh::bgzf_index;  // fastx.h: every BGZF member carries its own size, so the blocks are walked without inflating
 
 // One wave of the device ingest: blocks [first, first + n) of the file, of whose inflated text the
 // first head_skip and the last tail_skip bytes belong to the neighbouring waves.
@@ -719,6 +697,8 @@ SampleResult count_sample(const std::vector<const sgc_library*>& libs, uint32_t 
       r.submit_s += since(t0);
     }
   }
+  r.members_adopted = reader.members_adopted();
+  r.members_reframed = reader.members_reframed();
   auto t0 = Clock::now();
   std::vector<sgc_counter*> shards;
   unsigned devices_used = 0;
@@ -922,7 +902,7 @@ int main(int argc, char** argv) {
       unsigned long long reads = 0;
       double wait_s = 0, copy_s = 0, submit_s = 0;
       unsigned max_shards = 1;
-      unsigned long long span_reads = 0, device_blocks = 0;
+      unsigned long long span_reads = 0, device_blocks = 0, adopted = 0, reframed = 0;
       unsigned device_samples = 0;
       std::string host_because;
       double dev_index_s = 0, dev_create_s = 0, dev_waves_s = 0, dev_finish_s = 0;
@@ -930,6 +910,7 @@ int main(int argc, char** argv) {
         dev_index_s += r.dev_index_s, dev_create_s += r.dev_create_s, dev_waves_s += r.dev_waves_s, dev_finish_s += r.dev_finish_s;
         reads += r.total, wait_s += r.wait_s, copy_s += r.copy_s, submit_s += r.submit_s;
         span_reads += r.span_reads;
+        adopted += r.members_adopted, reframed += r.members_reframed;
         device_samples += r.device_ingest;
         device_blocks += r.device_blocks;
         if (!r.device_ingest && host_because.empty()) host_because = r.host_because;
@@ -937,11 +918,11 @@ int main(int argc, char** argv) {
       }
       fprintf(stderr, "{\"count_s\": %.6f, \"reads\": %llu, \"samples\": %zu, \"sample_workers\": %u, "
               "\"ingest_threads\": %u, \"gpus\": %d, \"read_shards_per_sample\": %u, \"span_reads\": %llu, \"device_ingest_samples\": %u, "
-              "\"device_blocks\": %llu, \"device_phases_s\": [%.4f, %.4f, %.4f, %.4f], \"host_ingest_because\": \"%s\", \"wait_inflate_s\": %.6f, "
+              "\"device_blocks\": %llu, \"device_phases_s\": [%.4f, %.4f, %.4f, %.4f], \"host_ingest_because\": \"%s\", \"members_adopted\": %llu, \"members_reframed\": %llu, \"wait_inflate_s\": %.6f, "
               "\"copy_to_pinned_s\": %.6f, \"submit_sync_s\": %.6f, \"read_inputs_s\": %.3f, "
               "\"device_tables_s\": %.3f, \"offsets_s\": %.3f}\n",
               count_s, reads, n_samples, workers, ingest_threads, gpus, max_shards, span_reads, device_samples, device_blocks,
-              dev_index_s, dev_create_s, dev_waves_s, dev_finish_s, host_because.c_str(), wait_s, copy_s, submit_s, t_inputs,
+              dev_index_s, dev_create_s, dev_waves_s, dev_finish_s, host_because.c_str(), adopted, reframed, wait_s, copy_s, submit_s, t_inputs,
               t_tables - t_inputs, t_offsets - t_tables);
     }
 

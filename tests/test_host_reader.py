@@ -216,3 +216,89 @@ def test_last_record_end_of_a_text_that_starts_anywhere(tmp_path):
         assert rc == 0 and out == (str(inside[-1] - a) if inside else "none"), (trial, a, b)
     (tmp_path / "piece").write_bytes(b"ACGT\nACGT")
     assert dump(tmp_path / "piece", 1, "cut")[1] == "none"
+
+
+def test_first_record_start_of_a_text_that_starts_anywhere(tmp_path):
+    """fastx_first_record_start: where an inflate thread starts framing a member (a run of BGZF
+    blocks) whose text begins anywhere inside a record; quality lines may begin with '@' or '+'."""
+    rng = random.Random(15)
+    recs = []
+    for i in range(300):
+        n = rng.choice([75, 75, 60, 1])
+        qual = bytes(rng.choice(b"@+IF#") for _ in range(n))
+        recs.append(b"@r%d x\n%s\n+\n%s\n" % (i, bytes(rng.choice(b"ACGTN") for _ in range(n)), qual))
+    text = b"".join(recs)
+    starts, at = [], 0
+    for r in recs:
+        starts.append(at)
+        at += len(r)
+    for trial in range(80):
+        a = rng.choice(starts) if trial % 4 == 0 else rng.randrange(0, len(text) - 3000)
+        (tmp_path / "piece").write_bytes(text[a:a + 2500])
+        rc, out, _ = dump(tmp_path / "piece", 1, "start", "4")
+        first = min(s for s in starts if s >= a)
+        # a text that begins inside a header line can look like a record start itself when the rest of the
+        # header begins with '@' (none here); otherwise the answer is the first true record start
+        assert rc == 0 and out == str(first - a), (trial, a, out)
+    fa = b"".join(b">g%d\n%s\n" % (i, b"ACGT" * 5) for i in range(50))
+    for a in (0, 1, 5, 9, 30):
+        (tmp_path / "piece").write_bytes(fa[a:])
+        want = fa.index(b"\n>", a - 1 if a else 0) + 1 - a if a and fa[a:a + 1] != b">" else 0
+        assert dump(tmp_path / "piece", 1, "start", "2")[1] == str(want), a
+    (tmp_path / "piece").write_bytes(b"ACGT\nACGT")
+    assert dump(tmp_path / "piece", 1, "start", "4")[1] == "none"
+    assert dump(tmp_path / "piece", 1, "start", "2")[1] == "none"
+
+
+def write_bgzf(path, text, block=65280, level=1):
+    import struct
+    import zlib
+
+    with open(path, "wb") as f:
+        for at in list(range(0, len(text), block)) + [None]:  # the last one is the empty end-of-file block
+            chunk = b"" if at is None else text[at:at + block]
+            c = zlib.compressobj(level, zlib.DEFLATED, -15)
+            d = c.compress(chunk) + c.flush()
+            f.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(d) + 25) + d
+                    + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+
+
+@pytest.mark.parametrize("kind", ["fastq", "fastq_ragged", "fastq_crlf", "fasta"])
+def test_bgzf_blocks_are_framed_by_the_inflate_threads(tmp_path, kind):
+    """BGZF cuts the text every 64 KB, inside records: the inflate threads take runs of blocks, frame
+    each run from the first record start they recognise, and the consumer only finishes the record
+    before it.  Same sequences as the sequential reader, and (uniform FASTQ, FASTA) no run framed twice."""
+    rng = random.Random(21)
+    n = 60000
+    nl = b"\r\n" if kind == "fastq_crlf" else b"\n"
+    recs = []
+    for i in range(n):
+        length = rng.choice([75, 75, 75, 80, 12, 0]) if kind == "fastq_ragged" else 75
+        recs.append((b"r%d x" % i, bytes(rng.choice(b"ACGTN") for _ in range(length))))
+    if kind == "fasta":
+        text = b"".join(b">" + i + nl + s + nl for i, s in recs)
+    else:
+        text = b"".join(b"@" + i + nl + s + nl + b"+" + nl + bytes(rng.choice(b"@+IF#") for _ in s) + nl for i, s in recs)
+    if kind == "fastq_crlf":
+        recs = [(i, s + b"\r") for i, s in recs]  # the reader hands the line over as it is; the CLI strips the '\r'
+    path = tmp_path / "reads.fx.gz"
+    write_bgzf(path, text)
+    want = fnv(recs, with_ids=False)
+    for threads in (1, 2, 8):
+        rc, out, err = dump(path, threads, "blocks")
+        assert (rc, out) == (0, want), (threads, err)
+        if threads > 1:
+            adopted, reframed = (int(x) for x in err.split()[1::2])
+            assert adopted >= 4, err
+            assert reframed == 0 or kind == "fastq_ragged", err
+    if kind == "fastq":
+        spec = (75, 10, 22, 24)
+        rc, out, err = dump(path, 8, "spans", ",".join(map(str, spec)))
+        n_out, h, n_span = out.split()
+        assert rc == 0 and f"{n_out} {h}" == span_fnv(recs, 75, 10, 22) and int(n_span) == n, (out, err)
+        assert err.split()[3] == "0", err
+    # a block that is not what its header says: the chain breaks, the rest is read sequentially or reported
+    blob = bytearray(path.read_bytes())
+    blob[len(blob) // 2] ^= 0x55
+    (tmp_path / "bad.fx.gz").write_bytes(bytes(blob))
+    assert dump(tmp_path / "bad.fx.gz", 8, "blocks")[0] == 1
