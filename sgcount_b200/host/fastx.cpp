@@ -238,7 +238,7 @@ class GzSource : public ByteSource {
   bool group_bgzf_blocks() {
     std::vector<uint64_t> begin;
     std::vector<uint32_t> isize;
-    if (!bgzf_index(data_, size_, begin, isize)) return false;
+    if (!bgzf_index(data_, size_, begin, isize, threads_)) return false;
     const size_t n_blocks = isize.size();
     const size_t run = std::min<size_t>(64, std::max<size_t>(1, n_blocks / (4 * (size_t)threads_)));
     for (size_t b = 0; b < n_blocks; b += run) cand_.push_back((size_t)begin[b]);
@@ -688,26 +688,112 @@ size_t fastx_first_record_start(const char* text, size_t n, int lines_per_record
   return SIZE_MAX;
 }
 
-bool bgzf_index(const uint8_t* d, size_t n, std::vector<uint64_t>& begin, std::vector<uint32_t>& isize) {
-  size_t pos = 0;
-  while (pos < n) {
-    if (n - pos < 28 || d[pos] != 0x1f || d[pos + 1] != 0x8b || d[pos + 2] != 8 || !(d[pos + 3] & 4)) return false;
-    const size_t xlen = d[pos + 10] | ((size_t)d[pos + 11] << 8);
-    if (pos + 12 + xlen > n) return false;
-    size_t bsize = 0;
-    for (size_t at = pos + 12; at + 4 <= pos + 12 + xlen;) {
-      const size_t slen = d[at + 2] | ((size_t)d[at + 3] << 8);
-      if (d[at] == 'B' && d[at + 1] == 'C' && slen == 2 && at + 6 <= pos + 12 + xlen) bsize = (d[at + 4] | ((size_t)d[at + 5] << 8)) + 1;
-      at += 4 + slen;
-    }
-    if (bsize < 28 || pos + bsize > n) return false;
+namespace {
+
+// Size of the BGZF block whose header starts at d[pos], or 0 if the bytes there are not one.
+inline size_t bgzf_block_size(const uint8_t* d, size_t n, size_t pos) {
+  if (n - pos < 28 || d[pos] != 0x1f || d[pos + 1] != 0x8b || d[pos + 2] != 8 || !(d[pos + 3] & 4)) return 0;
+  const size_t xlen = d[pos + 10] | ((size_t)d[pos + 11] << 8);
+  if (pos + 12 + xlen > n) return 0;
+  size_t bsize = 0;
+  for (size_t at = pos + 12; at + 4 <= pos + 12 + xlen;) {
+    const size_t slen = d[at + 2] | ((size_t)d[at + 3] << 8);
+    if (d[at] == 'B' && d[at + 1] == 'C' && slen == 2 && at + 6 <= pos + 12 + xlen) bsize = (d[at + 4] | ((size_t)d[at + 5] << 8)) + 1;
+    at += 4 + slen;
+  }
+  if (bsize < 28 || pos + bsize > n) return 0;
+  return bsize;
+}
+
+// Walks the blocks from `pos` until a block starts at or past `stop`; returns where it stopped, or
+// SIZE_MAX at bytes that are not a block.
+size_t bgzf_walk(const uint8_t* d, size_t n, size_t pos, size_t stop, std::vector<uint64_t>& begin, std::vector<uint32_t>& isize) {
+  while (pos < stop) {
+    const size_t bsize = bgzf_block_size(d, n, pos);
+    if (!bsize) return SIZE_MAX;
     begin.push_back(pos);
     uint32_t sz;
     memcpy(&sz, d + pos + bsize - 4, 4);
     isize.push_back(sz);
     pos += bsize;
   }
-  begin.push_back(pos);
+  return pos;
+}
+
+}  // namespace
+
+// The walk reads 18 bytes of every block, one block per page or two: it is the page faults of a
+// first pass over the mapping that cost (30 ms per GB).  A large file is therefore walked in parts
+// side by side: every part but the first begins at a GUESS — the first offset past its cut where
+// three block headers follow each other — and the guess is confirmed when the part before it
+// arrives at exactly that offset.  A guess that is not confirmed (compressed bytes that look like
+// three chained headers) sends the whole file through the sequential walk.
+bool bgzf_index(const uint8_t* d, size_t n, std::vector<uint64_t>& begin, std::vector<uint32_t>& isize, unsigned threads,
+                size_t min_parallel_bytes, bool* in_parts) {
+  begin.clear();
+  isize.clear();
+  if (in_parts) *in_parts = false;
+  const unsigned parts = n < min_parallel_bytes ? 1u : std::min(std::max(threads, 1u), 16u);
+  if (parts > 1) {
+    struct Part {
+      size_t start = SIZE_MAX, end = SIZE_MAX;
+      std::vector<uint64_t> begin;
+      std::vector<uint32_t> isize;
+    };
+    std::vector<Part> part(parts);
+    part[0].start = 0;
+    for (unsigned i = 1; i < parts; ++i) {
+      const size_t cut = n / parts * i, limit = std::min(n, cut + (1u << 20));
+      for (size_t pos = cut; pos + 28 <= limit; ++pos) {
+        const void* hit = memchr(d + pos, 0x1f, limit - pos);
+        if (!hit) break;
+        pos = (size_t)(static_cast<const uint8_t*>(hit) - d);
+        if (pos + 28 > limit) break;
+        size_t at = pos;
+        int chained = 0;
+        for (; chained < 3 && at < n; ++chained) {
+          const size_t b = bgzf_block_size(d, n, at);
+          if (!b) break;
+          at += b;
+        }
+        if (chained == 3 || (chained > 0 && at == n)) {
+          part[i].start = pos;
+          break;
+        }
+      }
+      if (part[i].start == SIZE_MAX) break;  // no block start near a cut: not worth guessing further
+    }
+    bool guessed = true;
+    for (unsigned i = 1; i < parts; ++i) guessed &= part[i].start != SIZE_MAX && part[i].start > part[i - 1].start;
+    if (guessed) {
+      std::vector<std::thread> pool;
+      auto walk = [&](unsigned i) {
+        part[i].end = bgzf_walk(d, n, part[i].start, i + 1 < parts ? part[i + 1].start : n, part[i].begin, part[i].isize);
+      };
+      for (unsigned i = 1; i < parts; ++i) pool.emplace_back(walk, i);
+      walk(0);
+      for (auto& t : pool) t.join();
+      bool confirmed = true;
+      for (unsigned i = 0; i < parts; ++i) confirmed &= part[i].end == (i + 1 < parts ? part[i + 1].start : n);
+      if (confirmed) {
+        size_t total = 0;
+        for (auto& p : part) total += p.isize.size();
+        begin.reserve(total + 1);
+        isize.reserve(total);
+        for (auto& p : part) {
+          begin.insert(begin.end(), p.begin.begin(), p.begin.end());
+          isize.insert(isize.end(), p.isize.begin(), p.isize.end());
+        }
+        begin.push_back(n);
+        if (in_parts) *in_parts = true;
+        return !isize.empty();
+      }
+      begin.clear();
+      isize.clear();
+    }
+  }
+  if (bgzf_walk(d, n, 0, n, begin, isize) != n) return false;
+  begin.push_back(n);
   return !isize.empty();
 }
 

@@ -64,6 +64,26 @@ int main(int argc, char** argv) {
         printf("%zu\n", at);
       return 0;
     }
+    if (argc > 4 && !strcmp(argv[3], "bgzfindex")) {  // bgzf_index: fastx_dump <path> <threads> bgzfindex <min bytes for the walk in parts>
+      FILE* f = fopen(argv[1], "rb");
+      if (!f) return 2;
+      std::vector<unsigned char> data;
+      unsigned char buf[1 << 16];
+      for (size_t got; (got = fread(buf, 1, sizeof buf, f)) > 0;) data.insert(data.end(), buf, buf + got);
+      fclose(f);
+      std::vector<uint64_t> begin;
+      std::vector<uint32_t> isize;
+      bool in_parts = false;
+      if (!sgh::bgzf_index(data.data(), data.size(), begin, isize, (unsigned)atoi(argv[2]), (size_t)atoll(argv[4]), &in_parts)) {
+        printf("not bgzf\n");
+        return 0;
+      }
+      unsigned long long h = 1469598103934665603ull;
+      for (uint64_t b : begin) h = (h ^ b) * 1099511628211ull;
+      for (uint32_t s : isize) h = (h ^ s) * 1099511628211ull;
+      printf("%zu %llx %d\n", isize.size(), h, in_parts ? 1 : 0);
+      return 0;
+    }
     if (argc > 3 && !strcmp(argv[3], "cut")) {  // fastq_last_record_end of the raw bytes of a file
       FILE* f = fopen(argv[1], "rb");
       if (!f) return 2;

@@ -475,7 +475,7 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
   }
   std::vector<uint64_t> begin;
   std::vector<uint32_t> isize;
-  if (!bgzf_index(file.data, file.size, begin, isize)) {
+  if (!bgzf_index(file.data, file.size, begin, isize, std::min(8u, std::max(1u, std::thread::hardware_concurrency())))) {
     why_not = "not BGZF";
     return false;
   }

@@ -302,3 +302,51 @@ def test_bgzf_blocks_are_framed_by_the_inflate_threads(tmp_path, kind):
     blob[len(blob) // 2] ^= 0x55
     (tmp_path / "bad.fx.gz").write_bytes(bytes(blob))
     assert dump(tmp_path / "bad.fx.gz", 8, "blocks")[0] == 1
+
+
+def test_bgzf_index_walked_in_parts_equals_the_sequential_walk(tmp_path):
+    """bgzf_index on a large file walks the blocks in parts, side by side, each part from a guessed
+    block start that the part before it must arrive at.  Same index as the sequential walk for every
+    thread count; a planted look-alike (three chained block headers inside one block's stored bytes,
+    right after a cut) is not confirmed and the file is walked sequentially."""
+    import struct
+    import zlib
+
+    rng = random.Random(5)
+    text = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rng.choice(b"ACGT") for _ in range(75)), b"I" * 75) for i in range(40000))
+    path = tmp_path / "reads.fq.gz"
+    write_bgzf(path, text, block=4000)
+    rc, want, _ = dump(path, 1, "bgzfindex", "0")
+    n_blocks, _, in_parts = want.split()
+    assert rc == 0 and int(n_blocks) == len(text) // 4000 + 2 and in_parts == "0"
+    for threads in (2, 3, 8, 16):
+        rc, out, _ = dump(path, threads, "bgzfindex", "0")
+        assert rc == 0 and out.split()[:2] == want.split()[:2] and out.split()[2] == "1", (threads, out)
+    # below the size limit the walk stays sequential
+    assert dump(path, 8, "bgzfindex", str(1 << 30))[1] == want
+
+    # a file whose second half begins, inside a STORED block, with bytes that read as three chained
+    # empty BGZF blocks: the guess of part 2 lands on them, the walk of part 1 steps over them
+    def member(payload_deflate, crc, isize):
+        return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(payload_deflate) + 25) + payload_deflate
+                + struct.pack("<II", crc, isize))
+
+    empty = member(b"\x03\0", 0, 0)
+    fake = empty * 3
+    filler = bytes(rng.choice(b"ACGT") for _ in range(3000))
+    payload = filler + fake + filler  # one stored block: 01 len ~len bytes
+    stored = b"\x01" + struct.pack("<HH", len(payload), len(payload) ^ 0xFFFF) + payload
+    tricky = member(stored, zlib.crc32(payload), len(payload))
+    one = member(zlib.compress(filler, 1)[2:-4], zlib.crc32(filler), len(filler))
+    head = one + one
+    blob = head + tricky + one + empty
+    # the cut of a two-part walk (len / 2) must fall in the filler just before the look-alike
+    at_fake = len(head) + 18 + 5 + len(filler)
+    assert at_fake - 2000 < len(blob) // 2 <= at_fake, (at_fake, len(blob))
+    (tmp_path / "tricky.gz").write_bytes(blob)
+    seq = dump(tmp_path / "tricky.gz", 1, "bgzfindex", "0")[1]
+    par = dump(tmp_path / "tricky.gz", 2, "bgzfindex", "0")[1]
+    assert seq.split()[0] == "5" and par.split()[:2] == seq.split()[:2] and par.split()[2] == "0", (seq, par)
+    # not BGZF at all
+    (tmp_path / "plain.gz").write_bytes(gzip.compress(text[:100000]))
+    assert dump(tmp_path / "plain.gz", 8, "bgzfindex", "0")[1] == "not bgzf"
