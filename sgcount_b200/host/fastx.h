@@ -179,7 +179,7 @@ size_t fastx_first_record_start(const char* text, size_t n, int lines_per_record
 // A file of `min_parallel_bytes` or more is walked by up to `threads` threads side by side (same
 // result; `in_parts` says whether it was).
 bool bgzf_index(const uint8_t* d, size_t n, std::vector<uint64_t>& begin, std::vector<uint32_t>& isize, unsigned threads = 1,
-                size_t min_parallel_bytes = 256u << 20, bool* in_parts = nullptr);
+                size_t min_parallel_bytes = 64u << 20, bool* in_parts = nullptr);
 
 // Offset just past the last complete FASTQ record that can be recognised in text[0, n) without
 // knowing where the text starts in its file (a BGZF block begins anywhere in a record), or

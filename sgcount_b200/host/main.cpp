@@ -323,9 +323,27 @@ struct SampleHead {
   bool any = false;      // the file holds at least one record
   bool fastq = false;    // '@' records (4 lines)
   bool uniform = true;   // every record read so far has first_len bases
+  bool bgzf = false;     // the file begins with a BGZF block (a candidate for the device ingest)
 };
+// Does the file begin with a gzip member that carries a 'BC' extra subfield (BGZF)?
+bool begins_with_bgzf_block(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  uint8_t b[12 + 256];
+  const size_t got = fread(b, 1, sizeof b, f);
+  fclose(f);
+  if (got < 18 || b[0] != 0x1f || b[1] != 0x8b || b[2] != 8 || !(b[3] & 4)) return false;
+  const size_t xlen = b[10] | ((size_t)b[11] << 8);
+  for (size_t at = 12; at + 4 <= std::min(got, 12 + xlen);) {
+    const size_t slen = b[at + 2] | ((size_t)b[at + 3] << 8);
+    if (b[at] == 'B' && b[at + 1] == 'C' && slen == 2) return true;
+    at += 4 + slen;
+  }
+  return false;
+}
 SampleHead read_head(const std::string& path, unsigned long records) {
   SampleHead h;
+  h.bgzf = begins_with_bgzf_block(path);
   sgh::FastxReader reader(path);
   const char *id, *seq;
   size_t id_len, seq_len;
@@ -839,13 +857,22 @@ int main(int argc, char** argv) {
     std::string first_error;
     std::vector<uint32_t> first_len(n_samples);
     std::vector<char> head_uniform(n_samples, 0), head_fastq(n_samples, 0);  // 4-line FASTQ? head reads of one length?
+    bool all_for_the_device = !args.host_inflate;
     for (size_t i = 0; i < n_samples; ++i) {
       first_len[i] = (uint32_t)heads[i].first_len;
       head_fastq[i] = heads[i].fastq;
       head_uniform[i] = heads[i].fastq && heads[i].uniform;
+      all_for_the_device &= heads[i].fastq && heads[i].bgzf;
     }
     heads.clear();
-    const unsigned workers = (unsigned)std::min<size_t>(std::max(args.threads, (unsigned)gpus), n_samples);
+    // Samples in flight: the reference's -t (count.rs:117-136), at least one per device — and, when
+    // every sample is BGZF and so inflated, framed and counted on its device, four per device
+    // whatever -t says: a sample's host thread only hands blocks over, and the device's inflate of
+    // one sample is bound by the latency of its longest block, not by throughput (a wave takes about
+    // as long with 10 000 blocks as with 60 000), so samples side by side cost next to nothing.
+    constexpr unsigned kDeviceSamplesInFlight = 4;
+    const unsigned wanted = std::max(args.threads, (unsigned)gpus * (all_for_the_device && per_sample == 1 ? kDeviceSamplesInFlight : 1u));
+    const unsigned workers = (unsigned)std::min<size_t>(wanted, n_samples);
     const unsigned ingest_threads =
         args.ingest_threads ? args.ingest_threads : std::max(1u, std::thread::hardware_concurrency() / workers);
     auto work = [&]() {
