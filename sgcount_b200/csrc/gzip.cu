@@ -23,6 +23,8 @@
 // takes this path (the head of the sample, which the host reads for the offset detector, says so);
 // anything irregular is reported and the caller counts the sample through the host path instead.
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "inflate_core.h"
@@ -265,14 +267,63 @@ __global__ void tail_restore_kernel(uint8_t* __restrict__ text, const StreamStat
     text[kHeadroom - tail + i] = tail_buf[i];
 }
 
+// Device scratch of the ingest streams comes from one memory pool per device whose unused memory stays
+// cached, through the stream-ordered allocator.  cudaFree waits for ALL work on the device and cudaMalloc
+// queues up behind it: with several samples in flight on one device (the CLI runs four) every sample that
+// finished — a dozen buffers to release — stalled the others' next allocation until their kernels had
+// drained, and the samples ran one after the other.  cudaFreeAsync is ordered on the stream only.
+struct ScratchPools {
+  std::mutex mu;
+  std::map<int, cudaMemPool_t> pool;  // NULL: the device has no memory pools (cudaMalloc / cudaFree instead)
+};
+cudaMemPool_t scratch_pool(int device) {
+  static ScratchPools pools;
+  std::lock_guard<std::mutex> lk(pools.mu);
+  auto it = pools.pool.find(device);
+  if (it != pools.pool.end()) return it->second;
+  cudaMemPool_t pool = nullptr;
+  int supported = 0;
+  if (cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && supported) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+      uint64_t keep = 8ull << 30;  // up to 8 GiB of freed memory stay with the pool for the next wave / sample
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      pool = nullptr;
+      cudaGetLastError();
+    }
+  }
+  pools.pool[device] = pool;
+  return pool;
+}
+int scratch_alloc(void** p, size_t bytes, cudaMemPool_t pool, cudaStream_t stream) {
+  if (pool)
+    SGC_CUDA_TRY(cudaMallocFromPoolAsync(p, bytes, pool, stream));
+  else
+    SGC_CUDA_TRY(cudaMalloc(p, bytes));
+  return SGC_OK;
+}
+void scratch_free(void* p, cudaMemPool_t pool, cudaStream_t stream) {
+  if (!p) return;
+  if (pool)
+    cudaFreeAsync(p, stream);
+  else
+    cudaFree(p);
+}
+
 template <typename T>
-int grow(T** p, size_t* cap, size_t need) {
+int grow(T** p, size_t* cap, size_t need, cudaMemPool_t pool, cudaStream_t stream) {
   if (need <= *cap) return SGC_OK;
-  cudaFree(*p);
+  scratch_free(*p, pool, stream);  // (stream order: the kernels that still read it come first)
   *p = nullptr;
   *cap = 0;
   const size_t want = need + need / 4;
-  SGC_CUDA_TRY(cudaMalloc(p, want * sizeof(T)));
+  int rc = scratch_alloc(reinterpret_cast<void**>(p), want * sizeof(T), pool, stream);
+  if (rc) return rc;
   *cap = want;
   return SGC_OK;
 }
@@ -287,6 +338,7 @@ struct sgc_fastq_stream {
   int device = 0;
   uint32_t read_len = 0, span_start = 0, span_len = 0, span_stride = 0;
   cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;  // scratch_pool(device)
   StreamState* d_state = nullptr;
   uint8_t *d_gz = nullptr, *d_text = nullptr, *d_spans = nullptr, *d_tail = nullptr;
   uint32_t *d_seq_start = nullptr, *d_seq_end = nullptr;  // variable-length mode
@@ -324,9 +376,9 @@ int stream_error(sgc_fastq_stream* s, const StreamState& st, uint64_t first_bloc
 // frames and counts the region made of the carried tail and n_text fresh bytes at d_text + kHeadroom
 int frame_and_count(sgc_fastq_stream* s, uint64_t n_text, uint64_t first_block) {
   const uint32_t n_chunks = (uint32_t)(((uint64_t)kHeadroom + n_text + kChunk - 1) / kChunk);
-  int rc = grow(&s->d_counts, &s->counts_cap, (size_t)n_chunks + 1);
-  if (rc == SGC_OK) rc = grow(&s->d_first, &s->first_cap, (size_t)n_chunks + 1);
-  if (rc == SGC_OK) rc = grow(&s->d_sums, &s->sums_cap, (size_t)n_chunks / 2048 + 2);
+  int rc = grow(&s->d_counts, &s->counts_cap, (size_t)n_chunks + 1, s->pool, s->stream);
+  if (rc == SGC_OK) rc = grow(&s->d_first, &s->first_cap, (size_t)n_chunks + 1, s->pool, s->stream);
+  if (rc == SGC_OK) rc = grow(&s->d_sums, &s->sums_cap, (size_t)n_chunks / 2048 + 2, s->pool, s->stream);
   if (rc) return rc;
   // the carried bytes go in front of the fresh text (they are kept in d_tail: d_text may have moved)
   tail_restore_kernel<<<8, 256, 0, s->stream>>>(s->d_text, s->d_state, s->d_tail);
@@ -342,10 +394,10 @@ int frame_and_count(sgc_fastq_stream* s, uint64_t n_text, uint64_t first_block) 
   if (pre.bad_block != 0xFFFFFFFFu) return stream_error(s, pre, first_block);
   const size_t max_records = (size_t)pre.records + 1;
   if (s->read_len) {
-    rc = grow(&s->d_spans, &s->spans_cap, max_records * s->span_stride + 256);
+    rc = grow(&s->d_spans, &s->spans_cap, max_records * s->span_stride + 256, s->pool, s->stream);
   } else {
-    rc = grow(&s->d_seq_start, &s->seq_cap_a, max_records);
-    if (rc == SGC_OK) rc = grow(&s->d_seq_end, &s->seq_cap_b, max_records);
+    rc = grow(&s->d_seq_start, &s->seq_cap_a, max_records, s->pool, s->stream);
+    if (rc == SGC_OK) rc = grow(&s->d_seq_end, &s->seq_cap_b, max_records, s->pool, s->stream);
   }
   if (rc) return rc;
   span_extract_kernel<<<n_chunks, kChunkThreads, 0, s->stream>>>(s->d_text, n_text, s->d_state, s->d_first, s->read_len,
@@ -381,18 +433,9 @@ void sgc::fastq_stream_release(sgc_fastq_stream* s) {
   list.erase(std::remove(list.begin(), list.end(), s), list.end());
   s->counter = nullptr;
   s->failed = true;  // nothing more can be submitted
-  cudaFree(s->d_state);
-  cudaFree(s->d_gz);
-  cudaFree(s->d_text);
-  cudaFree(s->d_spans);
-  cudaFree(s->d_tail);
-  cudaFree(s->d_seq_start);
-  cudaFree(s->d_seq_end);
-  cudaFree(s->d_begin);
-  cudaFree(s->d_outoff);
-  cudaFree(s->d_counts);
-  cudaFree(s->d_first);
-  cudaFree(s->d_sums);
+  for (void* p : {(void*)s->d_state, (void*)s->d_gz, (void*)s->d_text, (void*)s->d_spans, (void*)s->d_tail, (void*)s->d_seq_start,
+                  (void*)s->d_seq_end, (void*)s->d_begin, (void*)s->d_outoff, (void*)s->d_counts, (void*)s->d_first, (void*)s->d_sums})
+    scratch_free(p, s->pool, s->stream);
   s->d_state = nullptr;
   s->d_gz = s->d_text = s->d_spans = s->d_tail = nullptr;
   s->d_seq_start = s->d_seq_end = nullptr;
@@ -417,14 +460,15 @@ int sgc_fastq_stream_create(sgc_counter* counter, uint32_t read_len, uint32_t sp
   s->span_stride = (span_len + 7u) & ~7u;
   s->device = counter->lib->device;
   s->stream = counter->stream;  // one stream: the count of a wave follows its framing
+  s->pool = scratch_pool(s->device);
   struct Cleanup {
     sgc_fastq_stream* s;
     ~Cleanup() {
       if (s) sgc_fastq_stream_destroy(s);
     }
   } cleanup{s};
-  SGC_CUDA_TRY(cudaMalloc(&s->d_state, sizeof(StreamState)));
-  SGC_CUDA_TRY(cudaMalloc(&s->d_tail, kHeadroom));
+  if (int rc = scratch_alloc(reinterpret_cast<void**>(&s->d_state), sizeof(StreamState), s->pool, s->stream)) return rc;
+  if (int rc = scratch_alloc(reinterpret_cast<void**>(&s->d_tail), kHeadroom, s->pool, s->stream)) return rc;
   StreamState st0{};
   st0.bad_block = 0xFFFFFFFFu;
   SGC_CUDA_TRY(cudaMemcpyAsync(s->d_state, &st0, sizeof st0, cudaMemcpyHostToDevice, s->stream));
@@ -467,10 +511,10 @@ int sgc_fastq_stream_submit_range(sgc_fastq_stream* s, const uint8_t* gz, const 
   if (s->read_len == 0 && n_text >= (1ull << 32) - 2 * kHeadroom)
     return set_error(SGC_ERR_BATCH_TOO_LARGE, "in variable-length mode a wave of blocks must inflate to less than 4 GiB");
   const uint64_t gz_bytes = block_begin[n_blocks] - block_begin[0];
-  int rc = grow(&s->d_gz, &s->gz_cap, (size_t)gz_bytes + 64);  // the decoder prefetches up to 47 bytes past a block
-  if (rc == SGC_OK) rc = grow(&s->d_text, &s->text_cap, (size_t)kHeadroom + n_text + 64);
-  if (rc == SGC_OK) rc = grow(&s->d_begin, &s->begin_cap, (size_t)n_blocks + 1);
-  if (rc == SGC_OK) rc = grow(&s->d_outoff, &s->outoff_cap, (size_t)n_blocks + 1);
+  int rc = grow(&s->d_gz, &s->gz_cap, (size_t)gz_bytes + 64, s->pool, s->stream);  // the decoder prefetches up to 47 bytes past a block
+  if (rc == SGC_OK) rc = grow(&s->d_text, &s->text_cap, (size_t)kHeadroom + n_text + 64, s->pool, s->stream);
+  if (rc == SGC_OK) rc = grow(&s->d_begin, &s->begin_cap, (size_t)n_blocks + 1, s->pool, s->stream);
+  if (rc == SGC_OK) rc = grow(&s->d_outoff, &s->outoff_cap, (size_t)n_blocks + 1, s->pool, s->stream);
   if (rc) return rc;
   SGC_CUDA_TRY(cudaMemcpyAsync(s->d_gz, gz + block_begin[0], gz_bytes, cudaMemcpyHostToDevice, s->stream));
   SGC_CUDA_TRY(cudaMemcpyAsync(s->d_begin, block_begin, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, s->stream));

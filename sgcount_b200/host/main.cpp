@@ -853,8 +853,10 @@ int main(int argc, char** argv) {
     // the reference's only fan-out: samples in parallel (count.rs:117-136)
     std::vector<SampleResult> results(n_samples);
     std::atomic<size_t> next{0};
-    std::mutex err_mu;
+    std::mutex err_mu, print_mu;
     std::string first_error;
+    std::vector<char> finished(n_samples, 0);
+    size_t next_to_print = 0;
     std::vector<uint32_t> first_len(n_samples);
     std::vector<char> head_uniform(n_samples, 0), head_fastq(n_samples, 0);  // 4-line FASTQ? head reads of one length?
     bool all_for_the_device = !args.host_inflate;
@@ -907,10 +909,16 @@ int main(int argc, char** argv) {
             results[s].host_because = why_not;
           }
           if (!args.quiet) {
-            const SampleResult& r = results[s];
-            fprintf(stderr, "Finished: %s; Fraction mapped: %.3f [%llu / %llu]\n", names[s].c_str(),
-                    r.total ? (double)r.matched / (double)r.total : 0.0 / 0.0, (unsigned long long)r.matched,
-                    (unsigned long long)r.total);  // count.rs:36-42
+            // count.rs:36-42.  The lines come out in sample order, as they do from the reference's
+            // default single thread, however many samples are in flight here.
+            std::lock_guard<std::mutex> lk(print_mu);
+            finished[s] = 1;
+            for (; next_to_print < n_samples && finished[next_to_print]; ++next_to_print) {
+              const SampleResult& r = results[next_to_print];
+              fprintf(stderr, "Finished: %s; Fraction mapped: %.3f [%llu / %llu]\n", names[next_to_print].c_str(),
+                      r.total ? (double)r.matched / (double)r.total : 0.0 / 0.0, (unsigned long long)r.matched,
+                      (unsigned long long)r.total);
+            }
           }
         } catch (const std::exception& e) {
           std::lock_guard<std::mutex> lk(err_mu);
