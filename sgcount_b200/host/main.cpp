@@ -384,22 +384,6 @@ struct SampleResult {
   std::string host_because;                 // why the device ingest was not used
 };
 
-// Counters of finished device-ingest samples, destroyed together once every sample is done:
-// sgc_counter_destroy frees device memory, and cudaFree waits for ALL work on the device — with
-// several samples in flight on one device every finished sample would stall the others.
-std::mutex g_retired_mu;
-std::vector<sgc_counter*> g_retired;
-void retire_counter(sgc_counter* c) {
-  if (!c) return;
-  std::lock_guard<std::mutex> lk(g_retired_mu);
-  g_retired.push_back(c);
-}
-void destroy_retired_counters() {
-  std::lock_guard<std::mutex> lk(g_retired_mu);
-  for (sgc_counter* c : g_retired) sgc_counter_destroy(c);
-  g_retired.clear();
-}
-
 // ---- device ingest: BGZF blocks inflated, framed and counted on the GPU (sgc_fastq_stream_*) ----
 // A read-only mapping of a file.
 struct MappedFile {
@@ -558,8 +542,8 @@ bool count_sample_on_device(const std::vector<const sgc_library*>& libs, uint32_
     std::vector<Lane> lanes;
     ~Guard() {
       for (auto& l : lanes) {
-        sgc_fastq_stream_destroy(l.stream);  // (its scratch goes back to the device's pool: no synchronisation)
-        retire_counter(l.c);
+        sgc_fastq_stream_destroy(l.stream);
+        sgc_counter_destroy(l.c);
       }
     }
   } g;
@@ -947,10 +931,9 @@ int main(int argc, char** argv) {
     for (unsigned t = 1; t < workers; ++t) pool.emplace_back(work);
     work();
     for (auto& t : pool) t.join();
-    destroy_retired_counters();
-    const double count_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_count0).count();
     if (!first_error.empty()) fail("%s", first_error.c_str());
     if (args.timing) {
+      const double count_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_count0).count();
       unsigned long long reads = 0;
       double wait_s = 0, copy_s = 0, submit_s = 0;
       unsigned max_shards = 1;
