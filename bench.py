@@ -153,7 +153,7 @@ def run_cli(exe, lib_path, fq_paths, extra, out_path):
     import subprocess
 
     best = None
-    for _ in range(2):  # the first run pages the file in
+    for _ in range(3):  # the first run pages the file in; a box of this pool varies from run to run (profiles/r2e_cli_ab.txt)
         t0 = time.perf_counter()
         p = subprocess.run([exe, "-l", lib_path, "-i", *fq_paths, "-q", "-o", out_path, "--timing", *extra],
                            capture_output=True, text=True, timeout=900)
