@@ -239,7 +239,11 @@ int sgc_reduce_prepare(const int* devices, int n_devices);
  * ISIZE field.  One call is one wave: it should carry thousands of blocks (one device thread
  * each; the decode of a block is a long serial chain, so a wave takes about as long
  * whether it holds ten thousand blocks or three hundred thousand) and must inflate to less than 64 GiB.  Blocks may end anywhere in a record.
- * finish: end of the input; *n_records = records counted. */
+ * finish: end of the input; *n_records = records counted.
+ * Device memory: a stream's scratch (compressed bytes, text, span records) comes from one memory
+ * pool per device through the stream-ordered allocator and goes back to it when the stream is
+ * destroyed, without a device-wide synchronisation; the pool keeps up to 8 GiB of freed memory
+ * for the next stream and hands the rest back to the driver at the next synchronisation. */
 typedef struct sgc_fastq_stream sgc_fastq_stream;
 int sgc_fastq_stream_create(sgc_counter* counter, uint32_t read_len, uint32_t span_start, uint32_t span_len,
                             sgc_fastq_stream** out);
