@@ -350,3 +350,37 @@ def test_bgzf_index_walked_in_parts_equals_the_sequential_walk(tmp_path):
     # not BGZF at all
     (tmp_path / "plain.gz").write_bytes(gzip.compress(text[:100000]))
     assert dump(tmp_path / "plain.gz", 8, "bgzfindex", "0")[1] == "not bgzf"
+
+
+def test_bgzf_index_in_parts_on_random_files(tmp_path):
+    """Random BGZF files — stored and compressed blocks of every size, payloads with chained block
+    headers planted in them, now and then trailing bytes that are no block — give the same index
+    (or the same refusal) whatever the number of parts."""
+    import struct
+    import zlib
+
+    def member(payload, level):
+        if level < 0:  # a stored block keeps planted bytes as they are
+            body = b"\x01" + struct.pack("<HH", len(payload), len(payload) ^ 0xFFFF) + payload
+        else:
+            c = zlib.compressobj(level, zlib.DEFLATED, -15)
+            body = c.compress(payload) + c.flush()
+        return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(body) + 25) + body
+                + struct.pack("<II", zlib.crc32(payload), len(payload)))
+
+    fake = member(b"", 1)
+    for seed in range(40):
+        rng = random.Random(seed)
+        blocks = []
+        for _ in range(rng.randint(1, 40)):
+            payload = bytes(rng.choice(b"ACGT\n@+I") for _ in range(rng.choice([0, 10, 500, 3000, 20000])))
+            if rng.random() < 0.4:
+                at = rng.randint(0, len(payload))
+                payload = payload[:at] + fake * rng.randint(1, 4) + payload[at:]
+            blocks.append(member(payload, rng.choice([-1, -1, 1, 6])))
+        blob = b"".join(blocks) + (b"garbage" if rng.random() < 0.1 else b"")
+        path = tmp_path / "f.gz"
+        path.write_bytes(blob)
+        want = dump(path, 1, "bgzfindex", "0")[1].split()[:2]
+        for threads in (2, 5, 16):
+            assert dump(path, threads, "bgzfindex", "0")[1].split()[:2] == want, (seed, threads)
