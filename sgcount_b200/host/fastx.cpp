@@ -536,6 +536,64 @@ bool SeqParser::line(const char* p, size_t len, SeqBlock& out) {
   return true;
 }
 
+// Whole FASTQ records at a record start: as many as lie complete in [p, end), framed without the
+// per-line state machine and written through a pointer into space reserved once (the same four
+// newline searches per record, the same bytes out as line() produces; the record that is cut by
+// `end`, FASTA, and the first line of a file are left to the line-by-line code).  Returns where it
+// stopped; `ok` = false at a sequence of another length in span mode (see feed()).
+const char* SeqParser::fastq_records(const char* p, const char* end, SeqBlock& out, bool& ok) {
+  ok = true;
+  const size_t room = (size_t)(end - p);
+  const size_t at = out.lines.size();
+  // an upper bound of what the records in [p, end) can add
+  const size_t most = spans ? (room / ((size_t)spans->read_len + 4) + 1) * spans->stride : room + 1;
+  out.lines.resize(at + most);  // (BigAlloc default-initialises: no byte is touched here)
+  char* w = out.lines.data() + at;
+  auto newline = [end](const char* from) { return static_cast<const char*>(memchr(from, '\n', (size_t)(end - from))); };
+  while (p < end) {
+    const char* h = newline(p);
+    if (!h) break;
+    const char* seq = h + 1;
+    if (seq >= end) break;
+    const char* s_end = newline(seq);
+    if (!s_end || s_end + 1 >= end) break;
+    // (the usual third line is "+" alone: its newline is found without a search)
+    const char* plus_end = s_end + 2 < end && s_end[1] == '+' && s_end[2] == '\n' ? s_end + 2 : newline(s_end + 1);
+    if (!plus_end || plus_end + 1 >= end) break;
+    const char* q_end = newline(plus_end + 1);
+    if (!q_end) break;
+    const size_t l = (size_t)(s_end - seq);
+    if (spans) {
+      if (l != spans->read_len) {
+        ok = false;
+        break;
+      }
+      if (out.n == 0) {
+        out.spans = true;
+        out.first_len = spans->len;
+        out.stride = spans->stride;
+      }
+      memcpy(w, seq + spans->start, spans->len);
+      w += spans->stride;
+    } else {
+      if (l >= 0xFFFFFFFFull) throw FastxError("a sequence line of 4 GiB or more");
+      if (out.n == 0) {
+        out.first_len = (uint32_t)l;
+        out.stride = (uint32_t)l + 1;
+      } else {
+        out.uniform &= l == out.first_len;
+      }
+      memcpy(w, seq, l + 1);  // the sequence and its newline
+      w += l + 1;
+      out.len.push_back((uint32_t)l);
+    }
+    ++out.n;
+    p = q_end + 1;
+  }
+  out.lines.resize((size_t)(w - out.lines.data()));
+  return p;
+}
+
 bool SeqParser::feed(const char* data, size_t len, SeqBlock& out) {
   const char* p = data;
   const char* const end = data + len;
@@ -551,6 +609,12 @@ bool SeqParser::feed(const char* data, size_t len, SeqBlock& out) {
     p = nl + 1;
   }
   while (p < end) {
+    if (st.lines_per_record == 4 && st.phase == 0) {  // at a FASTQ record start: whole records at once
+      bool ok;
+      p = fastq_records(p, end, out, ok);
+      if (!ok) return false;
+      if (p >= end) break;
+    }
     const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
     if (!nl) {
       st.carry.assign(p, end);

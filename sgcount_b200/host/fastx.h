@@ -139,6 +139,7 @@ class SeqParser {
 
  private:
   bool line(const char* p, size_t len, SeqBlock& out);
+  const char* fastq_records(const char* p, const char* end, SeqBlock& out, bool& ok);
 };
 
 // The hot ingest path of count_sample (count.rs:15-45 hands `Counter::new` a record iterator;
